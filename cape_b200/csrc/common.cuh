@@ -1,0 +1,84 @@
+// Internal helpers shared by the kernels of libcape_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/cape_b200.h"
+
+namespace cape {
+
+void set_error(const std::string& msg);
+
+#define CAPE_CHECK_CUDA(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      cape::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+      return -2;                                                                           \
+    }                                                                                      \
+  } while (0)
+
+#define CAPE_REQUIRE(cond, msg)                                                            \
+  do {                                                                                     \
+    if (!(cond)) {                                                                         \
+      cape::set_error(std::string("invalid argument: ") + (msg));                          \
+      return -1;                                                                           \
+    }                                                                                      \
+  } while (0)
+
+struct EllOp {
+  int rows_out = 0, rows_in = 0, width = 0;
+  int32_t* idx = nullptr;   // device [rows_out, width], -1 = empty slot
+  float* w = nullptr;       // device [rows_out, width]
+  float* rowsum = nullptr;  // device [rows_out]
+};
+
+}  // namespace cape
+
+struct cape_topology {
+  int device = 0;
+  int sm_count = 148;
+  std::vector<cape::EllOp> ops;
+  void* workspace = nullptr;
+  int64_t workspace_bytes = 0;
+};
+
+namespace cape {
+
+// device-side view of an operator (identity when idx == nullptr)
+struct OpView {
+  const int32_t* idx;
+  const float* w;
+  const float* rowsum;
+  int width;
+};
+
+inline int get_op(const cape_topology* t, int op, int rows_out, int rows_in, OpView* v) {
+  if (op < 0) {
+    if (rows_in != rows_out) {
+      set_error("identity operator needs src_rows == rows_out");
+      return -1;
+    }
+    v->idx = nullptr; v->w = nullptr; v->rowsum = nullptr; v->width = 0;
+    return 0;
+  }
+  if (op >= (int)t->ops.size()) { set_error("operator id out of range"); return -1; }
+  const EllOp& o = t->ops[op];
+  if (o.rows_out != rows_out || o.rows_in != rows_in) {
+    set_error("operator shape mismatch: op is [" + std::to_string(o.rows_out) + "x" + std::to_string(o.rows_in) +
+              "], call wants [" + std::to_string(rows_out) + "x" + std::to_string(rows_in) + "]");
+    return -1;
+  }
+  v->idx = o.idx; v->w = o.w; v->rowsum = o.rowsum; v->width = o.width;
+  return 0;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void fma4(float4& a, float s, const float4& x) {
+  a.x = fmaf(s, x.x, a.x); a.y = fmaf(s, x.y, a.y); a.z = fmaf(s, x.z, a.z); a.w = fmaf(s, x.w, a.w);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace cape

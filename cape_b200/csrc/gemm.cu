@@ -1,0 +1,204 @@
+// Strided fp32 GEMM with deterministic split-K: the dense layers of CAPE
+// (tf.layers.dense at lib/models.py:496,506,510,557,560,582) and their gradients.
+// These are weight-bandwidth bound (2 x 55168x64 + 128x55168 fp32 = 56.7 MB read once per pass at batch 64),
+// so the contraction stays on the fp32 pipe; split-K over the 55168-long reduction fills the 148 SMs.
+#include "common.cuh"
+
+namespace cape {
+
+constexpr int G_BM = 64, G_BN = 64, G_BK = 16, G_STRIDE = 68;
+
+struct GemmParams {
+  int M, N, K;
+  const float* a; long long a_rs, a_cs;
+  const float* b; long long b_rs, b_cs;
+  float* c; long long c_rs;
+  const float* bias;
+  int act;
+  float leaky, alpha, beta;
+  int nsplit, k_per_split;
+  float* ws;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float leaky) {
+  if (act == CAPE_ACT_LEAKY) return v > 0.f ? v : leaky * v;
+  if (act == CAPE_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+__device__ __forceinline__ void gemm_load(const GemmParams& p, int m0, int n0, int k0, int kend, int tid,
+                                          float (&ra)[4], float (&rb)[4]) {
+  if (p.a_cs == 1) {
+    const int kk = tid & 15, mb = tid >> 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + mb + 16 * i, k = k0 + kk;
+      ra[i] = (m < p.M && k < kend) ? __ldg(p.a + (size_t)m * p.a_rs + k) : 0.f;
+    }
+  } else {
+    const int mm = tid & 63, kb = tid >> 6;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + mm, k = k0 + kb + 4 * i;
+      ra[i] = (m < p.M && k < kend) ? __ldg(p.a + (size_t)m * p.a_rs + (size_t)k * p.a_cs) : 0.f;
+    }
+  }
+  if (p.b_cs == 1) {
+    const int nn = tid & 63, kb = tid >> 6;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + nn, k = k0 + kb + 4 * i;
+      rb[i] = (n < p.N && k < kend) ? __ldg(p.b + (size_t)k * p.b_rs + n) : 0.f;
+    }
+  } else {
+    const int kk = tid & 15, nb = tid >> 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + nb + 16 * i, k = k0 + kk;
+      rb[i] = (n < p.N && k < kend) ? __ldg(p.b + (size_t)k * p.b_rs + (size_t)n * p.b_cs) : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void gemm_store(const GemmParams& p, int tid, const float (&ra)[4], const float (&rb)[4],
+                                           float* As, float* Bs) {
+  if (p.a_cs == 1) {
+    const int kk = tid & 15, mb = tid >> 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[kk * G_STRIDE + mb + 16 * i] = ra[i];
+  } else {
+    const int mm = tid & 63, kb = tid >> 6;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[(kb + 4 * i) * G_STRIDE + mm] = ra[i];
+  }
+  if (p.b_cs == 1) {
+    const int nn = tid & 63, kb = tid >> 6;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Bs[(kb + 4 * i) * G_STRIDE + nn] = rb[i];
+  } else {
+    const int kk = tid & 15, nb = tid >> 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Bs[kk * G_STRIDE + nb + 16 * i] = rb[i];
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) gemm_kernel(const __grid_constant__ GemmParams p) {
+  __shared__ __align__(16) float As[G_BK * G_STRIDE];
+  __shared__ __align__(16) float Bs[G_BK * G_STRIDE];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int n0 = blockIdx.x * G_BN, m0 = blockIdx.y * G_BM;
+  const int kbeg = blockIdx.z * p.k_per_split;
+  const int kend = min(p.K, kbeg + p.k_per_split);
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  float ra[4], rb[4];
+  if (kbeg < kend) gemm_load(p, m0, n0, kbeg, kend, tid, ra, rb);
+  for (int k0 = kbeg; k0 < kend; k0 += G_BK) {
+    gemm_store(p, tid, ra, rb, As, Bs);
+    __syncthreads();
+    if (k0 + G_BK < kend) gemm_load(p, m0, n0, k0 + G_BK, kend, tid, ra, rb);
+#pragma unroll
+    for (int kk = 0; kk < G_BK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk * G_STRIDE + ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk * G_STRIDE + tx * 4]);
+      acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+      acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
+      acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+      acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
+      acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
+      acc[2][2] = fmaf(a.z, b.z, acc[2][2]); acc[2][3] = fmaf(a.z, b.w, acc[2][3]);
+      acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
+      acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      if (p.nsplit > 1) {
+        p.ws[((size_t)blockIdx.z * p.M + m) * p.N + n] = acc[i][j];
+      } else {
+        float v = p.alpha * acc[i][j];
+        if (p.bias) v += __ldg(p.bias + n);
+        v = apply_act(v, p.act, p.leaky);
+        float* o = p.c + (size_t)m * p.c_rs + n;
+        if (p.beta != 0.f) v += p.beta * (*o);
+        *o = v;
+      }
+    }
+  }
+}
+
+__global__ void gemm_reduce_kernel(const __grid_constant__ GemmParams p) {
+  const long long total = (long long)p.M * p.N;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < p.nsplit; ++z) s += p.ws[(size_t)z * total + e];
+    const int m = (int)(e / p.N), n = (int)(e % p.N);
+    float v = p.alpha * s;
+    if (p.bias) v += __ldg(p.bias + n);
+    v = apply_act(v, p.act, p.leaky);
+    float* o = p.c + (size_t)m * p.c_rs + n;
+    if (p.beta != 0.f) v += p.beta * (*o);
+    *o = v;
+  }
+}
+
+}  // namespace cape
+
+using namespace cape;
+
+extern "C" int cape_gemm(cape_topology* t, int M, int N, int K, const float* a, int64_t a_rs, int64_t a_cs,
+                         const float* b, int64_t b_rs, int64_t b_cs, float* c, int64_t c_rs, const float* bias,
+                         int act, float leaky_alpha, float alpha, float beta, void* stream) {
+  CAPE_REQUIRE(t && a && b && c, "null pointer");
+  CAPE_REQUIRE(M > 0 && N > 0 && K > 0, "empty problem");
+  CAPE_REQUIRE(a_cs == 1 || a_rs == 1, "A needs a unit stride");
+  CAPE_REQUIRE(b_cs == 1 || b_rs == 1, "B needs a unit stride");
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.a = a; p.a_rs = a_rs; p.a_cs = a_cs;
+  p.b = b; p.b_rs = b_rs; p.b_cs = b_cs;
+  p.c = c; p.c_rs = c_rs; p.bias = bias; p.act = act; p.leaky = leaky_alpha; p.alpha = alpha; p.beta = beta;
+  const int mt = (M + G_BM - 1) / G_BM, nt = (N + G_BN - 1) / G_BN;
+  const long long tiles = (long long)mt * nt;
+  long long nsplit = 1;
+  if (tiles < 2LL * t->sm_count) {
+    nsplit = (4LL * t->sm_count + tiles - 1) / tiles;
+    const long long max_by_k = (K + 127) / 128;
+    if (nsplit > max_by_k) nsplit = max_by_k;
+    const long long per = (long long)M * N * (long long)sizeof(float);
+    if (nsplit > 1 && nsplit * per > t->workspace_bytes) nsplit = t->workspace_bytes / per;
+    if (nsplit < 1) nsplit = 1;
+  }
+  int kps = (int)((K + nsplit - 1) / nsplit);
+  kps = (kps + G_BK - 1) / G_BK * G_BK;
+  nsplit = (K + kps - 1) / kps;
+  p.nsplit = (int)nsplit; p.k_per_split = kps; p.ws = (float*)t->workspace;
+  CAPE_REQUIRE(mt <= 65535 && nsplit <= 65535, "grid too large");
+  dim3 grid(nt, mt, (unsigned)nsplit);
+  cudaStream_t st = (cudaStream_t)stream;
+  gemm_kernel<<<grid, 256, 0, st>>>(p);
+  CAPE_CHECK_CUDA(cudaGetLastError());
+  if (nsplit > 1) {
+    const long long total = (long long)M * N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 4 * t->sm_count) blocks = 4 * t->sm_count;
+    gemm_reduce_kernel<<<blocks, 256, 0, st>>>(p);
+    CAPE_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}

@@ -1,0 +1,178 @@
+"""Thin Python layer over the C ABI: topology handle, conv sites, kernel-call helpers.
+
+PyTorch is used only as plumbing (device buffers, streams); every compute call goes to libcape_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _lib
+from . import topology as topo
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, EPI_AFFINE, EPI_DUALMASK, EPI_LINEAR, EPI_SLOPE, ConvArgs, DwArgs,
+                   check)
+
+LEAKY_ALPHA = 0.2  # tf.nn.leaky_relu default (lib/models.py:109,506,582)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t):
+    assert t.dtype == torch.float32 and t.is_cuda, "expected a CUDA fp32 tensor"
+    return t
+
+
+class Topology:
+    """Owns a cape_topology handle on one device and the operator ids registered in it."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.CapeError("cape_b200 needs a CUDA device: there is no CPU execution path")
+        self.device = torch.device("cuda", device if isinstance(device, int) else device.index or 0)
+        h = C.c_void_p()
+        check(self.lib.cape_topology_create(self.device.index, C.byref(h)))
+        self.h = h
+        self.op_shapes = []
+        self._ws = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.cape_topology_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def add_operator(self, m):
+        """Register a scipy sparse matrix; returns its operator id."""
+        idx, w = topo.to_ell(m)
+        idx = np.ascontiguousarray(idx)
+        w = np.ascontiguousarray(w)
+        op = check(self.lib.cape_topology_add_operator(self.h, m.shape[0], m.shape[1], idx.shape[1],
+                                                       idx.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p)))
+        self.op_shapes.append((m.shape[0], m.shape[1], idx.shape[1]))
+        return op
+
+    def reserve_workspace(self, nbytes):
+        if nbytes > self._ws:
+            check(self.lib.cape_topology_reserve_workspace(self.h, int(nbytes)))
+            self._ws = int(nbytes)
+
+
+class ConvSite:
+    """One Chebyshev-conv call site: op_k = D . T_k(L~) . U for k < K (and the transposes for backward).
+
+    Mirrors the operand triple the reference passes around: the Laplacian given to `filter`
+    (lib/models.py:164,551,588,612,676,784,803), the U applied just before (:750,:782) and the D applied
+    just after (:168,:807).
+    """
+
+    def __init__(self, tp, L, K, U=None, D=None):
+        self.K = K
+        if U is not None and topo.is_identity(U, tol=1e-6):
+            U = None     # factor-1 levels: identity up to 5e-11
+        if D is not None and topo.is_identity(D, tol=0):
+            D = None
+        T = topo.cheb_polynomials(L, K)
+        self.rows_out = D.shape[0] if D is not None else L.shape[0]
+        self.rows_in = U.shape[1] if U is not None else L.shape[0]
+        self.ops, self.opsT, self.mats = [], [], []
+        for k in range(K):
+            m = topo.compose(D, T[k], U)
+            self.mats.append(m)
+            if m.shape[0] == m.shape[1] and topo.is_identity(m, tol=0):
+                self.ops.append(-1)
+                self.opsT.append(-1)
+            else:
+                self.ops.append(tp.add_operator(m))
+                self.opsT.append(tp.add_operator(sp.csr_matrix(m.T)))
+
+
+# ---------------------------------------------------------------------------------------------------
+# kernel-call helpers
+# ---------------------------------------------------------------------------------------------------
+def gemm(tp, A, B, Cout, bias=None, act=ACT_NONE, alpha=1.0, beta=0.0):
+    """Cout = act(alpha * A @ B + bias) + beta * Cout for 2-D (possibly transposed) views."""
+    M, K = A.shape
+    K2, N = B.shape
+    assert K == K2 and tuple(Cout.shape) == (M, N) and (Cout.stride(1) == 1 or N == 1)
+    a_rs, a_cs = A.stride()
+    b_rs, b_cs = B.stride()
+    if K == 1:          # degenerate dims: strides of size-1 axes are arbitrary in torch
+        a_cs = 1
+        if b_cs != 1:
+            b_rs = 1
+    if M == 1 and a_cs != 1:
+        a_rs = 1
+    if N == 1 and b_rs != 1:
+        b_cs = 1
+    check(tp.lib.cape_gemm(tp.h, M, N, K, _ptr(_f32(A)), a_rs, a_cs, _ptr(_f32(B)), b_rs, b_cs, _ptr(_f32(Cout)),
+                           Cout.stride(0), _ptr(bias), act, LEAKY_ALPHA, alpha, beta, _stream()))
+
+
+def cheb_call(tp, N, rows_out, ncols, terms, out, out2=None, cond=None, epilogue=EPI_LINEAR, act=ACT_NONE,
+              alpha=LEAKY_ALPHA, bias=None, bias_per_row=False, aux=None):
+    """terms: list of dicts(src, op, F, src_rows, src_stride, w, w_stride, w2, wc, wc2) with torch tensors."""
+    a = ConvArgs()
+    a.N, a.rows_out, a.ncols, a.nterms = N, rows_out, ncols, len(terms)
+    for i, t in enumerate(terms):
+        d = a.terms[i]
+        d.src = t["src"].data_ptr()
+        d.op = t["op"]
+        d.F = t["F"]
+        d.src_rows = t["src_rows"]
+        d.src_stride = t["src_stride"]
+        d.w_stride = t["w_stride"]
+        d.w2_stride = t.get("w2_stride", 0)
+        d.w = t["w"].data_ptr()
+        for k in ("w2", "wc", "wc2"):
+            v = t.get(k)
+            setattr(d, k, v.data_ptr() if v is not None else None)
+    if cond is not None:
+        a.cond = cond.data_ptr()
+        a.C = cond.shape[1]
+        assert cond.is_contiguous()
+    a.epilogue, a.act, a.alpha = epilogue, act, alpha
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.bias_per_row = 1 if bias_per_row else 0
+    a.aux = aux.data_ptr() if aux is not None else None
+    a.out = out.data_ptr()
+    a.out2 = out2.data_ptr() if out2 is not None else None
+    check(tp.lib.cape_cheb_fwd(tp.h, C.byref(a), _stream()))
+
+
+def cheb_dw(tp, N, rows_out, ncols, src, op, F, src_rows, src_stride, g, dw, dw_stride, accumulate=False):
+    a = DwArgs()
+    a.N, a.rows_out, a.ncols = N, rows_out, ncols
+    a.src, a.op, a.F, a.src_rows, a.src_stride = src.data_ptr(), op, F, src_rows, src_stride
+    a.g, a.dw, a.dw_stride, a.accumulate = g.data_ptr(), dw.data_ptr(), dw_stride, 1 if accumulate else 0
+    check(tp.lib.cape_cheb_dw(tp.h, C.byref(a), _stream()))
+
+
+def colsum(tp, g, N, rows, ncols, ops, out):
+    arr = (C.c_int * len(ops))(*ops)
+    check(tp.lib.cape_colsum(tp.h, _ptr(g), N, rows, ncols, arr, len(ops), _ptr(out), _stream()))
+
+
+def weight_transpose(tp, w, Fin, K, Fout, wt):
+    check(tp.lib.cape_cheb_weight_transpose(_ptr(w), Fin, K, Fout, _ptr(wt), _stream()))
+
+
+def act_bwd(tp, dy, y, g, alpha=LEAKY_ALPHA):
+    check(tp.lib.cape_act_bwd(_ptr(dy), _ptr(y), _ptr(g), dy.numel(), alpha, _stream()))
+
+
+def axpy(tp, y, x, a):
+    check(tp.lib.cape_axpy(_ptr(y), _ptr(x), float(a), y.numel(), _stream()))
+
+
+def resample(tp, op, x, y, N, rows_out, rows_in, F):
+    check(tp.lib.cape_resample(tp.h, op, _ptr(x), _ptr(y), N, rows_out, rows_in, F, _stream()))

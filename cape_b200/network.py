@@ -1,0 +1,647 @@
+"""Explicit forward/backward executor for the CAPE mesh-VAE-GAN on the fixed SMPL hierarchy.
+
+This replaces the TF-1.13 graph built by CAPE.build_graph (lib/models.py:267-351): the network is
+static, so forward and backward are spelled out layer by layer over preallocated device buffers and
+every layer is one (or a few) calls into libcape_b200.so.  Names in comments refer to the reference:
+encoder :514-561, decoder_cond_vert :564-617, res_block_affine :776-793, res_block_decoder :744-774,
+discriminator :648-678, loss :354-416, training :419-474.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import engine as E
+from . import topology as topo
+from .engine import (ACT_LEAKY, ACT_NONE, EPI_AFFINE, EPI_DUALMASK, EPI_LINEAR, EPI_SLOPE, ConvSite, Topology,
+                     act_bwd, axpy, cheb_call, cheb_dw, colsum, gemm, weight_transpose)
+from .params import init_params, is_d_param, is_g_param, param_specs
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+class ParamStore:
+    """Flat fp32 parameter / gradient / momentum buffers with named views (one all-reduce, one fused update)."""
+
+    def __init__(self, specs, names, device):
+        self.names = list(names)
+        self.shapes = {n: tuple(specs[n]) for n in self.names}
+        self.offsets = {}
+        off = 0
+        for n in self.names:
+            self.offsets[n] = off
+            off += _pad4(int(np.prod(self.shapes[n])))
+        self.size = max(off, 4)
+        self.flat = torch.zeros(self.size, device=device)
+        self.grad = torch.zeros(self.size, device=device)
+        self.mom = torch.zeros(self.size, device=device)
+
+    def _view(self, buf, n):
+        k = int(np.prod(self.shapes[n]))
+        return buf[self.offsets[n]: self.offsets[n] + k]
+
+    def w(self, n):
+        return self._view(self.flat, n)
+
+    def g(self, n):
+        return self._view(self.grad, n)
+
+    def load(self, values):
+        for n in self.names:
+            self.w(n).copy_(torch.as_tensor(np.asarray(values[n], np.float32).reshape(-1)))
+
+    def export(self, buf=None):
+        buf = self.flat if buf is None else buf
+        return {n: self._view(buf, n).detach().cpu().numpy().reshape(self.shapes[n]).copy() for n in self.names}
+
+
+class Arena:
+    """Bump allocator over one device buffer that is zeroed once per step (colsum targets)."""
+
+    def __init__(self):
+        self.reqs = []
+        self.buf = None
+
+    def request(self, *shape):
+        self.reqs.append(shape)
+        return len(self.reqs) - 1
+
+    def build(self, device):
+        offs, off = [], 0
+        for s in self.reqs:
+            offs.append(off)
+            off += _pad4(int(np.prod(s)))
+        self.buf = torch.zeros(max(off, 4), device=device)
+        self.views = [self.buf[o: o + int(np.prod(s))].view(*s) for o, s in zip(offs, self.reqs)]
+
+    def get(self, i):
+        return self.views[i]
+
+    def zero(self):
+        self.buf.zero_()
+
+
+class ChebLayer:
+    """chebyshev5 (+bias/act, +pool/unpool folded into the site, +condition channels, + optional affine
+    branch) with its backward."""
+
+    def __init__(self, net, site, F, C, Fout, W, gW, bias=None, gbias=None, act=ACT_NONE, Wa=None, gWa=None,
+                 bias_per_row=False, need_dx=True, maxN=1, n_cs_slots=1):
+        self.net, self.tp, self.site = net, net.tp, site
+        self.F, self.C, self.Fout, self.K = F, C, Fout, site.K
+        K = self.K
+        self.W3, self.gW3 = W.view(F + C, K, Fout), gW.view(F + C, K, Fout)
+        self.W, self.bias, self.gbias, self.act = W, bias, gbias, act
+        self.bias_per_row = bias_per_row
+        self.affine = Wa is not None
+        if self.affine:
+            self.Wa, self.Wa2, self.gWa2 = Wa, Wa.view(F + C, Fout), gWa.view(F + C, Fout)
+        self.need_dx = need_dx
+        dev = W.device
+        if need_dx:
+            self.Wt = torch.empty(Fout, K, F, device=dev)
+            if self.affine:
+                self.Wat = torch.empty(Fout, F, device=dev)
+        # colsum targets: [bias?] + K condition sums (+1 for the affine branch)
+        self.cs_ops = []
+        if bias is not None and not bias_per_row:
+            self.cs_ops.append(-1)
+        self.cs_cond0 = len(self.cs_ops)
+        if C:
+            self.cs_ops += list(site.ops)
+        # one zero-initialised target per backward call made within a step (colsum accumulates atomically)
+        self.cs_id = [net.arena.request(maxN, max(len(self.cs_ops), 1), Fout) for _ in range(n_cs_slots)]
+        self.csa_id = net.arena.request(maxN, 1, Fout) if (self.affine and C) else None
+
+    def prep(self):
+        if self.need_dx:
+            weight_transpose(self.tp, self.W, self.F, self.K, self.Fout, self.Wt)
+            if self.affine:
+                weight_transpose(self.tp, self.Wa, self.F, 1, self.Fout, self.Wat)
+
+    def fwd(self, x, ycat, out, out2=None):
+        N = x.shape[0]
+        s, F, C, K, Fout = self.site, self.F, self.C, self.K, self.Fout
+        assert x.shape[1] == s.rows_in and x.shape[2] >= F and out.shape[1] == s.rows_out
+        terms = []
+        for k in range(K):
+            t = dict(src=x, op=s.ops[k], F=F, src_rows=s.rows_in, src_stride=x.shape[2], w=self.W3[:, k, :],
+                     w_stride=K * Fout)
+            if C:
+                t["wc"] = self.W3[F:, k, :]
+            if self.affine and k == 0:
+                t["w2"], t["w2_stride"] = self.Wa2, Fout
+                if C:
+                    t["wc2"] = self.Wa2[F:]
+            terms.append(t)
+        cheb_call(self.tp, N, s.rows_out, Fout, terms, out, out2=out2, cond=ycat if C else None,
+                  epilogue=EPI_AFFINE if self.affine else EPI_LINEAR, act=self.act, bias=self.bias,
+                  bias_per_row=self.bias_per_row)
+
+    def bwd(self, x, ycat, g, g_aff=None, dx=None, dx2=None, dx_epi=EPI_LINEAR, dx_aux=None, dx_alpha=E.LEAKY_ALPHA,
+            dycat=None, want_dw=True, cs_slot=0):
+        """g: gradient w.r.t. the pre-activation of accumulator 0 ([N, rows_out, Fout]);
+        g_aff: gradient w.r.t. the affine branch (= d out) when the layer has one."""
+        tp, s, F, C, K, Fout = self.tp, self.site, self.F, self.C, self.K, self.Fout
+        N = g.shape[0]
+        sx = x.shape[2]
+        if want_dw:
+            for k in range(K):
+                cheb_dw(tp, N, s.rows_out, Fout, x, s.ops[k], F, s.rows_in, sx, g, self.gW3[:, k, :], K * Fout)
+            if self.affine:
+                cheb_dw(tp, N, s.rows_out, Fout, x, s.ops[0], F, s.rows_in, sx, g_aff, self.gWa2, Fout)
+        has_bias = self.bias is not None and not self.bias_per_row and want_dw
+        if (has_bias or C) and len(self.cs_ops):
+            cs = self.net.arena.get(self.cs_id[cs_slot])[:N]
+            nops = len(self.cs_ops)
+            if nops <= 4:
+                colsum(tp, g, N, s.rows_out, Fout, self.cs_ops, cs)
+            else:
+                for o in range(0, nops, 4):
+                    self._colsum_chunk(g, N, cs, o)
+            if has_bias:
+                gemm(tp, self.net.ones[:, :N], cs[:, 0, :], self.gbias.view(1, Fout))
+            if C:
+                for k in range(K):
+                    dq = cs[:, self.cs_cond0 + k, :]
+                    if want_dw:
+                        gemm(tp, ycat.t(), dq, self.gW3[F:, k, :])
+                    if dycat is not None:
+                        gemm(tp, dq, self.W3[F:, k, :].t(), dycat, beta=1.0)
+        if self.affine and C:
+            csa = self.net.arena.get(self.csa_id)[:N]
+            colsum(tp, g_aff, N, s.rows_out, Fout, [s.ops[0]], csa)
+            if want_dw:
+                gemm(tp, ycat.t(), csa[:, 0, :], self.gWa2[F:])
+            if dycat is not None:
+                gemm(tp, csa[:, 0, :], self.Wa2[F:].t(), dycat, beta=1.0)
+        if self.bias_per_row and want_dw:
+            gemm(tp, self.net.ones[:, :N], g.view(N, s.rows_out * Fout), self.gbias.view(1, s.rows_out * Fout))
+        if dx is not None:
+            assert self.need_dx
+            terms = []
+            if self.affine:
+                terms.append(dict(src=g_aff, op=s.opsT[0], F=Fout, src_rows=s.rows_out, src_stride=Fout, w=self.Wat,
+                                  w_stride=F))
+            for k in range(K):
+                terms.append(dict(src=g, op=s.opsT[k], F=Fout, src_rows=s.rows_out, src_stride=Fout,
+                                  w=self.Wt[:, k, :], w_stride=K * F))
+            cheb_call(tp, N, s.rows_in, F, terms, dx, out2=dx2, epilogue=dx_epi, aux=dx_aux, alpha=dx_alpha)
+
+    def _colsum_chunk(self, g, N, cs, o):
+        # more than 4 operators (K > 3 with conditions): contiguous scratch per chunk, then copy back
+        ops = self.cs_ops[o:o + 4]
+        tmp = torch.zeros(N, len(ops), self.Fout, device=g.device)
+        colsum(self.tp, g, N, self.site.rows_out, self.Fout, ops, tmp)
+        cs[:, o:o + len(ops), :] = tmp
+
+
+class Dense:
+    """tf.layers.dense (y = act(xW + b)) with backward."""
+
+    def __init__(self, net, W, b, gW, gb, act=ACT_NONE):
+        self.net, self.tp = net, net.tp
+        self.W, self.b, self.gW, self.gb, self.act = W, b, gW, gb, act
+
+    def fwd(self, x, out):
+        gemm(self.tp, x, self.W, out, bias=self.b, act=self.act)
+
+    def bwd(self, x, out, dout, gtmp=None, dx=None, dx_beta=0.0, want_dw=True):
+        g = dout
+        if self.act != ACT_NONE:
+            act_bwd(self.tp, dout, out, gtmp)
+            g = gtmp
+        N = g.shape[0]
+        if want_dw:
+            gemm(self.tp, x.t(), g, self.gW)
+            gemm(self.tp, self.net.ones[:, :N], g, self.gb.view(1, -1))
+        if dx is not None:
+            gemm(self.tp, g, self.W.t(), dx, beta=dx_beta)
+
+
+class CapeNetwork:
+    """Encoder/decoder/discriminator + losses + optimiser on one GPU for a fixed batch size."""
+
+    def __init__(self, L, D, U, L_d, D_d, cfg, batch_size, device=0, params=None, ref_compat=False):
+        self.cfg = dict(cfg)
+        self.N = int(batch_size)
+        self.ref_compat = bool(ref_compat)
+        c = self.cfg
+        if c["use_res_block"] or not c["use_res_block_dec"] or c["cond_encoder"] or c["reduce_dim"] <= 0:
+            raise NotImplementedError("only the shipped-config architecture is built: use_res_block=0, "
+                                      "use_res_block_dec=1, cond_encoder=0, reduce_dim>0")
+        if c["optimizer"] != "sgd" or c["loss"] != "l1":
+            raise NotImplementedError("only optimizer='sgd' (momentum) and loss='l1' are implemented")
+        if not c["affine"]:
+            raise NotImplementedError("non-affine (GroupNorm) decoder blocks: see cape_b200.network_gn")
+        self.tp = tp = Topology(device)
+        self.device = dev = tp.device
+        torch.cuda.set_device(dev)
+        self.p = [int(l.shape[0]) for l in L]
+        self.p_d = [int(l.shape[0]) for l in L_d]
+        F, K, Kd = c["F"], c["K"], c["Kd"]
+        nz, Cc = c["nz"], c["nz_cond"] + c["nz_cond2"]
+        self.nz, self.Cc = nz, Cc
+        N = self.N
+        self.specs = specs = param_specs(c, self.p, self.p_d)
+        gnames = [n for n in specs if is_g_param(n, True)]          # condition nets live in the G store
+        dnames = [n for n in specs if is_d_param(n)]
+        self.PG, self.PD = ParamStore(specs, gnames, dev), ParamStore(specs, dnames, dev)
+        vals = params if params is not None else init_params(specs, c["seed"])
+        self.PG.load(vals)
+        self.PD.load(vals)
+        self.arena = Arena()
+        self.ones = torch.ones(1, 2 * N, device=dev)
+        w, g = self._w, self._g
+
+        # ---- sites -------------------------------------------------------------------------------------
+        nl = len(F)
+        self.enc = []
+        fin = c["nn_input_channel"]
+        for i in range(nl):
+            site = ConvSite(tp, L[i], K[i], D=D[i])
+            sc = "generator/encoder/encoder_conv%d" % (i + 1)
+            self.enc.append(ChebLayer(self, site, fin, 0, F[i], w(sc + "/weights"), g(sc + "/weights"),
+                                      bias=w(sc + "/bias"), gbias=g(sc + "/bias"), act=ACT_LEAKY, need_dx=(i > 0),
+                                      maxN=N))
+            fin = F[i]
+        red = specs["generator/encoder/1x1-conv/weights"][1]
+        self.red = red
+        self.enc_1x1 = ChebLayer(self, ConvSite(tp, L[-1], 1), F[-1], 0, red, w("generator/encoder/1x1-conv/weights"),
+                                 g("generator/encoder/1x1-conv/weights"), maxN=N)
+        flat = self.p[-1] * red
+        self.flat = flat
+        dn = lambda s, act=ACT_NONE: Dense(self, w(s + "/dense/kernel").view(specs[s + "/dense/kernel"]),
+                                           w(s + "/dense/bias"), g(s + "/dense/kernel").view(specs[s + "/dense/kernel"]),
+                                           g(s + "/dense/bias"), act)
+        self.fc_mean, self.fc_var = dn("generator/encoder/fc_mean"), dn("generator/encoder/fc_var")
+        self.dec_fc1 = dn("generator/decoder/fc1", ACT_LEAKY)
+        self.dec_1x1 = ChebLayer(self, ConvSite(tp, L[-1], 1), red, 0, F[-1], w("generator/decoder/1x1-conv/weights"),
+                                 g("generator/decoder/1x1-conv/weights"), maxN=N)
+        self.dec = []
+        fin = F[-1]
+        for i in range(nl):
+            Fo = F[-i - 1] // 2
+            site = ConvSite(tp, L[-i - 2], K[-i - 1], U=U[-i - 1])
+            sc = "generator/decoder/decoder_resblock_affine%d" % (i + 1)
+            self.dec.append(ChebLayer(self, site, fin, Cc, Fo, w(sc + "/graph_conv/weights"),
+                                      g(sc + "/graph_conv/weights"), Wa=w(sc + "/affine/weights"),
+                                      gWa=g(sc + "/affine/weights"), maxN=N))
+            fin = Fo
+        self.dec_out = ChebLayer(self, ConvSite(tp, L[0], K[0]), fin, Cc, c["nn_input_channel"],
+                                 w("generator/decoder/outputs/weights"), g("generator/decoder/outputs/weights"),
+                                 bias=w("generator/decoder/outputs/bias"), gbias=g("generator/decoder/outputs/bias"),
+                                 bias_per_row=True, maxN=N)
+        self.disc = []
+        fin = c["nn_input_channel"]
+        for i in range(len(D_d)):
+            site = ConvSite(tp, L_d[i], Kd, D=D_d[i])
+            sc = "discriminator/shared/conv%d" % (i + 1)
+            self.disc.append(ChebLayer(self, site, fin, Cc if i == 0 else 0, F[i], w(sc + "/weights"),
+                                       g(sc + "/weights"), bias=w(sc + "/bias"), gbias=g(sc + "/bias"), act=ACT_LEAKY,
+                                       maxN=2 * N, n_cs_slots=2))
+            fin = F[i]
+        self.disc_pred = ChebLayer(self, ConvSite(tp, L_d[-1], K[-1]), fin, 0, 1,
+                                   w("discriminator/prediction_map/weights"), g("discriminator/prediction_map/weights"),
+                                   maxN=2 * N, n_cs_slots=2)
+        # condition nets (models.py:479-511)
+        self.c_pose1 = dn("condition_pose/fc1", ACT_LEAKY)
+        self.c_pose2 = dn("condition_pose/fc2")
+        if "condition_clo_label/fc2/dense/kernel" in specs:
+            self.c_clo1, self.c_clo2 = dn("condition_clo_label/fc1", ACT_LEAKY), dn("condition_clo_label/fc2")
+        else:
+            self.c_clo1, self.c_clo2 = dn("condition_clo_label/fc1"), None
+        self.nbr_op = tp.add_operator(_adjacency(L[0]))
+        self.n_edges = int(_adjacency(L[0]).nnz // 2)
+        self.arena.build(dev)
+
+        # ---- buffers -----------------------------------------------------------------------------------
+        z = lambda *s: torch.zeros(*s, device=dev)
+        P0 = self.p[0]
+        ci, c2i = c["cond_dim"], c["cond2_dim"]
+        self.in_x = z(N, P0, 3)                 # generator input (also its reconstruction target)
+        self.in_cond = z(2 * N, ci)             # rows [0,N): discriminator batch, [N,2N): generator batch
+        self.in_cond2 = z(2 * N, c2i)
+        self.in_eps = z(N, nz)
+        self.xcat = z(2 * N, P0, 3)             # [x_real ; x_hat]
+        self.x_hat = self.xcat[N:]
+        self.ycat = z(2 * N, Cc)                # [y | y2] for both batches
+        self.ycat_g = self.ycat[N:]
+        h1 = specs["condition_pose/fc1/dense/kernel"][1]
+        self.cp_h = z(2 * N, h1)
+        self.cc_h = z(2 * N, specs["condition_clo_label/fc1/dense/kernel"][1]) if self.c_clo2 else None
+        self.enc_act = [z(N, l.site.rows_out, l.Fout) for l in self.enc]
+        self.enc_red = z(N, self.p[-1], red)
+        self.z_mean, self.z_logvar = z(N, nz), z(N, nz)
+        self.z_total = z(N, nz + Cc)
+        self.dec_fc = z(N, flat)
+        self.dec_h0 = z(N, self.p[-1], F[-1])
+        self.dec_act = [z(N, l.site.rows_out, l.Fout) for l in self.dec]
+        self.dec_rg = [z(N, l.site.rows_out, l.Fout) for l in self.dec]
+        self.disc_act = [z(2 * N, l.site.rows_out, l.Fout) for l in self.disc]
+        self.logits = z(2 * N, self.p_d[-1], 1)
+        # gradients
+        self.d_logits = z(2 * N, self.p_d[-1], 1)
+        self.d_logits_g = z(N, self.p_d[-1], 1)
+        self.g_disc = [z(2 * N, l.site.rows_out, l.Fout) for l in self.disc]
+        self.d_xhat = z(N, P0, 3)
+        self.d_ycat = z(N, Cc)
+        self.g_dec = [z(N, l.site.rows_out, l.Fout) for l in self.dec]       # d out of each block
+        self.g_dec_m = [z(N, l.site.rows_out, l.Fout) for l in self.dec]     # masked (graph-conv branch)
+        self.g_dec_h0 = z(N, self.p[-1], F[-1])
+        self.g_dec_fc = z(N, flat)
+        self.g_dec_fc_t = z(N, flat)
+        self.g_z = z(N, nz)
+        self.g_mean, self.g_logvar = z(N, nz), z(N, nz)
+        self.g_enc_red = z(N, self.p[-1], red)
+        self.g_enc = [z(N, l.site.rows_out, l.Fout) for l in self.enc]
+        self.g_cp_h, self.g_cp_t = z(N, h1), z(N, h1)
+        self.g_cc_h = z(N, self.cc_h.shape[1]) if self.c_clo2 else None
+        self.g_cc_t = z(N, self.cc_h.shape[1]) if self.c_clo2 else None
+        self.losses = z(8)       # recon, edge, kl, gan_g, gan_d_real, gan_d_fake
+        self.sumsq = z(2)
+        self.lr = z(2)
+        self.step_count = 0
+        # workspace: split-K partials (dW of the widest layer, FC split-K)
+        tp.reserve_workspace(64 << 20)
+        self.prep_weights()
+
+    # ---- parameter access --------------------------------------------------------------------------------
+    def _store(self, n):
+        return self.PD if is_d_param(n) else self.PG
+
+    def _w(self, n):
+        return self._store(n).w(n)
+
+    def _g(self, n):
+        return self._store(n).g(n)
+
+    def get_params(self):
+        out = self.PG.export()
+        out.update(self.PD.export())
+        return out
+
+    def get_grads(self):
+        out = self.PG.export(self.PG.grad)
+        out.update(self.PD.export(self.PD.grad))
+        return out
+
+    def set_params(self, vals):
+        self.PG.load(vals)
+        self.PD.load(vals)
+        self.prep_weights()
+
+    def all_layers(self):
+        return self.enc + [self.enc_1x1, self.dec_1x1] + self.dec + [self.dec_out] + self.disc + [self.disc_pred]
+
+    def prep_weights(self):
+        """Re-layouts derived from the weights (transposes for the data-gradient pass); run after every update."""
+        for l in self.all_layers():
+            l.prep()
+
+    # ---- inputs --------------------------------------------------------------------------------------------
+    def set_inputs(self, x_g, cond_g, cond2_g, eps, x_d=None, cond_d=None, cond2_d=None, non_blocking=True):
+        """Host (pinned) or device tensors -> device input buffers."""
+        N = self.N
+        self.in_x.copy_(x_g, non_blocking=non_blocking)
+        self.in_cond[N:].copy_(cond_g, non_blocking=non_blocking)
+        self.in_cond2[N:].copy_(cond2_g, non_blocking=non_blocking)
+        self.in_eps.copy_(eps, non_blocking=non_blocking)
+        if x_d is not None:
+            self.xcat[:N].copy_(x_d, non_blocking=non_blocking)
+            self.in_cond[:N].copy_(cond_d, non_blocking=non_blocking)
+            self.in_cond2[:N].copy_(cond2_d, non_blocking=non_blocking)
+
+    # ---- forward pieces ---------------------------------------------------------------------------------------
+    def cond_fwd(self, lo, hi):
+        """condition nets on rows [lo,hi) of the stacked condition inputs -> ycat rows."""
+        nzc = self.cfg["nz_cond"]
+        self.c_pose1.fwd(self.in_cond[lo:hi], self.cp_h[lo:hi])
+        self.c_pose2.fwd(self.cp_h[lo:hi], self.ycat[lo:hi, :nzc])
+        if self.c_clo2 is None:
+            self.c_clo1.fwd(self.in_cond2[lo:hi], self.ycat[lo:hi, nzc:])
+        else:
+            self.c_clo1.fwd(self.in_cond2[lo:hi], self.cc_h[lo:hi])
+            self.c_clo2.fwd(self.cc_h[lo:hi], self.ycat[lo:hi, nzc:])
+
+    def encoder_fwd(self):
+        x = self.in_x
+        for l, a in zip(self.enc, self.enc_act):
+            l.fwd(x, None, a)
+            x = a
+        self.enc_1x1.fwd(x, None, self.enc_red)
+        flat = self.enc_red.view(self.N, self.flat)
+        self.fc_mean.fwd(flat, self.z_mean)
+        self.fc_var.fwd(flat, self.z_logvar)
+
+    def sample_fwd(self):
+        N, nz = self.N, self.nz
+        _lib.check(self.tp.lib.cape_vae_sample_fwd(E._ptr(self.z_mean), E._ptr(self.z_logvar), E._ptr(self.in_eps),
+                                                   E._ptr(self.z_total), nz + self.Cc, N, nz, E._stream()))
+        self.z_total[:, nz:].copy_(self.ycat_g)
+
+    def decoder_fwd(self, z_total=None, ycat=None, out=None):
+        z_total = self.z_total if z_total is None else z_total
+        ycat = self.ycat_g if ycat is None else ycat
+        out = self.x_hat if out is None else out
+        self.dec_fc1.fwd(z_total, self.dec_fc)
+        self.dec_1x1.fwd(self.dec_fc.view(self.N, self.p[-1], self.red), None, self.dec_h0)
+        x = self.dec_h0
+        for l, a, rg in zip(self.dec, self.dec_act, self.dec_rg):
+            l.fwd(x, ycat, a, out2=rg)
+            x = a
+        self.dec_out.fwd(x, ycat, out)
+
+    def disc_fwd(self, lo, hi):
+        x = self.xcat[lo:hi]
+        yc = self.ycat[lo:hi]
+        for l, a in zip(self.disc, self.disc_act):
+            l.fwd(x, yc, a[lo:hi])
+            x = a[lo:hi]
+        self.disc_pred.fwd(x, None, self.logits[lo:hi])
+
+    # ---- backward pieces ---------------------------------------------------------------------------------------
+    def disc_bwd(self, lo, hi, dlogits, want_dw, dx=None, dycat=None, cs_slot=0):
+        """dlogits: [hi-lo, 431, 1] upstream gradient.  want_dw: discriminator-loss path (weight grads);
+        dx/dycat: generator-loss path (gradient w.r.t. the input mesh and the condition embedding)."""
+        n = len(self.disc)
+        acts = [a[lo:hi] for a in self.disc_act]
+        gs = [gb[: hi - lo] for gb in self.g_disc]
+        yc = self.ycat[lo:hi]
+        self.disc_pred.bwd(acts[-1], None, dlogits, dx=gs[-1], dx_epi=EPI_SLOPE, dx_aux=acts[-1], want_dw=want_dw,
+                           cs_slot=cs_slot)
+        for i in range(n - 1, 0, -1):
+            self.disc[i].bwd(acts[i - 1], None, gs[i], dx=gs[i - 1], dx_epi=EPI_SLOPE, dx_aux=acts[i - 1],
+                             want_dw=want_dw, cs_slot=cs_slot)
+        self.disc[0].bwd(self.xcat[lo:hi], yc, gs[0], dx=dx, dycat=dycat, want_dw=want_dw, cs_slot=cs_slot)
+
+    def decoder_bwd(self):
+        """d_xhat -> decoder weight grads, d z_total, d ycat (accumulated)."""
+        N, nl = self.N, len(self.dec)
+        yc = self.ycat_g
+        last = self.dec_act[-1]
+        self.dec_out.bwd(last, yc, self.d_xhat, dx=self.g_dec[-1], dx2=self.g_dec_m[-1], dx_epi=EPI_DUALMASK,
+                         dx_aux=self.dec_rg[-1], dycat=self.d_ycat)
+        for i in range(nl - 1, -1, -1):
+            x = self.dec_act[i - 1] if i > 0 else self.dec_h0
+            if i > 0:
+                self.dec[i].bwd(x, yc, self.g_dec_m[i], g_aff=self.g_dec[i], dx=self.g_dec[i - 1],
+                                dx2=self.g_dec_m[i - 1], dx_epi=EPI_DUALMASK, dx_aux=self.dec_rg[i - 1],
+                                dycat=self.d_ycat)
+            else:
+                self.dec[i].bwd(x, yc, self.g_dec_m[i], g_aff=self.g_dec[i], dx=self.g_dec_h0, dycat=self.d_ycat)
+        fcv = self.dec_fc.view(N, self.p[-1], self.red)
+        self.dec_1x1.bwd(fcv, None, self.g_dec_h0, dx=self.g_dec_fc.view(N, self.p[-1], self.red))
+        self.dec_fc1.bwd(self.z_total, self.dec_fc, self.g_dec_fc, gtmp=self.g_dec_fc_t)
+        W = self.dec_fc1.W                     # [nz + Cc, flat]: rows [0,nz) latent code, rows [nz,..) condition (models.py:641)
+        gemm(self.tp, self.g_dec_fc_t, W[:self.nz].t(), self.g_z)
+        gemm(self.tp, self.g_dec_fc_t, W[self.nz:].t(), self.d_ycat, beta=1.0)
+
+    def encoder_bwd(self):
+        N, nz = self.N, self.nz
+        c = self.cfg
+        _lib.check(self.tp.lib.cape_vae_sample_bwd(E._ptr(self.g_z), nz, E._ptr(self.z_mean),
+                                                   E._ptr(self.z_logvar), E._ptr(self.in_eps), E._ptr(self.g_mean),
+                                                   E._ptr(self.g_logvar), N, nz, float(c["lambda_latent"]),
+                                                   E._stream()))
+        flat = self.enc_red.view(N, self.flat)
+        gflat = self.g_enc_red.view(N, self.flat)
+        self.fc_mean.bwd(flat, self.z_mean, self.g_mean, dx=gflat)
+        self.fc_var.bwd(flat, self.z_logvar, self.g_logvar, dx=gflat, dx_beta=1.0)
+        self.enc_1x1.bwd(self.enc_act[-1], None, self.g_enc_red, dx=self.g_enc[-1], dx_epi=EPI_SLOPE,
+                         dx_aux=self.enc_act[-1])
+        for i in range(len(self.enc) - 1, 0, -1):
+            self.enc[i].bwd(self.enc_act[i - 1], None, self.g_enc[i], dx=self.g_enc[i - 1], dx_epi=EPI_SLOPE,
+                            dx_aux=self.enc_act[i - 1])
+        self.enc[0].bwd(self.in_x, None, self.g_enc[0])
+
+    def cond_bwd(self):
+        """d_ycat (generator batch) -> condition-net weight grads."""
+        N = self.N
+        nzc = self.cfg["nz_cond"]
+        dy = self.d_ycat[:, :nzc]
+        dy2 = self.d_ycat[:, nzc:]
+        self.c_pose2.bwd(self.cp_h[N:], None, dy, dx=self.g_cp_h)
+        self.c_pose1.bwd(self.in_cond[N:], self.cp_h[N:], self.g_cp_h, gtmp=self.g_cp_t)
+        if self.c_clo2 is None:
+            self.c_clo1.bwd(self.in_cond2[N:], None, dy2)
+        else:
+            self.c_clo2.bwd(self.cc_h[N:], None, dy2, dx=self.g_cc_h)
+            self.c_clo1.bwd(self.in_cond2[N:], self.cc_h[N:], self.g_cc_h, gtmp=self.g_cc_t)
+
+    # ---- public passes ------------------------------------------------------------------------------------------
+    def forward_generator(self):
+        """condition nets + encoder + sampling + decoder on the generator batch (BASELINE config 2)."""
+        N = self.N
+        self.cond_fwd(N, 2 * N)
+        self.encoder_fwd()
+        self.sample_fwd()
+        self.decoder_fwd()
+        return self.x_hat
+
+    def lr_now(self, step):
+        """Learning-rate policy of CAPE.training (lib/models.py:426-442)."""
+        c = self.cfg
+        lr_g, lr_d = c["lr"], c["lr"] * c["lr_scaler"]
+        ds = int(c["decay_steps"])
+        if c["lr_warmup"]:
+            warm = int(c["decay_steps"] * 8)
+            if step < warm:
+                return lr_g * step / warm, lr_d * step / warm
+            k = math.floor((step - warm) / ds)
+        else:
+            k = math.floor(step / ds)
+        return lr_g * c["decay_rate"] ** k, lr_d * c["decay_rate"] ** k
+
+    def train_step(self, step=None, update=True, allreduce=None):
+        """One optimiser application on both players = one sess.run(op_train_*) of the reference
+        (lib/models.py:460-472).  Inputs must have been staged with set_inputs()."""
+        N, c, tp = self.N, self.cfg, self.tp
+        lam_gan = float(c["lambda_gan"])
+        step = self.step_count if step is None else step
+        self.arena.zero()
+        self.losses.zero_()
+        self.d_ycat.zero_()
+        # forward: both condition batches at once, generator, discriminator on [real ; fake]
+        self.cond_fwd(0, 2 * N)
+        self.encoder_fwd()
+        self.sample_fwd()
+        self.decoder_fwd()
+        self.disc_fwd(0, 2 * N)
+        nlog = N * self.p_d[-1]
+        L = self.losses
+        lib = tp.lib
+        st = E._stream
+        # GAN losses with soft labels 0.9 / 0.1 (models.py:383-390)
+        _lib.check(lib.cape_bce_logits(E._ptr(self.logits[N:]), nlog, 0.9, lam_gan, E._ptr(self.d_logits_g),
+                                       E._ptr(L[3:]), st()))
+        _lib.check(lib.cape_bce_logits(E._ptr(self.logits[:N]), nlog, 0.9, lam_gan, E._ptr(self.d_logits[:N]),
+                                       E._ptr(L[4:]), st()))
+        _lib.check(lib.cape_bce_logits(E._ptr(self.logits[N:]), nlog, 0.1, lam_gan, E._ptr(self.d_logits[N:]),
+                                       E._ptr(L[5:]), st()))
+        # discriminator-loss path: weight gradients from both halves
+        if not self.ref_compat:
+            self.disc_bwd(0, 2 * N, self.d_logits, want_dw=True)
+        # generator-loss path through D(fake): gradient w.r.t. x_hat and the condition embedding
+        self.disc_bwd(N, 2 * N, self.d_logits_g, want_dw=False, dx=self.d_xhat, dycat=self.d_ycat, cs_slot=1)
+        _lib.check(lib.cape_recon_losses(tp.h, self.nbr_op, E._ptr(self.x_hat), E._ptr(self.in_x), N, self.p[0],
+                                         float(c["lambda_recon"]), float(c["lambda_edge"]), self.n_edges,
+                                         E._ptr(self.z_mean), E._ptr(self.z_logvar), self.nz, E._ptr(self.d_xhat),
+                                         E._ptr(L), st()))
+        self.decoder_bwd()
+        self.encoder_bwd()
+        self.cond_bwd()
+        # fc L2 regularisation: regularization * sum(l2_regularizer(regularization)(W)) -> grad reg^2 * W (models.py:378)
+        r2 = float(c["regularization"]) ** 2
+        if r2 > 0:
+            for n in ("generator/encoder/fc_mean", "generator/encoder/fc_var", "generator/decoder/fc1"):
+                axpy(tp, self._g(n + "/dense/kernel"), self._w(n + "/dense/kernel"), r2)
+        if self.ref_compat:
+            self.PD.grad.copy_(self.PD.flat)          # models.py:466: the D "gradients" are its variables
+        if allreduce is not None:
+            allreduce(self.PG.grad, self.PD.grad)
+        if update:
+            self.apply_update(step)
+        return L
+
+    def apply_update(self, step):
+        """clip_by_global_norm(5.0) + MomentumOptimizer for both players (models.py:460-467)."""
+        lib = self.tp.lib
+        c = self.cfg
+        lr_g, lr_d = self.lr_now(step)
+        self.lr.copy_(torch.tensor([lr_g, lr_d], dtype=torch.float32), non_blocking=True)
+        self.sumsq.zero_()
+        if not c["optim_condnet"]:                 # models.py:455-458: condition nets excluded from vars_g
+            for n in self.PG.names:
+                if not n.startswith("generator"):
+                    self.PG.g(n).zero_()
+        for P, i in ((self.PG, 0), (self.PD, 1)):
+            _lib.check(lib.cape_sumsq(E._ptr(P.grad), P.size, E._ptr(self.sumsq[i:]), E._stream()))
+            _lib.check(lib.cape_sgd_clip_update(E._ptr(P.flat), E._ptr(P.grad), E._ptr(P.mom), P.size,
+                                                E._ptr(self.sumsq[i:]), 5.0, E._ptr(self.lr[i:]),
+                                                float(c["momentum"]), E._stream()))
+        self.step_count = step + 1
+        self.prep_weights()
+
+    def loss_dict(self):
+        """Host copy of the last step's loss terms (synchronises)."""
+        v = self.losses.detach().cpu().numpy()
+        c = self.cfg
+        out = dict(recon=float(v[0]), edge=float(v[1]), latent=float(v[2]), gan_g=float(v[3]),
+                   gan_d=float(v[4] + v[5]))
+        out["loss_g_noreg"] = (out["gan_g"] * c["lambda_gan"] + out["recon"] * c["lambda_recon"]
+                               + out["edge"] * c["lambda_edge"] + out["latent"] * c["lambda_latent"])
+        out["loss_d"] = out["gan_d"] * c["lambda_gan"]
+        return out
+
+
+def _adjacency(L):
+    import scipy.sparse as sp
+    A = sp.csr_matrix(L, copy=True)
+    A.setdiag(0)
+    A.eliminate_zeros()
+    A.data[:] = 1.0
+    return A

@@ -1,0 +1,127 @@
+"""The reference's operator seam on top of the CUDA kernels.
+
+The reference resolves its ops by name on `base_model` (lib/models.py:16-17,58-62):
+filter='chebyshev5', pool/unpool='poolwT', activation='b1leakyrelu'.  The functions below keep those
+names and argument meanings (x: [N, M, Fin] fp32, L / S: scipy sparse) but take the weights explicitly
+instead of creating TF variables (b1leakyrelu exists only as chebyshev5's fused epilogue), and are differentiable through torch.autograd so a parity test reads
+like a test of the reference op.  `chebyshev5` additionally exposes the fusions the kernels offer
+(bias + activation, pooling D and unpooling U folded into the gather).
+"""
+import torch
+
+from . import engine as E
+from .engine import ACT_LEAKY, ACT_NONE, ACT_RELU, EPI_LINEAR, EPI_SLOPE, ConvSite, Topology
+
+_topologies = {}
+_sites = {}
+
+
+def topology_for(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _topologies:
+        tp = Topology(idx)
+        tp.reserve_workspace(64 << 20)
+        _topologies[idx] = tp
+    return _topologies[idx]
+
+
+def _site(tp, L, K, U, D):
+    key = (tp.device.index, id(L), K, id(U), id(D))
+    if key not in _sites:
+        _sites[key] = (ConvSite(tp, L, K, U=U, D=D), L, U, D)   # keep the matrices alive: ids stay unique
+    return _sites[key][0]
+
+
+class _ChebFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, bias, site, tp, act):
+        N, M, Fin = x.shape
+        K = site.K
+        Fout = W.shape[1]
+        x = x.contiguous()
+        W = W.contiguous()
+        out = torch.empty(N, site.rows_out, Fout, device=x.device)
+        W3 = W.view(Fin, K, Fout)
+        terms = [dict(src=x, op=site.ops[k], F=Fin, src_rows=site.rows_in, src_stride=Fin, w=W3[:, k, :],
+                      w_stride=K * Fout) for k in range(K)]
+        b = bias.contiguous().view(-1) if bias is not None else None
+        E.cheb_call(tp, N, site.rows_out, Fout, terms, out, epilogue=EPI_LINEAR, act=act, bias=b)
+        ctx.save_for_backward(x, W, out)
+        ctx.site, ctx.tp, ctx.act, ctx.has_bias = site, tp, act, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, out = ctx.saved_tensors
+        site, tp, act = ctx.site, ctx.tp, ctx.act
+        N, _, Fin = x.shape
+        K, Fout = site.K, W.shape[1]
+        dy = dy.contiguous()
+        if act == ACT_NONE:
+            g = dy
+        else:
+            g = torch.empty_like(dy)
+            E.act_bwd(tp, dy, out, g, alpha=E.LEAKY_ALPHA if act == ACT_LEAKY else 0.0)
+        dW = torch.empty_like(W)
+        dW3 = dW.view(Fin, K, Fout)
+        for k in range(K):
+            E.cheb_dw(tp, N, site.rows_out, Fout, x, site.ops[k], Fin, site.rows_in, Fin, g, dW3[:, k, :], K * Fout)
+        db = None
+        if ctx.has_bias:
+            cs = torch.zeros(N, 1, Fout, device=x.device)
+            E.colsum(tp, g, N, site.rows_out, Fout, [-1], cs)
+            db = cs.sum(0).view(-1)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            Wt = torch.empty(Fout, K, Fin, device=x.device)
+            E.weight_transpose(tp, W, Fin, K, Fout, Wt)
+            dx = torch.empty_like(x)
+            terms = [dict(src=g, op=site.opsT[k], F=Fout, src_rows=site.rows_out, src_stride=Fout, w=Wt[:, k, :],
+                          w_stride=K * Fin) for k in range(K)]
+            E.cheb_call(tp, N, site.rows_in, Fin, terms, dx)
+        return dx, dW, db, None, None, None
+
+
+def chebyshev5(x, L, W, K, bias=None, activation=None, pool=None, unpool=None):
+    """Chebyshev graph convolution y = sum_k T_k(L~) x W[k::K] (lib/models.py:69-103); W is [Fin*K, Fout] with row
+    index fin*K + k.  Optional fusions: `unpool` U applied to x first (models.py:750,782), `bias`+`activation`
+    ('b1leakyrelu' | 'b1relu' | None, models.py:105-121) and `pool` D applied last (models.py:168)."""
+    tp = topology_for(x.device)
+    site = _site(tp, L, K, unpool, pool)
+    act = {None: ACT_NONE, "b1leakyrelu": ACT_LEAKY, "b1relu": ACT_RELU}[activation]
+    return _ChebFn.apply(x, W, bias, site, tp, act)
+
+
+class _ResampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ops, tp):
+        op, opT, rows_out, rows_in = ops
+        x = x.contiguous()
+        N, M, F = x.shape
+        y = torch.empty(N, rows_out, F, device=x.device)
+        E.resample(tp, op, x, y, N, rows_out, rows_in, F)
+        ctx.ops, ctx.tp = ops, tp
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        op, opT, rows_out, rows_in = ctx.ops
+        dy = dy.contiguous()
+        N, _, F = dy.shape
+        dx = torch.empty(N, rows_in, F, device=dy.device)
+        E.resample(ctx.tp, opT, dy, dx, N, rows_in, rows_out, F)
+        return dx, None, None
+
+
+_resamplers = {}
+
+
+def poolwT(x, S):
+    """Pool / unpool with a precomputed sampling matrix S [M', M] (lib/models.py:129-152)."""
+    import scipy.sparse as sp
+    tp = topology_for(x.device)
+    key = (tp.device.index, id(S))
+    if key not in _resamplers:
+        m = sp.csr_matrix(S)
+        _resamplers[key] = ((tp.add_operator(m), tp.add_operator(sp.csr_matrix(m.T)), m.shape[0], m.shape[1]), S)
+    return _ResampleFn.apply(x, _resamplers[key][0], tp)

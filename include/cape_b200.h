@@ -1,0 +1,182 @@
+/*
+ * cape_b200.h -- C ABI of libcape_b200.so: the B200 (sm_100a) implementation of CAPE's graph-conv hot path.
+ *
+ * The reference (qianlim/CAPE, TF-1.13) has no FFI; its operator seam is name-based dispatch on
+ * `base_model` (lib/models.py:16-17,58-62: filter='chebyshev5', pool/unpool='poolwT',
+ * activation='b1leakyrelu').  Each entry point below cites the reference op(s) it replaces.  A maintainer
+ * of the reference would bind these with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; cape_last_error() gives the message (thread-local);
+ *     no C++ exception crosses the boundary.
+ *   - all tensors are fp32, row-major, caller-owned DEVICE pointers; feature tensors are [N, rows, F] with F
+ *     contiguous (the reference's [N, M, F] placeholders, lib/models.py:272-282).
+ *   - every kernel is enqueued on the caller's `stream` (a cudaStream_t passed as void*); no hidden
+ *     synchronisation, no allocation inside hot calls (workspace is owned by the topology handle).
+ *   - the topology handle is immutable after the last cape_topology_add_operator() and may be shared
+ *     across streams of one device.
+ */
+#ifndef CAPE_B200_H
+#define CAPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAPE_ABI_VERSION 1
+#define CAPE_MAX_TERMS 8
+
+typedef struct cape_topology cape_topology;
+
+/* ---- error / version --------------------------------------------------------------------------- */
+const char* cape_last_error(void);
+int cape_abi_version(void);
+
+/* ---- topology handle: the fixed sparse operators ------------------------------------------------
+ * Replaces the graph-build-time conversion of scipy matrices into tf.SparseTensor
+ * (lib/models.py:74-79 for the rescaled Laplacian, :141-145 for D/U).
+ * An operator is a sparse [rows_out x rows_in] matrix in ELL form: idx/w are [rows_out, width] row-major,
+ * unused slots have idx = -1.  The host composes D * T_k(L~) * U offline (cape_b200/topology.py) so that
+ * pooling (lib/models.py:168) and unpooling (:750,:782) are folded into the conv's neighbour gather.
+ * The library also keeps each operator's row sums (the constants c_k of the condition broadcast,
+ * lib/models.py:813-832).  Returns the operator id (>=0) or <0. */
+int cape_topology_create(int device, cape_topology** out);
+void cape_topology_destroy(cape_topology* t);
+int cape_topology_add_operator(cape_topology* t, int rows_out, int rows_in, int width,
+                               const int32_t* idx_host, const float* w_host);
+/* split-K / partial-sum workspace used by the dW and GEMM kernels (bytes); call once before hot calls. */
+int cape_topology_reserve_workspace(cape_topology* t, int64_t bytes);
+
+/* ---- fused Chebyshev graph convolution ----------------------------------------------------------
+ * One term = one polynomial order (or one branch of a block):
+ *   A_t[n, r, f] = sum_j w_op[r, j] * src[n, idx_op[r, j], f]        (op < 0: identity, A_t = src)
+ *   acc0 (and acc1 if w2) += A_t[:, :, :F] @ W_t[:F, :ncols],   W_t element (f, c) = w[f * w_stride + c]
+ * plus the condition broadcast without materialising it (lib/models.py:591-594,606-609,663-666):
+ *   acc += rowsum(op)[r] * (cond[n, :C] @ Wc_t[:C, :ncols]),    Wc_t element (j, c) = wc[j * w_stride + c]
+ */
+typedef struct {
+  const float* src;   /* [N, src_rows, src_stride] */
+  int op;             /* operator id, or -1 for identity */
+  int F;              /* reduction length (channels of src used) */
+  int src_rows;
+  int src_stride;     /* floats between consecutive rows of src (>= F) */
+  int w_stride;       /* floats between consecutive reduction rows of w / wc */
+  int w2_stride;      /* same for w2 / wc2 */
+  const float* w;     /* -> accumulator 0 */
+  const float* w2;    /* -> accumulator 1 (NULL: none) */
+  const float* wc;    /* condition rows for accumulator 0 (NULL: none) */
+  const float* wc2;   /* condition rows for accumulator 1 (NULL: none) */
+} cape_term;
+
+enum {
+  CAPE_EPI_LINEAR = 0,   /* out = act(acc0 + bias)                       chebyshev5 + b1leakyrelu, models.py:69-109 */
+  CAPE_EPI_AFFINE = 1,   /* out = acc1 + relu(acc0); out2 = relu(acc0)   res_block_affine, models.py:776-793 */
+  CAPE_EPI_SLOPE = 2,    /* out = acc0 * (aux > 0 ? 1 : alpha)           backward through (leaky-)ReLU given its output */
+  CAPE_EPI_DUALMASK = 3  /* out = acc0; out2 = acc0 * (aux > 0)          backward into an affine block's output */
+};
+enum { CAPE_ACT_NONE = 0, CAPE_ACT_LEAKY = 1, CAPE_ACT_RELU = 2 };
+
+typedef struct {
+  int N, rows_out, ncols;
+  int nterms;
+  cape_term terms[CAPE_MAX_TERMS];
+  const float* cond;   /* [N, C] condition embedding (NULL: none) */
+  int C;
+  int epilogue;        /* CAPE_EPI_* */
+  int act;             /* CAPE_ACT_* (LINEAR only) */
+  float alpha;         /* negative slope (LEAKY: 0.2 = tf.nn.leaky_relu default; SLOPE epilogue) */
+  const float* bias;   /* [ncols] or [rows_out, ncols] (NULL: none) */
+  int bias_per_row;    /* 1: per-vertex bias (decoder outputs, models.py:615) */
+  const float* aux;    /* [N, rows_out, ncols] (SLOPE / DUALMASK) */
+  float* out;          /* [N, rows_out, ncols] */
+  float* out2;         /* [N, rows_out, ncols] or NULL */
+} cape_conv_args;
+
+/* Forward of chebyshev5 (+poolwT, +b1leakyrelu, +fit_cond_dim/concat) -- lib/models.py:69-103,105-109,
+ * 129-152,813-832; also the data-gradient pass (same form with transposed operators and weights). */
+int cape_cheb_fwd(cape_topology* t, const cape_conv_args* a, void* stream);
+
+/* Weight gradient of one term:  dw[f * dw_stride + c] (+)= sum_{n,r} A_t[n,r,f] * g[n,r,c]
+ * (TF autodiff of lib/models.py:102; deterministic split-K through the topology workspace). */
+typedef struct {
+  int N, rows_out, ncols;
+  const float* src; int op; int F; int src_rows; int src_stride;
+  const float* g;      /* [N, rows_out, ncols] */
+  float* dw; int dw_stride;
+  int accumulate;      /* 0: overwrite, 1: add */
+} cape_dw_args;
+int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* stream);
+
+/* Per-sample weighted column sums: out[n, j, c] = sum_r rowsum(op_j)[r] * g[n, r, c]  (op_j < 0: ones).
+ * Gives the bias gradient (models.py:105-109) and the gradient of the condition broadcast
+ * (the reduce-over-vertices implied by fit_cond_dim, models.py:829-830).  out must be zeroed by the caller. */
+int cape_colsum(cape_topology* t, const float* g, int N, int rows, int ncols,
+                const int* ops, int nops, float* out, void* stream);
+
+/* ---- dense layers (tf.layers.dense, lib/models.py:496,506,510,557,560,582) ------------------------
+ * C[M,N] = act(alpha * A.B + bias) (+ beta * C);  A(m,k) = a[m*a_rs + k*a_cs], B(k,n) = b[k*b_rs + n*b_cs]. */
+int cape_gemm(cape_topology* t, int M, int N, int K,
+              const float* a, int64_t a_rs, int64_t a_cs,
+              const float* b, int64_t b_rs, int64_t b_cs,
+              float* c, int64_t c_rs,
+              const float* bias, int act, float leaky_alpha, float alpha, float beta, void* stream);
+
+/* Stand-alone mesh resampling y[n] = S x[n] (poolwT, lib/models.py:129-152) for an operator registered in the
+ * topology (D: row selection, U: 3-tap barycentric); the backward pass is the same call with S^T. */
+int cape_resample(cape_topology* t, int op, const float* x, float* y, int N, int rows_out, int rows_in, int F,
+                  void* stream);
+
+/* Weight re-layout for the data-gradient pass of chebyshev5: wt[(c*K + k)*Fin + f] = w[(f*K + k)*Fout + c]
+ * for f < Fin (rows of w beyond Fin*K -- the condition channels -- are not touched). */
+int cape_cheb_weight_transpose(const float* w, int Fin, int K, int Fout, float* wt, void* stream);
+
+/* ---- elementwise helpers ------------------------------------------------------------------------ */
+/* g = dy * (y > 0 ? 1 : alpha)   (backward of leaky_relu given its output) */
+int cape_act_bwd(const float* dy, const float* y, float* g, int64_t n, float alpha, void* stream);
+/* y += a * x */
+int cape_axpy(float* y, const float* x, float a, int64_t n, void* stream);
+/* z = mean + sqrt(exp(logvar)) * eps  (vae_sampling, lib/models.py:193-196); z written with row stride z_stride */
+int cape_vae_sample_fwd(const float* mean, const float* logvar, const float* eps, float* z, int z_stride,
+                        int N, int nz, void* stream);
+/* dmean = dz + kl_scale*mean/N ; dlogvar = dz*eps*0.5*sqrt(exp(lv)) + kl_scale*0.5*(exp(lv)-1)/N */
+int cape_vae_sample_bwd(const float* dz, int dz_stride, const float* mean, const float* logvar, const float* eps,
+                        float* dmean, float* dlogvar, int N, int nz, float kl_scale, void* stream);
+
+/* ---- losses (CAPE.loss, lib/models.py:354-416; losses.edge_loss_calc, lib/losses.py:9-25) ----------
+ * Reconstruction L1 (mean |pred-gt|), edge loss (mean over edges of ||(p_a-p_b)-(g_a-g_b)||_2; the
+ * template added at models.py:375 cancels), KL (mean_n -0.5*sum(1+lv-mu^2-e^lv)); writes
+ * losses[0..2] = {recon, edge, kl} (unweighted) and ACCUMULATES lambda-weighted gradients into dpred.
+ * nbr_op: id of the level-0 adjacency operator (its idx table lists each vertex's neighbours). */
+int cape_recon_losses(cape_topology* t, int nbr_op, const float* pred, const float* gt, int N, int rows,
+                      float lambda_l1, float lambda_edge, int n_edges,
+                      const float* mean, const float* logvar, int nz,
+                      float* dpred, float* losses, void* stream);
+/* Sigmoid cross-entropy with a constant label (tf.nn.sigmoid_cross_entropy_with_logits, models.py:387-389):
+ * loss[0] += mean(bce(logits, label)); dlogits = scale * d mean(bce)/dlogits  */
+int cape_bce_logits(const float* logits, int64_t n, float label, float scale, float* dlogits, float* loss,
+                    void* stream);
+
+/* ---- optimiser (CAPE.training, lib/models.py:419-474) -----------------------------------------------
+ * sumsq[0] = sum(g^2) (sumsq must be zeroed);  then
+ * coef = clip / max(sqrt(sumsq), clip) (tf.clip_by_global_norm), a = momentum*a + coef*g, w -= lr*a
+ * (tf.train.MomentumOptimizer, non-Nesterov).  lr is read from device memory (no host sync). */
+int cape_sumsq(const float* g, int64_t n, float* sumsq, void* stream);
+int cape_sgd_clip_update(float* w, const float* g, float* mom, int64_t n, const float* sumsq, float clip_norm,
+                         const float* lr_dev, float momentum, void* stream);
+
+/* ---- group norm (CAPE.gn, lib/models.py:681-712) + ReLU, for the non-affine decoder blocks ------------
+ * x: [N, rows, C], G groups of C/G contiguous channels; stats over (C/G x rows) per (n, g), biased variance,
+ * y = relu(gamma*(x-mean)*rstd + beta).  stats: [N, G, 2] = (mean, rstd), saved for the backward pass.
+ * Backward: dy is the gradient w.r.t. y (after the ReLU); dgamma/dbeta are ACCUMULATED (zero them first).
+ * Both use the topology workspace (N*G*2 doubles) for fp64 group sums. */
+int cape_gn_relu_fwd(cape_topology* t, const float* x, int N, int rows, int C, int G, float eps,
+                     const float* gamma, const float* beta, float* y, float* stats, void* stream);
+int cape_gn_relu_bwd(cape_topology* t, const float* x, const float* y, const float* dy, int N, int rows, int C, int G,
+                     const float* gamma, const float* stats, float* dx, float* dgamma, float* dbeta, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAPE_B200_H */

@@ -1,0 +1,318 @@
+"""CPU oracle for CAPE's graph-conv hot path -- TEST INFRASTRUCTURE ONLY.
+
+A torch-CPU (autograd) restatement of the reference's TF-1.13 graph, function by function, citing
+/root/reference/lib/models.py.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference leg may import this file; the product path (cape_b200/) never does.
+
+PARITY UNPINNED BY THE REFERENCE: the reference ships no tests or golden vectors and its
+arithmetic lives in tensorflow-gpu==1.13.2 (requirements.txt:11), which cannot be installed here.  The
+oracle is pinned instead by (i) the reference's own importable host code (lib/mesh_sampling.py
+laplacian/rescale_L run in the build container; vectors committed under tests/golden/ by
+tests/golden/make_golden.py), (ii) an independent float64 dense-polynomial formulation of the
+Chebyshev conv (oracle/np_ops.py), (iii) a literal numpy/scipy transcription of the op bodies
+(oracle/np_ops.py) that follows the reference's transposes/reshapes line by line.
+
+TF-default semantics encoded here (TF-1.13 docs): tf.nn.leaky_relu alpha=0.2; tf.layers.dense y=xW+b;
+tf.losses.* Reduction.MEAN over all elements; l2_regularizer(s)(w) = s*sum(w^2)/2; MomentumOptimizer
+a <- m*a + g, w <- w - lr*a; clip_by_global_norm scale = clip/max(norm, clip);
+exponential_decay(staircase=True) uses floor.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+
+# --------------------------------------------------------------------------------------------------
+# host-side operator prep (lib/mesh_sampling.py:10-38)
+# --------------------------------------------------------------------------------------------------
+def laplacian(W, normalized=True):
+    """lib/mesh_sampling.py:10-29."""
+    d = W.sum(axis=0)
+    if not normalized:
+        D = sp.diags(np.asarray(d).squeeze(), 0)
+        L = D - W
+    else:
+        d = d + np.spacing(np.array(0, W.dtype))
+        d = 1 / np.sqrt(d)
+        D = sp.diags(np.asarray(d).squeeze(), 0)
+        I = sp.identity(d.size, dtype=W.dtype)
+        L = I - D * W * D
+    return sp.csr_matrix(L)
+
+
+def rescale_L(L, lmax=2):
+    """lib/mesh_sampling.py:31-38 (on a copy, as chebyshev5 does at models.py:74)."""
+    L = sp.csr_matrix(L, copy=True)
+    M = L.shape[0]
+    I = sp.identity(M, format="csr", dtype=L.dtype)
+    L /= lmax / 2        # in place (mesh_sampling.py:36-37): keeps the fp32 dtype
+    L -= I
+    return sp.csr_matrix(L)
+
+
+def _to_torch_sparse(m, dtype):
+    m = sp.coo_matrix(m)
+    idx = torch.from_numpy(np.vstack([m.row, m.col]).astype(np.int64))
+    val = torch.from_numpy(m.data.astype(np.float64)).to(dtype)
+    return torch.sparse_coo_tensor(idx, val, m.shape).coalesce()
+
+
+class Oracle:
+    """Functional mirror of base_model + CAPE (lib/models.py:13-832).
+
+    params: dict name -> torch tensor (requires_grad as the caller wishes), names are the reference's TF
+    variable names ('generator/encoder/encoder_conv1/weights', ...).
+    """
+
+    def __init__(self, L, D, U, L_d, D_d, cfg, dtype=torch.float32):
+        self.cfg = cfg
+        self.dtype = dtype
+        self.F = list(cfg["F"])
+        self.K = list(cfg["K"])
+        self.Kd = cfg["Kd"]
+        self.p = [int(l.shape[0]) for l in L]
+        # models.py:74-79: rescaled Laplacian as a sparse tensor (rescale done per call there; hoisted here)
+        self.Lt = [_to_torch_sparse(rescale_L(l, lmax=2), dtype) for l in L]
+        self.Lt_d = [_to_torch_sparse(rescale_L(l, lmax=2), dtype) for l in L_d]
+        self.Dm = [_to_torch_sparse(d, dtype) for d in D]
+        self.Um = [_to_torch_sparse(u, dtype) for u in U]
+        self.Dm_d = [_to_torch_sparse(d, dtype) for d in D_d]
+        rd = cfg.get("reduce_dim", 64)
+        self.reduce_rate = self.F[-1] // rd if rd > 0 else 1  # models.py:254-257
+        self.reduce_dim = rd
+
+    # ---- ops ---------------------------------------------------------------------------------------
+    def chebyshev5(self, x, Lt, W, K):
+        """models.py:69-103, including its layout shuffles."""
+        N, M, Fin = x.shape
+        x0 = x.permute(1, 2, 0).reshape(M, Fin * N)           # :81-82
+        xs = [x0]
+        if K > 1:
+            x1 = torch.sparse.mm(Lt, x0)                        # :91
+            xs.append(x1)
+        for _ in range(2, K):
+            x2 = 2 * torch.sparse.mm(Lt, x1) - x0               # :94
+            xs.append(x2)
+            x0, x1 = x1, x2
+        xk = torch.stack(xs, 0).reshape(K, M, Fin, N)           # :97
+        xk = xk.permute(3, 1, 2, 0).reshape(N * M, Fin * K)     # :98-99
+        return (xk @ W).reshape(N, M, -1)                       # :102-103
+
+    def b1leakyrelu(self, x, b):
+        """models.py:105-109 (tf.nn.leaky_relu default alpha=0.2)."""
+        return torch.nn.functional.leaky_relu(x + b.reshape(1, 1, -1), 0.2)
+
+    def poolwT(self, x, S):
+        """models.py:129-152."""
+        N, M, Fin = x.shape
+        Mp = S.shape[0]
+        xt = x.permute(1, 2, 0).reshape(M, Fin * N)
+        xt = torch.sparse.mm(S, xt)
+        return xt.reshape(Mp, Fin, N).permute(2, 0, 1)
+
+    def fit_cond_dim(self, x, y):
+        """models.py:813-832."""
+        return y.reshape(x.shape[0], 1, -1) * torch.ones(x.shape[0], x.shape[1], y.shape[-1], dtype=x.dtype)
+
+    def dense(self, x, P, scope, act=None):
+        y = x @ P[scope + "/dense/kernel"] + P[scope + "/dense/bias"]
+        if act == "leaky":
+            y = torch.nn.functional.leaky_relu(y, 0.2)
+        return y
+
+    def gn(self, x, gamma, beta, G=32, eps=1e-5):
+        """models.py:693-709."""
+        xt = x.permute(0, 2, 1)
+        N, C, V = xt.shape
+        G = min(G, C)
+        xg = xt.reshape(N, G, C // G, V)
+        mean = xg.mean(dim=(2, 3), keepdim=True)
+        var = ((xg - mean) ** 2).mean(dim=(2, 3), keepdim=True)
+        xg = (xg - mean) / torch.sqrt(var + eps)
+        out = xg.reshape(N, C, V) * gamma.reshape(1, C, 1) + beta.reshape(1, C, 1)
+        return out.permute(0, 2, 1)
+
+    # ---- network -----------------------------------------------------------------------------------
+    def condition(self, y, P, name, nz_cond, nlayers):
+        """models.py:479-511."""
+        scope = "condition_%s" % name
+        y_dim = y.shape[-1]
+        if nlayers == 1:
+            return self.dense(y, P, scope + "/fc1")
+        y = self.dense(y, P, scope + "/fc1", act="leaky")
+        return self.dense(y, P, scope + "/fc2")
+
+    def cond_embeddings(self, cond, cond2, P):
+        """models.py:284-286: pose net has nlayers=2 hard-coded, clothing net n_layer_cond."""
+        y = self.condition(cond, P, "pose", self.cfg["nz_cond"], 2)
+        y2 = self.condition(cond2, P, "clo_label", self.cfg["nz_cond2"], self.cfg.get("n_layer_cond", 1))
+        return y, y2
+
+    def encoder(self, x, P):
+        """models.py:514-561 with use_res_block=0, cond_encoder=0 (all shipped configs)."""
+        s = "generator/encoder/"
+        for i in range(len(self.F)):
+            sc = s + "encoder_conv%d" % (i + 1)
+            x = self.chebyshev5(x, self.Lt[i], P[sc + "/weights"], self.K[i])     # cnp :164
+            x = self.b1leakyrelu(x, P[sc + "/bias"])                              # :166
+            x = self.poolwT(x, self.Dm[i])                                        # :168
+        if self.reduce_dim > 0:
+            x = self.chebyshev5(x, self.Lt[-1], P[s + "1x1-conv/weights"], 1)      # :551
+        x = x.reshape(x.shape[0], -1)                                             # :554
+        z_mean = self.dense(x, P, s + "fc_mean")
+        z_logvar = self.dense(x, P, s + "fc_var")
+        return z_mean, z_logvar
+
+    def res_block_affine(self, x, i, P, scope):
+        """models.py:776-793."""
+        x = self.poolwT(x, self.Um[-i - 1])
+        Lt = self.Lt[-i - 2]
+        x_gc = self.chebyshev5(x, Lt, P[scope + "/graph_conv/weights"], self.K[-i - 1])
+        x_gc = torch.relu(x_gc)
+        x_aff = self.chebyshev5(x, Lt, P[scope + "/affine/weights"], 1)
+        return x_aff + x_gc
+
+    def res_block_decoder(self, x_in, i, P, scope):
+        """models.py:744-774."""
+        x_unpooled = self.poolwT(x_in, self.Um[-i - 1])
+        Lt = self.Lt[-i - 2]
+        Fo = self.F[-i - 1]
+        x = torch.relu(self.gn(x_unpooled, P[scope + "/group_norm/gamma"], P[scope + "/group_norm/beta"]))
+        x = self.chebyshev5(x, Lt, P[scope + "/graph_linear_1/weights"], 1)
+        x = torch.relu(self.gn(x, P[scope + "/group_norm_1/gamma"], P[scope + "/group_norm_1/beta"]))
+        x = self.chebyshev5(x, Lt, P[scope + "/graph_conv/weights"], self.K[-i - 1])
+        x = torch.relu(self.gn(x, P[scope + "/group_norm_2/gamma"], P[scope + "/group_norm_2/beta"]))
+        x = self.chebyshev5(x, Lt, P[scope + "/graph_linear_2/weights"], 1)
+        if x_unpooled.shape[-1] != Fo:
+            x_unpooled = self.chebyshev5(x_unpooled, Lt, P[scope + "/graph_linear_input/weights"], 1)
+        return x + x_unpooled
+
+    def decoder_cond_vert(self, z_total, y, y2, P):
+        """models.py:564-617 with use_res_block_dec=1."""
+        s = "generator/decoder/"
+        x = self.dense(z_total, P, s + "fc1", act="leaky")                       # :582
+        x = x.reshape(x.shape[0], self.p[-1], -1)                                # :584
+        if self.reduce_dim > 0:
+            x = self.chebyshev5(x, self.Lt[-1], P[s + "1x1-conv/weights"], 1)     # :588
+        x = torch.cat([x, self.fit_cond_dim(x, y), self.fit_cond_dim(x, y2)], -1)  # :591-594
+        for i in range(len(self.F)):
+            if self.cfg["affine"]:
+                x = self.res_block_affine(x, i, P, s + "decoder_resblock_affine%d" % (i + 1))
+            else:
+                x = self.res_block_decoder(x, i, P, s + "decoder_resblock_cmr%d" % (i + 1))
+            x = torch.cat([x, self.fit_cond_dim(x, y), self.fit_cond_dim(x, y2)], -1)  # :606-609
+        x = self.chebyshev5(x, self.Lt[0], P[s + "outputs/weights"], self.K[0])   # :612
+        return x + P[s + "outputs/bias"]                                          # :615-616
+
+    def generator(self, x, y, y2, eps, P):
+        """models.py:620-645; eps is vae_sampling's random_normal made explicit (:194)."""
+        z_mean, z_logvar = self.encoder(x, P)
+        z = z_mean + torch.sqrt(torch.exp(z_logvar)) * eps                        # :195
+        z_total = torch.cat([z, y, y2], 1)                                        # :641
+        return self.decoder_cond_vert(z_total, y, y2, P), z_mean, z_logvar
+
+    def discriminator(self, x, y, y2, P):
+        """models.py:648-678 (pred_map uses self.poly_order[-1], not Kd: :676)."""
+        x = torch.cat([x, self.fit_cond_dim(x, y), self.fit_cond_dim(x, y2)], -1)
+        for i in range(len(self.Dm_d)):
+            sc = "discriminator/shared/conv%d" % (i + 1)
+            x = self.chebyshev5(x, self.Lt_d[i], P[sc + "/weights"], self.Kd)     # cnp_d :803
+            x = self.b1leakyrelu(x, P[sc + "/bias"])
+            x = self.poolwT(x, self.Dm_d[i])
+        return self.chebyshev5(x, self.Lt_d[-1], P["discriminator/prediction_map/weights"], self.K[-1])
+
+    # ---- losses (models.py:354-416, losses.py:9-25) ---------------------------------------------------
+    @staticmethod
+    def bce_logits(l, t):
+        return (torch.clamp(l, min=0) - l * t + torch.log1p(torch.exp(-torch.abs(l)))).mean()
+
+    def losses(self, x_hat, gt, z_mean, z_logvar, d_real, d_fake, P, edges, smooth=0.1):
+        cfg = self.cfg
+        recon = (x_hat - gt).abs().mean()                                          # :358-360
+        latent = (-0.5 * (1 + z_logvar - z_mean ** 2 - torch.exp(z_logvar)).sum(1)).mean()  # :371-372
+        e0 = torch.as_tensor(edges[:, 0].astype(np.int64))
+        e1 = torch.as_tensor(edges[:, 1].astype(np.int64))
+        ev = lambda a: a[:, e0] - a[:, e1]
+        edge = torch.linalg.norm(ev(x_hat) - ev(gt), dim=-1).mean()                # losses.py:21-25
+        reg = cfg["regularization"]
+        # models.py:378: regularization * sum(l2_regularizer(regularization)(kernel)) over 'generator' dense kernels
+        reg_g = 0.0
+        for name in ("generator/encoder/fc_mean", "generator/encoder/fc_var", "generator/decoder/fc1"):
+            reg_g = reg_g + reg * (P[name + "/dense/kernel"] ** 2).sum() / 2
+        reg_g = reg * reg_g
+        out = OrderedDict(recon=recon, latent=latent, edge=edge, reg_g=reg_g)
+        if d_fake is not None:
+            out["gan_g"] = self.bce_logits(d_fake, 1 - smooth)                     # :387
+            out["loss_g"] = (out["gan_g"] * cfg["lambda_gan"] + recon * cfg["lambda_recon"] + edge * cfg["lambda_edge"]
+                             + latent * cfg["lambda_latent"] + reg_g)              # :393-395
+            if d_real is not None:
+                out["gan_d"] = self.bce_logits(d_real, 1 - smooth) + self.bce_logits(d_fake, smooth)  # :388-390
+                out["loss_d"] = out["gan_d"] * cfg["lambda_gan"]                   # :397 (reg_d = 0: no dense in D)
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# one training update (models.py:419-474)
+# --------------------------------------------------------------------------------------------------
+def lr_schedule(cfg, step):
+    """models.py:426-442.  `step` = global_step value read when the update runs."""
+    lr_g = cfg["lr"]
+    lr_d = cfg["lr"] * cfg["lr_scaler"]
+    ds = int(cfg["decay_steps"])
+    if cfg.get("lr_warmup", False):
+        warm = int(cfg["decay_steps"] * 8)
+        if step < warm:
+            return lr_g * step / warm, lr_d * step / warm
+        k = math.floor((step - warm) / ds)
+    else:
+        k = math.floor(step / ds)
+    return lr_g * cfg["decay_rate"] ** k, lr_d * cfg["decay_rate"] ** k
+
+
+def g_var_names(P, optim_condnet=True):
+    return [k for k in P if k.startswith("generator") or (optim_condnet and "condition" in k)]
+
+
+def d_var_names(P):
+    return [k for k in P if k.startswith("discriminator")]
+
+
+def train_update(oracle, P, mom, batch, step, edges, ref_compat=False, clip=5.0):
+    """One optimiser application = what a single sess.run(op_train_*) does (models.py:460-472).
+
+    batch: dict with x_g, gt, cond_g, cond2_g, eps, x_d, cond_d, cond2_d (torch tensors).
+    ref_compat=True reproduces models.py:466 (the discriminator 'gradients' are its clipped variables);
+    False applies the real discriminator gradients (clipped by their own global norm).
+    Updates P and mom in place (plain tensors), returns the loss dict.
+    """
+    cfg = oracle.cfg
+    Pg = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
+    y, y2 = oracle.cond_embeddings(batch["cond_g"], batch["cond2_g"], Pg)
+    yd, y2d = oracle.cond_embeddings(batch["cond_d"], batch["cond2_d"], Pg)
+    x_hat, zm, zl = oracle.generator(batch["x_g"], y, y2, batch["eps"], Pg)
+    d_real = oracle.discriminator(batch["x_d"], yd, y2d, Pg)
+    d_fake = oracle.discriminator(x_hat, y, y2, Pg)
+    L = oracle.losses(x_hat, batch["gt"], zm, zl, d_real, d_fake, Pg, edges)
+    gn = g_var_names(Pg, cfg.get("optim_condnet", True))
+    dn = d_var_names(Pg)
+    grads_g = torch.autograd.grad(L["loss_g"], [Pg[k] for k in gn], retain_graph=True, allow_unused=True)
+    grads_g = [g if g is not None else torch.zeros_like(Pg[k]) for g, k in zip(grads_g, gn)]
+    if ref_compat:
+        grads_d = [Pg[k].detach() for k in dn]                                     # models.py:466
+    else:
+        grads_d = torch.autograd.grad(L["loss_d"], [Pg[k] for k in dn], allow_unused=True)
+        grads_d = [g if g is not None else torch.zeros_like(Pg[k]) for g, k in zip(grads_d, dn)]
+    lr_g, lr_d = lr_schedule(cfg, step)
+    for names, grads, lr in ((gn, grads_g, lr_g), (dn, grads_d, lr_d)):
+        norm = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).item()
+        coef = clip / max(norm, clip)
+        for k, g in zip(names, grads):
+            mom[k] = cfg["momentum"] * mom[k] + coef * g.detach()
+            P[k] = P[k] - lr * mom[k]
+    out = {k: float(v) for k, v in L.items()}
+    out["grads"] = {k: g.detach() for k, g in zip(gn + dn, list(grads_g) + list(grads_d))}
+    out["x_hat"] = x_hat.detach()
+    return out

@@ -1,0 +1,89 @@
+"""Host-side topology: fixtures, Laplacians vs the reference's own code (golden), operator algebra."""
+import os
+
+import numpy as np
+import scipy.sparse as sp
+
+from cape_b200 import topology as T
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_fixture_invariants(hierarchy):
+    """Facts of SURVEY.md section 0 / Appendix B that the kernels rely on."""
+    h = hierarchy
+    assert h["p"] == [6890, 6890, 3445, 3445, 1723, 1723, 862, 862, 862]
+    assert [l.shape[0] for l in h["L_d"]] == [6890, 3445, 1723, 862, 431]
+    for d in h["D"] + h["D_d"]:
+        d = sp.csr_matrix(d)
+        assert (np.diff(d.indptr) == 1).all() and (d.data == 1.0).all()      # pure row selection
+        assert (np.diff(d.indices) > 0).all()                                # increasing columns
+    for u in h["U"]:
+        assert (np.diff(sp.csr_matrix(u).indptr) == 3).all()                 # 3-tap barycentric
+    for i in (0, 2, 4, 6, 7):
+        assert T.is_identity(h["D"][i], tol=0) and T.is_identity(h["U"][i], tol=1e-6)
+    rs = np.asarray(h["U"][5].sum(1)).ravel()
+    assert rs.min() < 0.95 and rs.max() > 1.02                               # row sums are NOT 1
+    e = T.smpl_edges()
+    assert e.shape == (20664, 2) and (e[:, 0] < e[:, 1]).all()
+
+
+def test_laplacian_matches_reference_golden(hierarchy):
+    """laplacian + rescale_L reproduce the reference's lib/mesh_sampling.py output bit for bit."""
+    z = np.load(os.path.join(GOLD, "lap_golden.npz"))
+    for kind, Ls in (("for_demo", hierarchy["L"]), ("ds2", hierarchy["L_d"])):
+        for i, L in enumerate(Ls):
+            L = sp.csr_matrix(L)
+            L.sort_indices()
+            assert L.dtype == np.float32
+            assert np.array_equal(L.indices, z["%s.L.%d.indices" % (kind, i)])
+            assert np.array_equal(L.data, z["%s.L.%d.data" % (kind, i)])
+            Lt = T.rescale_L(L, lmax=2)
+            Lt.sort_indices()
+            assert Lt.dtype == np.float32
+            assert np.array_equal(Lt.indptr, z["%s.Lt.%d.indptr" % (kind, i)])
+            assert np.array_equal(Lt.indices, z["%s.Lt.%d.indices" % (kind, i)])
+            assert np.array_equal(Lt.data, z["%s.Lt.%d.data" % (kind, i)])
+            assert abs(Lt.diagonal()).max() == 0.0                           # zero diagonal (lmax = 2)
+
+
+def test_rescale_does_not_modify_input(hierarchy):
+    L = hierarchy["L"][0]
+    before = L.copy()
+    T.rescale_L(L)
+    assert (L != before).nnz == 0
+
+
+def _apply_ell(idx, w, x):
+    y = np.zeros((idx.shape[0],) + x.shape[1:], np.float64)
+    for j in range(idx.shape[1]):
+        ok = idx[:, j] >= 0
+        y[ok] += w[ok, j, None].astype(np.float64) * x[idx[ok, j]]
+    return y
+
+
+def test_composed_operator_equals_sequential(hierarchy):
+    """D . T_k(L~) . U as one ELL gather == unpool -> Chebyshev recurrence -> pool."""
+    h = hierarchy
+    rng = np.random.RandomState(0)
+    L, U, D = h["L"][2], h["U"][3], h["D"][3]           # unpool 1723 -> 3445, conv at 3445, pool -> 1723
+    x = rng.normal(size=(U.shape[1], 5))
+    Lt = T.rescale_L(L).astype(np.float64)
+    z = U.astype(np.float64) @ x
+    t0, t1 = z, Lt @ z
+    t2 = 2 * (Lt @ t1) - t0
+    Ts = T.cheb_polynomials(L, 3)
+    for k, ref in enumerate((t0, t1, t2)):
+        m = T.compose(D, Ts[k], U)
+        idx, w = T.to_ell(m)
+        got = _apply_ell(idx, w, x)
+        want = D.astype(np.float64) @ ref
+        assert np.abs(got - want).max() < 1e-5 * max(1.0, np.abs(want).max())
+        # left-packed, -1 padded
+        valid = idx >= 0
+        assert (valid[:, :-1] >= valid[:, 1:]).all()
+
+
+def test_adjacency_ell_counts_edges(hierarchy):
+    idx, _ = T.adjacency_ell(hierarchy["L"][0])
+    assert (idx >= 0).sum() == 2 * 20664
