@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- meshes/sec of the CAPE-affineconv nz64 VAE+GAN training step on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W     (CPU arm: the oracle port, host threads)
+
+Workload (BASELINE.json configs[2], the config the metric "meshes/sec fwd+bwd CAPE-affineconv nz64" is quoted on;
+configs[3] = the same step data-parallel): full train step = condition nets + encoder + decoder + discriminator
+(real+fake) forward, all backward passes, losses, global-norm clip + momentum update of both players; batch 64
+meshes per GPU (weak scaling), synthetic [N,6890,3] offsets, random-init weights, fp32 throughout.
+
+One JSON line on stdout (rank 0).  `value`: device-resident inputs, CUDA-event timing of exactly K steps.
+`e2e`: the same step through the public API with pinned HOST inputs copied in and the loss copied out every step.
+`roofline`: the dominant kernel family (the fused ELL-gather Chebyshev conv) -- algorithmic bytes
+over its launches in one step / their CUDA-event time, against the measured HBM peak.  `cpu_baseline`: the
+oracle (torch-CPU port of the reference graph) on a bounded sample, timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "meshes/sec fwd+bwd CAPE-affineconv nz64"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cape_b200", choices=["cape_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="meshes per GPU per step")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--cpu-sample", type=int, default=4, help="meshes per step of the CPU arm / cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    return ap.parse_args()
+
+
+def config_and_hierarchy():
+    from cape_b200 import topology as T
+    from cape_b200.params import NZ64_AFFINE
+    L, D, U, p, L_d, D_d, _ = T.load_graph_mtx(load_for_demo=True)
+    cfg = dict(NZ64_AFFINE, decay_steps=100)
+    return cfg, dict(L=L, D=D, U=U, p=p, L_d=L_d, D_d=D_d)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference graph (the reference's TF-1.13 CPU path cannot run here)
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_rate(n_sample, steps, warmup):
+    """meshes/sec of oracle.train_update (same work as the GPU step) with all host threads."""
+    import torch
+    from oracle import cape_oracle as O
+    from cape_b200 import topology as T
+    from cape_b200.params import init_params, param_specs
+    from cape_b200.synthetic import make_batch
+    cfg, h = config_and_hierarchy()
+    torch.set_num_threads(os.cpu_count() or 1)
+    specs = param_specs(cfg, [l.shape[0] for l in h["L"]], [l.shape[0] for l in h["L_d"]])
+    params = init_params(specs, cfg["seed"])
+    o = O.Oracle(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], cfg)
+    P = {k: torch.from_numpy(v) for k, v in params.items()}
+    mom = {k: torch.zeros_like(v) for k, v in P.items()}
+    b = {k: torch.from_numpy(v) for k, v in make_batch(n_sample, cfg["nz"], seed=cfg["seed"]).items()}
+    edges = T.smpl_edges()
+    for i in range(warmup):
+        O.train_update(o, P, mom, b, 1000 + i, edges)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        O.train_update(o, P, mom, b, 2000 + i, edges)
+    dt = time.perf_counter() - t0
+    return n_sample * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, sps, threads = cpu_port_rate(args.cpu_sample, args.steps, args.warmup)
+    sample = "%d meshes per step (full VAE+GAN update: enc+dec+2xdisc fwd/bwd+clip+momentum), torch-CPU oracle port" % args.cpu_sample
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "meshes/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "CAPE-affineconv nz64_pose32_clotype32 full VAE+GAN train step",
+                       "meshes_per_step": args.cpu_sample,
+                       "note": "reference TF-1.13 cannot be installed (no tensorflow wheel, py3.12); this is the oracle port "
+                               "of lib/models.py on the host cores"},
+            "cpu_baseline": {"value": rate, "unit": "meshes/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from cape_b200 import _lib
+    from cape_b200 import engine as E
+    from cape_b200.network import CapeNetwork
+    from cape_b200.synthetic import make_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (impl cape_b200) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    cfg, h = config_and_hierarchy()
+    N = args.batch
+    net = CapeNetwork(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], cfg, N, device=local)
+    hb = {k: torch.from_numpy(v).pin_memory() for k, v in make_batch(N, cfg["nz"], seed=cfg["seed"] + rank).items()}
+    order = ("x_g", "cond_g", "cond2_g", "eps", "x_d", "cond_d", "cond2_d")
+    h2d_bytes = sum(hb[k].numel() * 4 for k in order)
+
+    def stage():
+        net.set_inputs(*[hb[k] for k in order])
+
+    allreduce = None
+    if world > 1:
+        def allreduce(gg, gd):
+            dist.all_reduce(gg, op=dist.ReduceOp.AVG)
+            dist.all_reduce(gd, op=dist.ReduceOp.AVG)
+
+    use_graph = not args.no_graph
+    stage()
+    c0 = lib.cape_launch_count()
+    net.train_step(step=0, allreduce=allreduce)            # eager step: lazy inits + launch count of one step
+    torch.cuda.synchronize()
+    launches_per_step = lib.cape_launch_count() - c0
+    graph_note = "eager"
+    if use_graph:
+        try:
+            net.capture_graphs()
+            graph_note = "2 CUDA graphs/step (fwd+bwd, update)"
+        except Exception as e:                              # pragma: no cover
+            use_graph = False
+            graph_note = "eager (graph capture failed: %s)" % str(e)[:80]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        net.train_step(step=i, allreduce=allreduce, use_graph=use_graph)
+
+    # ---- device-resident timing ----------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step(1 + i)
+    barrier()
+    clocks = Clocks(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step(100 + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if clocks else None
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # ---- end to end: pinned host inputs in, loss out, every step ----------------------------------------------------
+    d2h_bytes = net.losses.numel() * 4
+    for i in range(2):
+        stage(); step(300 + i); net.losses.cpu()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        stage()
+        step(400 + i)
+        loss_host = net.losses.cpu()                      # D2H of the step's loss terms (synchronises)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_meshes = N * world * args.steps
+    line = {"metric": METRIC, "value": total_meshes / (ms * 1e-3), "unit": "meshes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "CAPE-affineconv nz64_pose32_clotype32 full VAE+GAN train step (BASELINE configs[2]; "
+                                   "configs[3] when n_gpus=8)",
+                       "meshes_per_gpu": N, "global_batch": N * world, "parallelism": "dp%d" % world,
+                       "launch": graph_note,
+                       "l2": "no explicit flush: one step streams ~%.0f GB of activations, >> 126 MB L2" % (0.383 * N),
+                       "update_rule": "real discriminator gradients (ref_compat=False); lib/models.py:466 quirk available "
+                                      "as ref_compat=True"},
+            "clocks": clk,
+            "e2e": {"value": total_meshes / e2e_s, "unit": "meshes/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "loss": {k: float(v) for k, v in zip(("recon", "edge", "kl", "gan_g", "gan_d_real", "gan_d_fake"),
+                                                 loss_host.tolist())}}
+
+    # ---- roofline of the dominant kernel family (one profiled eager step, CUDA events per launch) ---------------------
+    if not args.no_profile:
+        E.PROFILE = []
+        stage()
+        net.train_step(step=500, allreduce=None, update=False)
+        torch.cuda.synchronize()
+        fam = {}
+        rows = []
+        for family, tag, nbytes, e0, e1 in E.PROFILE:
+            dt = e0.elapsed_time(e1) * 1e-3
+            f = fam.setdefault(family, [0.0, 0.0, 0])
+            f[0] += nbytes; f[1] += dt; f[2] += 1
+            rows.append({"family": family, "launch": tag, "alg_bytes": nbytes, "us": dt * 1e6,
+                         "GBps": nbytes / dt / 1e9 if dt > 0 else None})
+        E.PROFILE = None
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        dom = max(fam.items(), key=lambda kv: kv[1][1])
+        nb, dt, cnt = dom[1]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom[0])
+        tot_b = sum(f[0] for f in fam.values())
+        tot_t = sum(f[1] for f in fam.values())
+        line["roofline"] = {"bound": "hbm", "kernel": dom[0], "achieved": nb / dt / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": nb / dt / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                            "launches_per_step": cnt, "alg_bytes_per_launch": nb / cnt, "us_per_launch": dt / cnt * 1e6,
+                            "share_of_profiled_time": dt / tot_t,
+                            "families": {k: {"alg_GB": v[0] / 1e9, "ms": v[1] * 1e3, "launches": v[2],
+                                             "GBps": v[0] / v[1] / 1e9} for k, v in fam.items()},
+                            "alg_mb_per_mesh_profiled": tot_b / N / 1e6,
+                            "whole_step_frac_of_hbm_roofline": (0.3831e9 * N / (ms / args.steps * 1e-3)) / 1e9 / peak}
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "launch_profile.json"), "w"), indent=1)
+
+    # ---- CPU baseline: the oracle port on a bounded sample (rank 0, N=1 only) ------------------------------------------
+    if world == 1 and not args.no_cpu_baseline:
+        rate, sps, threads = cpu_port_rate(args.cpu_sample, 2, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "meshes/s", "cores": threads, "kind": "port",
+                                "sample": "%d meshes x 2 steps after 1 warm-up, same train step, torch-CPU oracle port "
+                                          "(%.1f s/step)" % (args.cpu_sample, sps)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

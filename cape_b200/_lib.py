@@ -36,6 +36,7 @@ class DwArgs(C.Structure):
 SIGNATURES = {
     "cape_last_error": (C.c_char_p, []),
     "cape_abi_version": (C.c_int, []),
+    "cape_launch_count": (C.c_int64, []),
     "cape_topology_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "cape_topology_destroy": (None, [C.c_void_p]),
     "cape_topology_add_operator": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -9,6 +9,7 @@
 namespace cape {
 
 void set_error(const std::string& msg);
+void count_launches(int n);   // bookkeeping for cape_launch_count()
 
 #define CAPE_CHECK_CUDA(expr)                                                              \
   do {                                                                                     \

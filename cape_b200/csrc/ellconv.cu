@@ -630,6 +630,7 @@ extern "C" int cape_resample(cape_topology* t, int op, const float* x, float* y,
   const long long blocks = (total * 32 + 255) / 256;
   resample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(v, x, y, total, rows_out, rows_in, F, vec);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   return 0;
 }
 
@@ -692,6 +693,7 @@ extern "C" int cape_cheb_fwd(cape_topology* t, const cape_conv_args* a, void* st
     else ellconv_kernel<64, false><<<grid, NT, 0, st>>>(p);
   }
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   return 0;
 }
 
@@ -726,6 +728,7 @@ extern "C" int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* strea
   dim3 grid(ftiles, ctiles, (unsigned)nsplit);
   ellconv_dw_kernel<<<grid, NT, 0, st>>>(p);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   if (nsplit > 1) {
     const long long total = (long long)a->F * a->ncols;
     int blocks = (int)((total + 255) / 256);
@@ -733,6 +736,7 @@ extern "C" int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* strea
     reduce_splits_kernel<<<blocks, 256, 0, st>>>((const float*)t->workspace, (int)nsplit, a->F, a->ncols, a->dw,
                                                   a->dw_stride, a->accumulate);
     CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   }
   return 0;
 }
@@ -762,5 +766,6 @@ extern "C" int cape_colsum(cape_topology* t, const float* g, int N, int rows, in
   dim3 grid(rblocks, N, ctiles);
   colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   return 0;
 }

@@ -136,14 +136,17 @@ extern "C" int cape_gn_relu_fwd(cape_topology* t, const float* x, int N, int row
   dim3 grid((rows + GN_ROWS - 1) / GN_ROWS, N);
   gn_stats_kernel<<<grid, 256, 0, st>>>(x, rows, C, G, acc);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   const double inv_cnt = 1.0 / ((double)rows * (C / G));
   gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, st>>>(acc, N * G, inv_cnt, eps, stats);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   const long long total = (long long)N * rows * C;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   gn_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, total, rows, C, G, gamma, beta, stats, y);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   return 0;
 }
 
@@ -158,11 +161,13 @@ extern "C" int cape_gn_relu_bwd(cape_topology* t, const float* x, const float* y
   dim3 grid((rows + GN_ROWS - 1) / GN_ROWS, N);
   gn_bwd_stats_kernel<<<grid, 256, 0, st>>>(x, y, dy, rows, C, G, gamma, stats, dgamma, dbeta, acc);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   const double inv_cnt = 1.0 / ((double)rows * (C / G));
   const long long total = (long long)N * rows * C;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   gn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, dy, total, rows, C, G, gamma, stats, acc, inv_cnt, dx);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   return 0;
 }

@@ -202,6 +202,7 @@ extern "C" int cape_act_bwd(const float* dy, const float* y, float* g, int64_t n
   CAPE_REQUIRE(dy && y && g && n > 0, "bad arguments");
   act_bwd_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(dy, y, g, n, alpha);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   return 0;
 }
 
@@ -209,6 +210,7 @@ extern "C" int cape_axpy(float* y, const float* x, float a, int64_t n, void* str
   CAPE_REQUIRE(y && x && n > 0, "bad arguments");
   axpy_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(y, x, a, n);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   return 0;
 }
 
@@ -217,6 +219,7 @@ extern "C" int cape_vae_sample_fwd(const float* mean, const float* logvar, const
   CAPE_REQUIRE(mean && logvar && eps && z && N > 0 && nz > 0 && z_stride >= nz, "bad arguments");
   vae_fwd_kernel<<<(N * nz + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mean, logvar, eps, z, z_stride, N, nz);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   return 0;
 }
 
@@ -227,6 +230,7 @@ extern "C" int cape_vae_sample_bwd(const float* dz, int dz_stride, const float* 
   vae_bwd_kernel<<<(N * nz + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dz, dz_stride, mean, logvar, eps, dmean,
                                                                         dlogvar, N, nz, kl_scale);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   return 0;
 }
 
@@ -248,9 +252,11 @@ extern "C" int cape_recon_losses(cape_topology* t, int nbr_op, const float* pred
   cudaStream_t st = (cudaStream_t)stream;
   recon_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   if (mean && logvar && nz > 0) {
     kl_kernel<<<blocks_for((long long)N * nz, 256, 64), 256, 0, st>>>(mean, logvar, N * nz, 1.f / (float)N, losses);
     CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   }
   return 0;
 }
@@ -261,6 +267,7 @@ extern "C" int cape_bce_logits(const float* logits, int64_t n, float label, floa
   bce_kernel<<<blocks_for(n, 256, 256), 256, 0, (cudaStream_t)stream>>>(logits, n, label, scale / (float)n,
                                                                          1.f / (float)n, dlogits, loss);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   return 0;
 }
 
@@ -269,6 +276,7 @@ extern "C" int cape_sumsq(const float* g, int64_t n, float* sumsq, void* stream)
   CAPE_REQUIRE(aligned16(g), "g must be 16-byte aligned");
   sumsq_kernel<<<blocks_for(n / 4 + 1, 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(g, n, sumsq);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   return 0;
 }
 
@@ -278,6 +286,7 @@ extern "C" int cape_sgd_clip_update(float* w, const float* g, float* mom, int64_
   sgd_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(w, g, mom, n, sumsq, clip_norm, lr_dev,
                                                                              momentum);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   return 0;
 }
 
@@ -286,5 +295,6 @@ extern "C" int cape_cheb_weight_transpose(const float* w, int Fin, int K, int Fo
   dim3 grid((Fin + 31) / 32, (Fout + 31) / 32, K), block(32, 8);
   wtrans_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, Fin, K, Fout, wt);
   CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
   return 0;
 }

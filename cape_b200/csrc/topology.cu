@@ -1,17 +1,22 @@
 // Topology handle: device-resident ELL operators (the fixed SMPL mesh hierarchy) + workspace.
 // Replaces the per-graph tf.SparseTensor construction of lib/models.py:74-79,141-145.
 #include "common.cuh"
+#include <atomic>
 #include <cstring>
 
 namespace cape {
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 }  // namespace cape
 
 using namespace cape;
 
 extern "C" const char* cape_last_error(void) { return g_last_error.c_str(); }
 extern "C" int cape_abi_version(void) { return CAPE_ABI_VERSION; }
+extern "C" int64_t cape_launch_count(void) { return (int64_t)cape::launches(); }
 
 extern "C" int cape_topology_create(int device, cape_topology** out) {
   CAPE_REQUIRE(out != nullptr, "out is null");

@@ -15,6 +15,29 @@ from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, EPI_AFFINE, EPI_DUALMASK, EPI_
 
 LEAKY_ALPHA = 0.2  # tf.nn.leaky_relu default (lib/models.py:109,506,582)
 
+# Optional per-launch timing (bench.py's roofline pass): when PROFILE is a list, every helper below brackets its
+# launch with CUDA events on the launching stream and appends (family, tag, algorithmic_bytes, ev0, ev1).
+PROFILE = None
+
+
+class _Prof:
+    def __init__(self, family, tag):
+        self.on = PROFILE is not None and tag is not None
+        self.family, self.tag = family, tag
+
+    def __enter__(self):
+        if self.on:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.e1.record()
+            PROFILE.append((self.family, self.tag[0], self.tag[1], self.e0, self.e1))
+        return False
+
 
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
@@ -77,6 +100,11 @@ class ConvSite:
 
     def __init__(self, tp, L, K, U=None, D=None):
         self.K = K
+        self.ref_unpool, self.ref_pool = U is not None, D is not None   # poolwT calls in the reference graph
+        self.M = L.shape[0]
+        self.ref_rows_in = U.shape[1] if U is not None else L.shape[0]
+        self.ref_rows_out = D.shape[0] if D is not None else L.shape[0]
+        self.nnz = int(topo.rescale_L(L).nnz)
         if U is not None and topo.is_identity(U, tol=1e-6):
             U = None     # factor-1 levels: identity up to 5e-11
         if D is not None and topo.is_identity(D, tol=0):
@@ -99,7 +127,7 @@ class ConvSite:
 # ---------------------------------------------------------------------------------------------------
 # kernel-call helpers
 # ---------------------------------------------------------------------------------------------------
-def gemm(tp, A, B, Cout, bias=None, act=ACT_NONE, alpha=1.0, beta=0.0):
+def gemm(tp, A, B, Cout, bias=None, act=ACT_NONE, alpha=1.0, beta=0.0, tag=None):
     """Cout = act(alpha * A @ B + bias) + beta * Cout for 2-D (possibly transposed) views."""
     M, K = A.shape
     K2, N = B.shape
@@ -114,12 +142,13 @@ def gemm(tp, A, B, Cout, bias=None, act=ACT_NONE, alpha=1.0, beta=0.0):
         a_rs = 1
     if N == 1 and b_rs != 1:
         b_cs = 1
-    check(tp.lib.cape_gemm(tp.h, M, N, K, _ptr(_f32(A)), a_rs, a_cs, _ptr(_f32(B)), b_rs, b_cs, _ptr(_f32(Cout)),
-                           Cout.stride(0), _ptr(bias), act, LEAKY_ALPHA, alpha, beta, _stream()))
+    with _Prof("gemm", tag):
+        check(tp.lib.cape_gemm(tp.h, M, N, K, _ptr(_f32(A)), a_rs, a_cs, _ptr(_f32(B)), b_rs, b_cs, _ptr(_f32(Cout)),
+                               Cout.stride(0), _ptr(bias), act, LEAKY_ALPHA, alpha, beta, _stream()))
 
 
 def cheb_call(tp, N, rows_out, ncols, terms, out, out2=None, cond=None, epilogue=EPI_LINEAR, act=ACT_NONE,
-              alpha=LEAKY_ALPHA, bias=None, bias_per_row=False, aux=None):
+              alpha=LEAKY_ALPHA, bias=None, bias_per_row=False, aux=None, tag=None):
     """terms: list of dicts(src, op, F, src_rows, src_stride, w, w_stride, w2, wc, wc2) with torch tensors."""
     a = ConvArgs()
     a.N, a.rows_out, a.ncols, a.nterms = N, rows_out, ncols, len(terms)
@@ -146,15 +175,17 @@ def cheb_call(tp, N, rows_out, ncols, terms, out, out2=None, cond=None, epilogue
     a.aux = aux.data_ptr() if aux is not None else None
     a.out = out.data_ptr()
     a.out2 = out2.data_ptr() if out2 is not None else None
-    check(tp.lib.cape_cheb_fwd(tp.h, C.byref(a), _stream()))
+    with _Prof("ellconv", tag):
+        check(tp.lib.cape_cheb_fwd(tp.h, C.byref(a), _stream()))
 
 
-def cheb_dw(tp, N, rows_out, ncols, src, op, F, src_rows, src_stride, g, dw, dw_stride, accumulate=False):
+def cheb_dw(tp, N, rows_out, ncols, src, op, F, src_rows, src_stride, g, dw, dw_stride, accumulate=False, tag=None):
     a = DwArgs()
     a.N, a.rows_out, a.ncols = N, rows_out, ncols
     a.src, a.op, a.F, a.src_rows, a.src_stride = src.data_ptr(), op, F, src_rows, src_stride
     a.g, a.dw, a.dw_stride, a.accumulate = g.data_ptr(), dw.data_ptr(), dw_stride, 1 if accumulate else 0
-    check(tp.lib.cape_cheb_dw(tp.h, C.byref(a), _stream()))
+    with _Prof("ellconv_dw", tag):
+        check(tp.lib.cape_cheb_dw(tp.h, C.byref(a), _stream()))
 
 
 def colsum(tp, g, N, rows, ncols, ops, out):

@@ -89,8 +89,8 @@ class ChebLayer:
     branch) with its backward."""
 
     def __init__(self, net, site, F, C, Fout, W, gW, bias=None, gbias=None, act=ACT_NONE, Wa=None, gWa=None,
-                 bias_per_row=False, need_dx=True, maxN=1, n_cs_slots=1):
-        self.net, self.tp, self.site = net, net.tp, site
+                 bias_per_row=False, need_dx=True, maxN=1, n_cs_slots=1, name=""):
+        self.net, self.tp, self.site, self.name = net, net.tp, site, name
         self.F, self.C, self.Fout, self.K = F, C, Fout, site.K
         K = self.K
         self.W3, self.gW3 = W.view(F + C, K, Fout), gW.view(F + C, K, Fout)
@@ -116,6 +116,26 @@ class ChebLayer:
         self.cs_id = [net.arena.request(maxN, max(len(self.cs_ops), 1), Fout) for _ in range(n_cs_slots)]
         self.csa_id = net.arena.request(maxN, 1, Fout) if (self.affine and C) else None
 
+    def alg_bytes(self, N, what):
+        """Algorithmic bytes of what this layer's launches replace in the reference graph, per SURVEY.md 8(d):
+        every tensor crossing a layer boundary once, fp32, Fin INCLUDING the materialised condition channels;
+        conv fwd 4NM(Fin+Fout) + 4*Fin*K*Fout (+12 nnz if K>1), resample 4NF(M+M'), bwd = 4NM(2Fin+Fout) + 2x weights
+        (attributed: dx launch = Fin+Fout share + resamples, dW launches = the extra Fin share)."""
+        s, Fin, Fo, K = self.site, self.F + self.C, self.Fout, self.K
+        wbytes = 4 * Fin * K * Fo + (12 * s.nnz if K > 1 else 0)
+        conv = 4 * N * s.M * (Fin + Fo) + wbytes
+        if self.affine:
+            conv += 4 * N * s.M * (Fin + Fo) + 4 * Fin * Fo
+            wbytes += 4 * Fin * Fo
+        res = 0
+        if s.ref_unpool:
+            res += 4 * N * Fin * (s.ref_rows_in + s.M)
+        if s.ref_pool:
+            res += 4 * N * Fo * (s.M + s.ref_rows_out)
+        if what in ("fwd", "dx"):
+            return conv + res
+        return 4 * N * s.M * Fin * (2 if self.affine else 1) + wbytes      # all dW launches of the layer together
+
     def prep(self):
         if self.need_dx:
             weight_transpose(self.tp, self.W, self.F, self.K, self.Fout, self.Wt)
@@ -139,7 +159,7 @@ class ChebLayer:
             terms.append(t)
         cheb_call(self.tp, N, s.rows_out, Fout, terms, out, out2=out2, cond=ycat if C else None,
                   epilogue=EPI_AFFINE if self.affine else EPI_LINEAR, act=self.act, bias=self.bias,
-                  bias_per_row=self.bias_per_row)
+                  bias_per_row=self.bias_per_row, tag=(self.name + ":fwd", self.alg_bytes(N, "fwd")))
 
     def bwd(self, x, ycat, g, g_aff=None, dx=None, dx2=None, dx_epi=EPI_LINEAR, dx_aux=None, dx_alpha=E.LEAKY_ALPHA,
             dycat=None, want_dw=True, cs_slot=0):
@@ -149,10 +169,12 @@ class ChebLayer:
         N = g.shape[0]
         sx = x.shape[2]
         if want_dw:
+            nl = K + (1 if self.affine else 0)
+            tg = (self.name + ":dW", self.alg_bytes(N, "dW") / nl)
             for k in range(K):
-                cheb_dw(tp, N, s.rows_out, Fout, x, s.ops[k], F, s.rows_in, sx, g, self.gW3[:, k, :], K * Fout)
+                cheb_dw(tp, N, s.rows_out, Fout, x, s.ops[k], F, s.rows_in, sx, g, self.gW3[:, k, :], K * Fout, tag=tg)
             if self.affine:
-                cheb_dw(tp, N, s.rows_out, Fout, x, s.ops[0], F, s.rows_in, sx, g_aff, self.gWa2, Fout)
+                cheb_dw(tp, N, s.rows_out, Fout, x, s.ops[0], F, s.rows_in, sx, g_aff, self.gWa2, Fout, tag=tg)
         has_bias = self.bias is not None and not self.bias_per_row and want_dw
         if (has_bias or C) and len(self.cs_ops):
             cs = self.net.arena.get(self.cs_id[cs_slot])[:N]
@@ -189,7 +211,8 @@ class ChebLayer:
             for k in range(K):
                 terms.append(dict(src=g, op=s.opsT[k], F=Fout, src_rows=s.rows_out, src_stride=Fout,
                                   w=self.Wt[:, k, :], w_stride=K * F))
-            cheb_call(tp, N, s.rows_in, F, terms, dx, out2=dx2, epilogue=dx_epi, aux=dx_aux, alpha=dx_alpha)
+            cheb_call(tp, N, s.rows_in, F, terms, dx, out2=dx2, epilogue=dx_epi, aux=dx_aux, alpha=dx_alpha,
+                      tag=(self.name + ":dx", self.alg_bytes(N, "dx")))
 
     def _colsum_chunk(self, g, N, cs, o):
         # more than 4 operators (K > 3 with conditions): contiguous scratch per chunk, then copy back
@@ -202,12 +225,15 @@ class ChebLayer:
 class Dense:
     """tf.layers.dense (y = act(xW + b)) with backward."""
 
-    def __init__(self, net, W, b, gW, gb, act=ACT_NONE):
-        self.net, self.tp = net, net.tp
+    def __init__(self, net, W, b, gW, gb, act=ACT_NONE, name=""):
+        self.net, self.tp, self.name = net, net.tp, name
         self.W, self.b, self.gW, self.gb, self.act = W, b, gW, gb, act
 
     def fwd(self, x, out):
-        gemm(self.tp, x, self.W, out, bias=self.b, act=self.act)
+        M, K = x.shape
+        Nn = self.W.shape[1]
+        gemm(self.tp, x, self.W, out, bias=self.b, act=self.act,
+             tag=(self.name + ":fwd", 4 * (M * (K + Nn) + K * Nn)))      # SURVEY 8(d): 4N(in+out) + 4 in*out
 
     def bwd(self, x, out, dout, gtmp=None, dx=None, dx_beta=0.0, want_dw=True):
         g = dout
@@ -266,21 +292,21 @@ class CapeNetwork:
             sc = "generator/encoder/encoder_conv%d" % (i + 1)
             self.enc.append(ChebLayer(self, site, fin, 0, F[i], w(sc + "/weights"), g(sc + "/weights"),
                                       bias=w(sc + "/bias"), gbias=g(sc + "/bias"), act=ACT_LEAKY, need_dx=(i > 0),
-                                      maxN=N))
+                                      maxN=N, name="enc/conv%d" % (i + 1)))
             fin = F[i]
         red = specs["generator/encoder/1x1-conv/weights"][1]
         self.red = red
         self.enc_1x1 = ChebLayer(self, ConvSite(tp, L[-1], 1), F[-1], 0, red, w("generator/encoder/1x1-conv/weights"),
-                                 g("generator/encoder/1x1-conv/weights"), maxN=N)
+                                 g("generator/encoder/1x1-conv/weights"), maxN=N, name="enc/1x1")
         flat = self.p[-1] * red
         self.flat = flat
         dn = lambda s, act=ACT_NONE: Dense(self, w(s + "/dense/kernel").view(specs[s + "/dense/kernel"]),
                                            w(s + "/dense/bias"), g(s + "/dense/kernel").view(specs[s + "/dense/kernel"]),
-                                           g(s + "/dense/bias"), act)
+                                           g(s + "/dense/bias"), act, name=s.split("/", 1)[-1])
         self.fc_mean, self.fc_var = dn("generator/encoder/fc_mean"), dn("generator/encoder/fc_var")
         self.dec_fc1 = dn("generator/decoder/fc1", ACT_LEAKY)
         self.dec_1x1 = ChebLayer(self, ConvSite(tp, L[-1], 1), red, 0, F[-1], w("generator/decoder/1x1-conv/weights"),
-                                 g("generator/decoder/1x1-conv/weights"), maxN=N)
+                                 g("generator/decoder/1x1-conv/weights"), maxN=N, name="dec/1x1")
         self.dec = []
         fin = F[-1]
         for i in range(nl):
@@ -289,12 +315,12 @@ class CapeNetwork:
             sc = "generator/decoder/decoder_resblock_affine%d" % (i + 1)
             self.dec.append(ChebLayer(self, site, fin, Cc, Fo, w(sc + "/graph_conv/weights"),
                                       g(sc + "/graph_conv/weights"), Wa=w(sc + "/affine/weights"),
-                                      gWa=g(sc + "/affine/weights"), maxN=N))
+                                      gWa=g(sc + "/affine/weights"), maxN=N, name="dec/aff%d" % (i + 1)))
             fin = Fo
         self.dec_out = ChebLayer(self, ConvSite(tp, L[0], K[0]), fin, Cc, c["nn_input_channel"],
                                  w("generator/decoder/outputs/weights"), g("generator/decoder/outputs/weights"),
                                  bias=w("generator/decoder/outputs/bias"), gbias=g("generator/decoder/outputs/bias"),
-                                 bias_per_row=True, maxN=N)
+                                 bias_per_row=True, maxN=N, name="dec/outputs")
         self.disc = []
         fin = c["nn_input_channel"]
         for i in range(len(D_d)):
@@ -302,11 +328,11 @@ class CapeNetwork:
             sc = "discriminator/shared/conv%d" % (i + 1)
             self.disc.append(ChebLayer(self, site, fin, Cc if i == 0 else 0, F[i], w(sc + "/weights"),
                                        g(sc + "/weights"), bias=w(sc + "/bias"), gbias=g(sc + "/bias"), act=ACT_LEAKY,
-                                       maxN=2 * N, n_cs_slots=2))
+                                       maxN=2 * N, n_cs_slots=2, name="disc/conv%d" % (i + 1)))
             fin = F[i]
         self.disc_pred = ChebLayer(self, ConvSite(tp, L_d[-1], K[-1]), fin, 0, 1,
                                    w("discriminator/prediction_map/weights"), g("discriminator/prediction_map/weights"),
-                                   maxN=2 * N, n_cs_slots=2)
+                                   maxN=2 * N, n_cs_slots=2, name="disc/pred_map")
         # condition nets (models.py:479-511)
         self.c_pose1 = dn("condition_pose/fc1", ACT_LEAKY)
         self.c_pose2 = dn("condition_pose/fc2")
@@ -364,6 +390,8 @@ class CapeNetwork:
         self.losses = z(8)       # recon, edge, kl, gan_g, gan_d_real, gan_d_fake
         self.sumsq = z(2)
         self.lr = z(2)
+        self._lr_host = torch.zeros(256, 2).pin_memory()   # ring: the async H2D of step k must not see step k+1's value
+        self._lr_slot = 0
         self.step_count = 0
         # workspace: split-K partials (dW of the widest layer, FC split-K)
         tp.reserve_workspace(64 << 20)
@@ -556,12 +584,10 @@ class CapeNetwork:
             k = math.floor(step / ds)
         return lr_g * c["decay_rate"] ** k, lr_d * c["decay_rate"] ** k
 
-    def train_step(self, step=None, update=True, allreduce=None):
-        """One optimiser application on both players = one sess.run(op_train_*) of the reference
-        (lib/models.py:460-472).  Inputs must have been staged with set_inputs()."""
+    def enqueue_fwd_bwd(self):
+        """Forward + backward of both players for the staged batch; pure device work (CUDA-graph capturable)."""
         N, c, tp = self.N, self.cfg, self.tp
         lam_gan = float(c["lambda_gan"])
-        step = self.step_count if step is None else step
         self.arena.zero()
         self.losses.zero_()
         self.d_ycat.zero_()
@@ -601,30 +627,60 @@ class CapeNetwork:
                 axpy(tp, self._g(n + "/dense/kernel"), self._w(n + "/dense/kernel"), r2)
         if self.ref_compat:
             self.PD.grad.copy_(self.PD.flat)          # models.py:466: the D "gradients" are its variables
-        if allreduce is not None:
-            allreduce(self.PG.grad, self.PD.grad)
-        if update:
-            self.apply_update(step)
-        return L
-
-    def apply_update(self, step):
-        """clip_by_global_norm(5.0) + MomentumOptimizer for both players (models.py:460-467)."""
-        lib = self.tp.lib
-        c = self.cfg
-        lr_g, lr_d = self.lr_now(step)
-        self.lr.copy_(torch.tensor([lr_g, lr_d], dtype=torch.float32), non_blocking=True)
-        self.sumsq.zero_()
-        if not c["optim_condnet"]:                 # models.py:455-458: condition nets excluded from vars_g
+        if not c["optim_condnet"]:                    # models.py:455-458: condition nets excluded from vars_g
             for n in self.PG.names:
                 if not n.startswith("generator"):
                     self.PG.g(n).zero_()
+
+    def enqueue_update(self):
+        """clip_by_global_norm(5.0) + MomentumOptimizer for both players (models.py:460-467) + weight re-layouts.
+        Learning rates are read from device memory (set_lr), so this too is CUDA-graph capturable."""
+        lib = self.tp.lib
+        self.sumsq.zero_()
         for P, i in ((self.PG, 0), (self.PD, 1)):
             _lib.check(lib.cape_sumsq(E._ptr(P.grad), P.size, E._ptr(self.sumsq[i:]), E._stream()))
             _lib.check(lib.cape_sgd_clip_update(E._ptr(P.flat), E._ptr(P.grad), E._ptr(P.mom), P.size,
                                                 E._ptr(self.sumsq[i:]), 5.0, E._ptr(self.lr[i:]),
-                                                float(c["momentum"]), E._stream()))
-        self.step_count = step + 1
+                                                float(self.cfg["momentum"]), E._stream()))
         self.prep_weights()
+
+    def set_lr(self, step):
+        lr_g, lr_d = self.lr_now(step)
+        slot = self._lr_host[self._lr_slot]
+        self._lr_slot = (self._lr_slot + 1) % self._lr_host.shape[0]
+        slot[0], slot[1] = lr_g, lr_d
+        self.lr.copy_(slot, non_blocking=True)
+
+    def capture_graphs(self):
+        """Capture forward/backward and the update into two CUDA graphs (the gradient all-reduce runs between
+        them).  One eager step must have run before (lazy initialisations, workspace growth)."""
+        self.graph_fb, self.graph_up = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(self.graph_fb):
+            self.enqueue_fwd_bwd()
+        with torch.cuda.graph(self.graph_up):
+            self.enqueue_update()
+        torch.cuda.synchronize()
+
+    def train_step(self, step=None, update=True, allreduce=None, use_graph=False):
+        """One optimiser application on both players = one sess.run(op_train_*) of the reference
+        (lib/models.py:460-472).  Inputs must have been staged with set_inputs()."""
+        step = self.step_count if step is None else step
+        if update:
+            self.set_lr(step)
+        if use_graph:
+            self.graph_fb.replay()
+        else:
+            self.enqueue_fwd_bwd()
+        if allreduce is not None:
+            allreduce(self.PG.grad, self.PD.grad)
+        if update:
+            if use_graph:
+                self.graph_up.replay()
+            else:
+                self.enqueue_update()
+            self.step_count = step + 1
+        return self.losses
 
     def loss_dict(self):
         """Host copy of the last step's loss terms (synchronises)."""

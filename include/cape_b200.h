@@ -33,6 +33,8 @@ typedef struct cape_topology cape_topology;
 /* ---- error / version --------------------------------------------------------------------------- */
 const char* cape_last_error(void);
 int cape_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+int64_t cape_launch_count(void);
 
 /* ---- topology handle: the fixed sparse operators ------------------------------------------------
  * Replaces the graph-build-time conversion of scipy matrices into tf.SparseTensor

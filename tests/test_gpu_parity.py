@@ -1,0 +1,94 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle (tests/parity.py).
+Tolerance: 1e-4 relative fp32 (BASELINE.json north_star)."""
+import pytest
+import torch
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_all(res, tol=parity.TOL):
+    bad = {k: v for k, v in res.items() if not v < tol}
+    assert not bad, "parity failures (rel err): %s" % bad
+
+
+@pytest.fixture(scope="module")
+def cfg():
+    from cape_b200.params import NZ64_AFFINE
+    return dict(NZ64_AFFINE, decay_steps=10)
+
+
+def test_golden_vectors(hierarchy):
+    """BASELINE configs[0] (single Chebyshev K=6 layer on the 6890x3 template, batch 1) + fused cnp + unpool
+    against the committed golden outputs."""
+    _assert_all(parity.golden_ops(hierarchy))
+
+
+def test_dense_layers():
+    _assert_all(parity.gemm_cases())
+
+
+def test_chebyshev_forward_and_gradients(hierarchy):
+    """Every shape class of the path: pooled encoder conv, unpooled decoder conv, K=3 discriminator conv, 1x1,
+    thin (Fout=3, Fout=1) and first (Fin=3) layers -- forward, dx, dW, db."""
+    _assert_all(parity.cheb_grad_cases(hierarchy))
+
+
+def test_group_norm():
+    _assert_all(parity.gn_case())
+    _assert_all(parity.gn_case(N=3, rows=6890, C=32, seed=1))
+
+
+def test_train_step_matches_oracle(hierarchy, cfg):
+    """Full VAE+GAN update (enc+dec+disc fwd/bwd, losses, clip, momentum): x_hat, 5 loss terms, every gradient and
+    every post-update parameter."""
+    res = parity.train_step(hierarchy, cfg, N=2)
+    assert res["x_hat (vertex-L2)"] < 1e-4
+    _assert_all(res)
+
+
+def test_train_step_reference_quirks(hierarchy, cfg):
+    """ref_compat=True reproduces lib/models.py:466 (discriminator 'gradients' = its clipped variables)."""
+    _assert_all(parity.train_step(hierarchy, cfg, N=2, ref_compat=True))
+
+
+def test_train_step_odd_batch(hierarchy, cfg):
+    """Batch that does not divide the 128-row tiles; other seed."""
+    _assert_all(parity.train_step(hierarchy, cfg, N=5, seed=7))
+
+
+def test_size_independent_properties(hierarchy, cfg):
+    """Full-size (batch 64) checks that need no oracle: linearity of the conv in x and W, batch-permutation
+    equivariance of the generator, CUDA-graph replay == eager."""
+    import numpy as np
+    from cape_b200 import ops
+    from cape_b200.network import CapeNetwork
+    from cape_b200.synthetic import make_batch
+    h = hierarchy
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x1 = torch.randn(64, 6890, 64, device="cuda", generator=g)
+    x2 = torch.randn(64, 6890, 64, device="cuda", generator=g)
+    W = torch.randn(128, 64, device="cuda", generator=g) * 0.1
+    f = lambda x, w: ops.chebyshev5(x, h["L"][1], w, 2, pool=h["D"][1])
+    lhs = f(2.0 * x1 - 3.0 * x2, W)
+    rhs = 2.0 * f(x1, W) - 3.0 * f(x2, W)
+    assert float((lhs - rhs).abs().max() / rhs.abs().max()) < 1e-5
+    N = 64
+    net = CapeNetwork(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], cfg, N)
+    b = {k: torch.from_numpy(v) for k, v in make_batch(N, cfg["nz"], seed=3).items()}
+    net.set_inputs(b["x_g"], b["cond_g"], b["cond2_g"], b["eps"], b["x_d"], b["cond_d"], b["cond2_d"])
+    y = net.forward_generator().clone()
+    perm = torch.from_numpy(np.random.RandomState(0).permutation(N))
+    net.set_inputs(b["x_g"][perm], b["cond_g"][perm], b["cond2_g"][perm], b["eps"][perm])
+    yp = net.forward_generator().clone()
+    assert float((yp - y[perm.cuda()]).abs().max() / y.abs().max()) < 1e-5
+    # eager step == graph-replayed step (same inputs, update disabled)
+    net.set_inputs(b["x_g"], b["cond_g"], b["cond2_g"], b["eps"], b["x_d"], b["cond_d"], b["cond2_d"])
+    net.train_step(step=100, update=False)
+    g_eager = net.PG.grad.clone()
+    net.capture_graphs()
+    net.train_step(step=100, update=False, use_graph=True)
+    torch.cuda.synchronize()
+    d = float((net.PG.grad - g_eager).abs().max() / g_eager.abs().max())
+    assert d < 1e-5, d
