@@ -16,7 +16,8 @@ f32p = C.c_void_p  # device pointers travel as integers
 class Term(C.Structure):
     _fields_ = [("src", C.c_void_p), ("op", C.c_int), ("F", C.c_int), ("src_rows", C.c_int),
                 ("src_stride", C.c_int), ("w_stride", C.c_int), ("w2_stride", C.c_int), ("w", C.c_void_p), ("w2", C.c_void_p),
-                ("wc", C.c_void_p), ("wc2", C.c_void_p)]
+                ("wc", C.c_void_p), ("wc2", C.c_void_p), ("wT", C.c_void_p), ("w2T", C.c_void_p),
+                ("wT_stride", C.c_int), ("w2T_stride", C.c_int)]
 
 
 class ConvArgs(C.Structure):
@@ -41,6 +42,7 @@ SIGNATURES = {
     "cape_topology_destroy": (None, [C.c_void_p]),
     "cape_topology_add_operator": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cape_topology_reserve_workspace": (C.c_int, [C.c_void_p, C.c_int64]),
+    "cape_set_tensor_cores": (C.c_int, [C.c_int]),
     "cape_cheb_fwd": (C.c_int, [C.c_void_p, C.POINTER(ConvArgs), C.c_void_p]),
     "cape_cheb_dw": (C.c_int, [C.c_void_p, C.POINTER(DwArgs), C.c_void_p]),
     "cape_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int,

@@ -7,44 +7,9 @@
 // neighbour-row reads, and contracts it with the weight tile.  Nothing but the final activation
 // is written to HBM: no transposes, no stacked basis, no materialised condition channels.
 #include "common.cuh"
+#include "ellconv_params.cuh"
 
 namespace cape {
-
-constexpr int BM = 128;   // output rows per CTA
-constexpr int BK = 32;    // reduction chunk
-constexpr int NT = 256;   // threads per CTA
-constexpr int AS_STRIDE = BK + 4;
-constexpr int MAX_SLOTS = 2 * CAPE_MAX_TERMS;
-
-struct TermDev {
-  const float* src;
-  OpView op;
-  int F, src_rows, src_stride, w_stride, w2_stride;
-  const float* w;
-  const float* w2;
-  int vec;
-};
-
-struct ConvParams {
-  int N, rows_out, ncols, nterms;
-  long long total_rows;
-  TermDev terms[CAPE_MAX_TERMS];
-  // condition slots: (term, accumulator) pairs that carry condition weights
-  int nslots;
-  int slot_term[MAX_SLOTS];
-  int slot_acc[MAX_SLOTS];
-  const float* slot_w[MAX_SLOTS];
-  const float* cond;
-  int C;
-  int epilogue, act;
-  float alpha;
-  const float* bias;
-  int bias_per_row;
-  const float* aux;
-  float* out;
-  float* out2;
-  int wvec, ovec;
-};
 
 // ---- A-tile gather ------------------------------------------------------------------------------
 __device__ __forceinline__ void gather_A(const TermDev& tm, int f0, const int* s_n, const int* s_r, int tid,
@@ -653,6 +618,7 @@ extern "C" int cape_cheb_fwd(cape_topology* t, const cape_conv_args* a, void* st
     if (get_op(t, s.op, a->rows_out, s.src_rows, &d.op) != 0) return -1;
     d.src = s.src; d.F = s.F; d.src_rows = s.src_rows; d.src_stride = s.src_stride; d.w_stride = s.w_stride; d.w2_stride = s.w2_stride;
     d.w = s.w; d.w2 = s.w2;
+    d.wT = s.wT; d.w2T = s.w2T; d.wT_stride = s.wT_stride; d.w2T_stride = s.w2T_stride;
     d.vec = (s.F % 4 == 0) && (s.src_stride % 4 == 0) && aligned16(s.src);
     wvec = wvec && (s.w_stride % 4 == 0) && aligned16(s.w) && (!s.w2 || aligned16(s.w2));
     if (s.w2) {
@@ -683,8 +649,12 @@ extern "C" int cape_cheb_fwd(cape_topology* t, const cape_conv_args* a, void* st
     const long long max_samples = (BM - 1) / a->rows_out + 2;
     CAPE_REQUIRE(max_samples * p.nslots * BNsel <= BM * AS_STRIDE, "rows_out too small for the condition staging buffer");
   }
-  dim3 grid((unsigned)((p.total_rows + BM - 1) / BM), (unsigned)((a->ncols + BNsel - 1) / BNsel));
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int rc = launch_ellconv_tc(t, p, dual, st);     // tcgen05 path when eligible
+    if (rc != 0) return rc < 0 ? rc : 0;
+  }
+  dim3 grid((unsigned)((p.total_rows + BM - 1) / BM), (unsigned)((a->ncols + BNsel - 1) / BNsel));
   if (dual) {
     if (BNsel == 32) ellconv_kernel<32, true><<<grid, NT, 0, st>>>(p);
     else ellconv_kernel<64, true><<<grid, NT, 0, st>>>(p);

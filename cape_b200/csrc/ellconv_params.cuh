@@ -1,0 +1,51 @@
+// Parameter blocks shared by the SIMT (ellconv.cu) and tcgen05 (ellconv_tc.cu) fused-conv kernels.
+#pragma once
+#include "common.cuh"
+
+namespace cape {
+
+constexpr int BM = 128;   // output rows per CTA
+constexpr int BK = 32;    // reduction chunk
+constexpr int NT = 256;   // threads per CTA
+constexpr int AS_STRIDE = BK + 4;
+constexpr int MAX_SLOTS = 2 * CAPE_MAX_TERMS;
+
+struct TermDev {
+  const float* src;
+  OpView op;
+  int F, src_rows, src_stride, w_stride, w2_stride;
+  const float* w;
+  const float* w2;
+  const float* wT;    // K-major copy of w: element (f, c) = wT[c * wT_stride + f] (tcgen05 path), or nullptr
+  const float* w2T;
+  int wT_stride, w2T_stride;
+  int vec;
+};
+
+struct ConvParams {
+  int N, rows_out, ncols, nterms;
+  long long total_rows;
+  TermDev terms[CAPE_MAX_TERMS];
+  // condition slots: (term, accumulator) pairs that carry condition weights
+  int nslots;
+  int slot_term[MAX_SLOTS];
+  int slot_acc[MAX_SLOTS];
+  const float* slot_w[MAX_SLOTS];
+  const float* cond;
+  int C;
+  int epilogue, act;
+  float alpha;
+  const float* bias;
+  int bias_per_row;
+  const float* aux;
+  float* out;
+  float* out2;
+  int wvec, ovec;
+};
+
+
+// tcgen05 path (ellconv_tc.cu): returns 1 if it launched, 0 if the problem is not eligible, <0 on error.
+int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaStream_t st);
+bool tensor_cores_enabled();
+
+}  // namespace cape

@@ -1,0 +1,411 @@
+// tcgen05 / TMEM version of the fused ELL-gather Chebyshev convolution (sm_100a only).
+//
+// Same math and epilogues as ellconv.cu, but the [128 x Fin*K] x [Fin*K x BN] contraction runs on the 5th-gen
+// tensor cores with fp32 accuracy by 3xTF32 error compensation:  a = a_hi + a_lo (a_hi = top 19 bits, a_lo = the
+// exact remainder), acc += a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32 accumulation in TMEM; the dropped a_lo*b_lo
+// term is ~2^-22 relative, so results stay within the 1e-4 parity gate with a wide margin.
+//
+// CTA = 9 warps.  Warps 0-7 build operand tiles: the Chebyshev-basis chunk A[128 rows x 32 k] is gathered from
+// neighbour rows with float4 loads (same ELL tables as the SIMT path), split into hi/lo and written to shared
+// memory in the canonical K-major SWIZZLE_128B UMMA layout; the weight chunk B[BN x 32 k] (K-major copy of W) is
+// loaded and split the same way.  Warp 8 issues tcgen05.mma (kind::tf32, M=128, N=BN, K=8; 12 per chunk, 24
+// for the two-accumulator affine block) and releases pipeline stages with tcgen05.commit -> mbarrier.  After the
+// last chunk warps 0-7 become the epilogue: tcgen05.ld the accumulators from TMEM, add the condition broadcast /
+// bias, apply the activation (or the affine-block / backward epilogues) and store rows with float4 writes.
+#include "common.cuh"
+#include "ellconv_params.cuh"
+
+namespace cape {
+
+namespace {
+
+constexpr int TC_PROD_WARPS = 8;
+constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
+constexpr int TC_THREADS = TC_PROD_THREADS + 32;
+constexpr int A_TILE_BYTES = BM * 128;            // 128 rows x 32 fp32 (one 128-byte swizzle row each)
+constexpr int QS_FLOATS = 4096;
+constexpr int MAX_STAGES = 4;
+constexpr uint32_t SPIN_LIMIT = 1u << 27;         // trap instead of hanging the GPU if a barrier never flips
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor, sm100 "version 1"):
+// start address >> 4 | LBO(ignored for swizzled K-major)=1 | SBO = 1024 B (8 rows x 128 B) | layout_type = 2.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+// 16 accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void split_store(float4 v, char* hi_tile, char* lo_tile, uint32_t off) {
+  float4 h, l;
+  h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+  h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+  h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+  h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+  *reinterpret_cast<float4*>(hi_tile + off) = h;
+  *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
+template <int BN, bool DUAL>
+struct TcCfg {
+  static constexpr int B_TILE_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + (DUAL ? 4 : 2) * B_TILE_BYTES;
+  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > MAX_STAGES ? MAX_STAGES : STAGES_RAW;
+  static constexpr int TMEM_COLS = DUAL ? 2 * BN : BN;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + QS_FLOATS * 4 + 2 * BM * 4 + 256;
+  static_assert(STAGES >= 2, "need at least a double buffer");
+};
+
+template <int BN, bool DUAL>
+__global__ void __launch_bounds__(TC_THREADS, 1) ellconv_tc_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = TcCfg<BN, DUAL>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: required by SWIZZLE_128B operand tiles
+  char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  char* stage_base = smem;
+  float* qs = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  int* s_n = reinterpret_cast<int*>(qs + QS_FLOATS);
+  int* s_r = s_n + BM;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_r + BM);        // full[STAGES], empty[STAGES], accum
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long row0 = (long long)blockIdx.x * BM;
+  const int col0 = blockIdx.y * BN;
+
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES), bar_accum = smem_u32(bars + 2 * MAX_STAGES);
+
+  if (tid < BM) {
+    const long long R = row0 + tid;
+    if (R < p.total_rows) { s_n[tid] = (int)(R / p.rows_out); s_r[tid] = (int)(R % p.rows_out); }
+    else { s_n[tid] = -1; s_r[tid] = 0; }
+  }
+  if (warp == TC_PROD_WARPS) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, TC_PROD_WARPS); mbar_init(bar_empty + 8 * s, 1); }
+      mbar_init(bar_accum, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // chunk sequence: for each term, ceil(F/32) chunks
+  if (warp < TC_PROD_WARPS) {
+    // =========================== producers ===========================
+    const int l8 = tid & 7, rs = tid >> 3;       // 8 lanes per 128-byte row, 32 row slots
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < p.nterms; ++t) {
+      const TermDev& tm = p.terms[t];
+      const bool has2 = DUAL && tm.w2T != nullptr;
+      for (int f0 = 0; f0 < tm.F; f0 += BK) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        char* st = stage_base + (size_t)stage * Cfg::STAGE_BYTES;
+        char* a_hi = st;
+        char* a_lo = st + A_TILE_BYTES;
+        char* b_hi = st + 2 * A_TILE_BYTES;
+        char* b_lo = b_hi + Cfg::B_TILE_BYTES;
+        const int f = f0 + l8 * 4;
+        // ---- A: gather 4 rows per thread
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = rs + 32 * i;
+          const int n = s_n[row], r = s_r[row];
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n >= 0 && f < tm.F) {
+            const float* base = tm.src + (size_t)n * tm.src_rows * tm.src_stride + f;
+            if (tm.op.idx == nullptr) {
+              v = ldg4(base + (size_t)r * tm.src_stride);
+            } else {
+              const int32_t* ip = tm.op.idx + (size_t)r * tm.op.width;
+              const float* wp = tm.op.w + (size_t)r * tm.op.width;
+              for (int j = 0; j < tm.op.width; ++j) {
+                const int id = __ldg(ip + j);
+                if (id < 0) break;
+                fma4(v, __ldg(wp + j), ldg4(base + (size_t)id * tm.src_stride));
+              }
+            }
+          }
+          split_store(v, a_hi, a_lo, (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4)));
+        }
+        // ---- B (and B2): rows = output columns, K-major copy of the weights
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) {
+          const int c = rs + 32 * i;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col0 + c < p.ncols && f < tm.F) v = ldg4(tm.wT + (size_t)(col0 + c) * tm.wT_stride + f);
+          const uint32_t off = (uint32_t)(c * 128 + ((l8 ^ (c & 7)) << 4));
+          split_store(v, b_hi, b_lo, off);
+          if (DUAL) {
+            if (has2) {
+              float4 v2 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (col0 + c < p.ncols && f < tm.F) v2 = ldg4(tm.w2T + (size_t)(col0 + c) * tm.w2T_stride + f);
+              split_store(v2, b_lo + Cfg::B_TILE_BYTES, b_lo + 2 * Cfg::B_TILE_BYTES, off);
+            }
+          }
+        }
+        fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+
+    // ---- condition broadcast vectors (same as the SIMT kernel): q[s][slot][c] = cond[n0+s,:] @ Wc_slot[:, col0+c]
+    const int n_first = s_n[0];
+    if (p.nslots > 0) {
+      int n_last = n_first;
+      for (int i = BM - 1; i > 0; --i)
+        if (s_n[i] >= 0) { n_last = s_n[i]; break; }
+      const int S = n_last - n_first + 1;
+      const int total = S * p.nslots * BN;
+      for (int o = tid; o < total; o += TC_PROD_THREADS) {
+        const int c = o % BN;
+        const int slot = (o / BN) % p.nslots;
+        const int s = o / (BN * p.nslots);
+        float q = 0.f;
+        if (col0 + c < p.ncols) {
+          const float* y = p.cond + (size_t)(n_first + s) * p.C;
+          const float* wc = p.slot_w[slot] + col0 + c;
+          const int ws = p.slot_acc[slot] ? p.terms[p.slot_term[slot]].w2_stride : p.terms[p.slot_term[slot]].w_stride;
+          for (int j = 0; j < p.C; ++j) q = fmaf(__ldg(y + j), __ldg(wc + (size_t)j * ws), q);
+        }
+        qs[o] = q;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
+    }
+
+    // =========================== epilogue ===========================
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
+    const int quad = warp & 3, half = warp >> 2;          // TMEM lane quadrant of this warp; column half
+    const int row = quad * 32 + lane;
+    const int n = s_n[row], r = s_r[row];
+    constexpr int CPW = BN / 2;                           // columns per warp
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const size_t orow = (size_t)(row0 + row) * p.ncols;
+#pragma unroll 1
+    for (int g = 0; g < CPW / 16; ++g) {
+      const int cl = half * CPW + g * 16;                 // column within the tile
+      float v0[16], v1[16];
+      tmem_ld16(taddr_row + (uint32_t)cl, v0);             // warp-collective: executed by every lane
+      if (DUAL) tmem_ld16(taddr_row + (uint32_t)(BN + cl), v1);
+      if (n < 0) continue;
+      const int c0 = col0 + cl;
+      if (c0 >= p.ncols) continue;
+      for (int slot = 0; slot < p.nslots; ++slot) {
+        const TermDev& tm = p.terms[p.slot_term[slot]];
+        const float coef = tm.op.rowsum ? __ldg(tm.op.rowsum + r) : 1.f;
+        const float* q = qs + ((size_t)(n - n_first) * p.nslots + slot) * BN + cl;
+        if (p.slot_acc[slot] == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v0[j] = fmaf(coef, q[j], v0[j]);
+        } else if (DUAL) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v1[j] = fmaf(coef, q[j], v1[j]);
+        }
+      }
+      float o1[16], o2[16];
+      bool write2 = false;
+      if (p.epilogue == CAPE_EPI_LINEAR) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v = v0[j];
+          if (p.bias != nullptr) v += __ldg(p.bias + (p.bias_per_row ? (size_t)r * p.ncols : 0) + c0 + j);
+          if (p.act == CAPE_ACT_LEAKY) v = v > 0.f ? v : p.alpha * v;
+          else if (p.act == CAPE_ACT_RELU) v = fmaxf(v, 0.f);
+          o1[j] = v;
+        }
+      } else if (p.epilogue == CAPE_EPI_AFFINE) {
+        write2 = p.out2 != nullptr;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float rg = fmaxf(v0[j], 0.f);
+          o1[j] = (DUAL ? v1[j] : 0.f) + rg;
+          o2[j] = rg;
+        }
+      } else {
+        float ax[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 a4 = ldg4(p.aux + orow + c0 + j);
+          ax[j] = a4.x; ax[j + 1] = a4.y; ax[j + 2] = a4.z; ax[j + 3] = a4.w;
+        }
+        if (p.epilogue == CAPE_EPI_SLOPE) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o1[j] = v0[j] * (ax[j] > 0.f ? 1.f : p.alpha);
+        } else {
+          write2 = p.out2 != nullptr;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { o1[j] = v0[j]; o2[j] = ax[j] > 0.f ? v0[j] : 0.f; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        *reinterpret_cast<float4*>(p.out + orow + c0 + j) = make_float4(o1[j], o1[j + 1], o1[j + 2], o1[j + 3]);
+        if (write2)
+          *reinterpret_cast<float4*>(p.out2 + orow + c0 + j) = make_float4(o2[j], o2[j + 1], o2[j + 2], o2[j + 3]);
+      }
+    }
+    tc_fence_before();
+  } else {
+    // =========================== MMA issuer (one elected lane) ===========================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N=BN, M=128
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, acc0_on = 0, acc1_on = 0;
+      for (int t = 0; t < p.nterms; ++t) {
+        const bool has2 = DUAL && p.terms[t].w2T != nullptr;
+        for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + (size_t)stage * Cfg::STAGE_BYTES);
+          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
+          const uint64_t b_hi = make_desc(sa + 2 * A_TILE_BYTES), b_lo = make_desc(sa + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES);
+          const uint64_t b2_hi = make_desc(sa + 2 * A_TILE_BYTES + 2 * Cfg::B_TILE_BYTES);
+          const uint64_t b2_lo = make_desc(sa + 2 * A_TILE_BYTES + 3 * Cfg::B_TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t adv = (uint64_t)(ks * 2);      // +32 bytes along K inside the 128-byte swizzle row
+            umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, acc0_on);
+            acc0_on = 1;
+            umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
+            umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+            if (has2) {
+              umma_tf32(tmem_base + BN, a_hi + adv, b2_hi + adv, idesc, acc1_on);
+              acc1_on = 1;
+              umma_tf32(tmem_base + BN, a_lo + adv, b2_hi + adv, idesc, 1);
+              umma_tf32(tmem_base + BN, a_hi + adv, b2_lo + adv, idesc, 1);
+            }
+          }
+          umma_commit(bar_empty + 8 * stage);              // stage reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      umma_commit(bar_accum);                              // accumulators complete
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == TC_PROD_WARPS) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+template <int BN, bool DUAL>
+int launch_one(const ConvParams& p, cudaStream_t st) {
+  using Cfg = TcCfg<BN, DUAL>;
+  static bool configured = false;
+  if (!configured) {
+    CAPE_CHECK_CUDA(cudaFuncSetAttribute(ellconv_tc_kernel<BN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid((unsigned)((p.total_rows + BM - 1) / BM), (unsigned)((p.ncols + BN - 1) / BN));
+  ellconv_tc_kernel<BN, DUAL><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+  CAPE_CHECK_CUDA(cudaGetLastError());
+  count_launches(1);
+  return 1;
+}
+
+}  // namespace
+
+static bool g_tc_enabled = true;
+bool tensor_cores_enabled() { return g_tc_enabled; }
+
+int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaStream_t st) {
+  (void)t;
+  if (!g_tc_enabled) return 0;
+  if (p.ncols % 16 != 0 || p.ncols < 32 || !p.ovec) return 0;
+  long long kred = 0;
+  for (int i = 0; i < p.nterms; ++i) {
+    const TermDev& tm = p.terms[i];
+    if (!tm.vec || tm.wT == nullptr || (tm.wT_stride % 4) != 0 || !aligned16(tm.wT)) return 0;
+    if (tm.w2 != nullptr && (tm.w2T == nullptr || (tm.w2T_stride % 4) != 0 || !aligned16(tm.w2T))) return 0;
+    kred += tm.F;
+  }
+  if (kred < 64) return 0;                       // tiny reductions: the SIMT kernel is as good and simpler
+  if (p.nslots > 0) {
+    const int bn = p.ncols >= 128 ? 128 : (p.ncols >= 64 ? 64 : 32);
+    const long long max_samples = (BM - 1) / p.rows_out + 2;
+    if (max_samples * p.nslots * bn > QS_FLOATS) return 0;
+  }
+  if (dual) {
+    if (p.ncols >= 128) return launch_one<128, true>(p, st);
+    if (p.ncols >= 64) return launch_one<64, true>(p, st);
+    return launch_one<32, true>(p, st);
+  }
+  if (p.ncols >= 128) return launch_one<128, false>(p, st);
+  if (p.ncols >= 64) return launch_one<64, false>(p, st);
+  return launch_one<32, false>(p, st);
+}
+
+}  // namespace cape
+
+extern "C" int cape_set_tensor_cores(int enable) {
+  const int prev = cape::g_tc_enabled ? 1 : 0;
+  cape::g_tc_enabled = enable != 0;
+  return prev;
+}

@@ -162,9 +162,11 @@ def cheb_call(tp, N, rows_out, ncols, terms, out, out2=None, cond=None, epilogue
         d.w_stride = t["w_stride"]
         d.w2_stride = t.get("w2_stride", 0)
         d.w = t["w"].data_ptr()
-        for k in ("w2", "wc", "wc2"):
+        for k in ("w2", "wc", "wc2", "wT", "w2T"):
             v = t.get(k)
             setattr(d, k, v.data_ptr() if v is not None else None)
+        d.wT_stride = t.get("wT_stride", 0)
+        d.w2T_stride = t.get("w2T_stride", 0)
     if cond is not None:
         a.cond = cond.data_ptr()
         a.C = cond.shape[1]

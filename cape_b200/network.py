@@ -101,10 +101,10 @@ class ChebLayer:
             self.Wa, self.Wa2, self.gWa2 = Wa, Wa.view(F + C, Fout), gWa.view(F + C, Fout)
         self.need_dx = need_dx
         dev = W.device
-        if need_dx:
-            self.Wt = torch.empty(Fout, K, F, device=dev)
-            if self.affine:
-                self.Wat = torch.empty(Fout, F, device=dev)
+        # K-major copies of the weights: B operand of the tcgen05 forward, and N-major operand of the data gradient
+        self.Wt = torch.empty(Fout, K, F, device=dev)
+        if self.affine:
+            self.Wat = torch.empty(Fout, F, device=dev)
         # colsum targets: [bias?] + K condition sums (+1 for the affine branch)
         self.cs_ops = []
         if bias is not None and not bias_per_row:
@@ -137,10 +137,9 @@ class ChebLayer:
         return 4 * N * s.M * Fin * (2 if self.affine else 1) + wbytes      # all dW launches of the layer together
 
     def prep(self):
-        if self.need_dx:
-            weight_transpose(self.tp, self.W, self.F, self.K, self.Fout, self.Wt)
-            if self.affine:
-                weight_transpose(self.tp, self.Wa, self.F, 1, self.Fout, self.Wat)
+        weight_transpose(self.tp, self.W, self.F, self.K, self.Fout, self.Wt)
+        if self.affine:
+            weight_transpose(self.tp, self.Wa, self.F, 1, self.Fout, self.Wat)
 
     def fwd(self, x, ycat, out, out2=None):
         N = x.shape[0]
@@ -149,11 +148,12 @@ class ChebLayer:
         terms = []
         for k in range(K):
             t = dict(src=x, op=s.ops[k], F=F, src_rows=s.rows_in, src_stride=x.shape[2], w=self.W3[:, k, :],
-                     w_stride=K * Fout)
+                     w_stride=K * Fout, wT=self.Wt[:, k, :], wT_stride=K * F)
             if C:
                 t["wc"] = self.W3[F:, k, :]
             if self.affine and k == 0:
                 t["w2"], t["w2_stride"] = self.Wa2, Fout
+                t["w2T"], t["w2T_stride"] = self.Wat, F
                 if C:
                     t["wc2"] = self.Wa2[F:]
             terms.append(t)
@@ -207,10 +207,10 @@ class ChebLayer:
             terms = []
             if self.affine:
                 terms.append(dict(src=g_aff, op=s.opsT[0], F=Fout, src_rows=s.rows_out, src_stride=Fout, w=self.Wat,
-                                  w_stride=F))
+                                  w_stride=F, wT=self.Wa2, wT_stride=Fout))
             for k in range(K):
                 terms.append(dict(src=g, op=s.opsT[k], F=Fout, src_rows=s.rows_out, src_stride=Fout,
-                                  w=self.Wt[:, k, :], w_stride=K * F))
+                                  w=self.Wt[:, k, :], w_stride=K * F, wT=self.W3[:, k, :], wT_stride=K * Fout))
             cheb_call(tp, N, s.rows_in, F, terms, dx, out2=dx2, epilogue=dx_epi, aux=dx_aux, alpha=dx_alpha,
                       tag=(self.name + ":dx", self.alg_bytes(N, "dx")))
 

@@ -42,8 +42,10 @@ class _ChebFn(torch.autograd.Function):
         W = W.contiguous()
         out = torch.empty(N, site.rows_out, Fout, device=x.device)
         W3 = W.view(Fin, K, Fout)
+        Wt = torch.empty(Fout, K, Fin, device=x.device)
+        E.weight_transpose(tp, W, Fin, K, Fout, Wt)
         terms = [dict(src=x, op=site.ops[k], F=Fin, src_rows=site.rows_in, src_stride=Fin, w=W3[:, k, :],
-                      w_stride=K * Fout) for k in range(K)]
+                      w_stride=K * Fout, wT=Wt[:, k, :], wT_stride=K * Fin) for k in range(K)]
         b = bias.contiguous().view(-1) if bias is not None else None
         E.cheb_call(tp, N, site.rows_out, Fout, terms, out, epilogue=EPI_LINEAR, act=act, bias=b)
         ctx.save_for_backward(x, W, out)
@@ -76,8 +78,9 @@ class _ChebFn(torch.autograd.Function):
             Wt = torch.empty(Fout, K, Fin, device=x.device)
             E.weight_transpose(tp, W, Fin, K, Fout, Wt)
             dx = torch.empty_like(x)
+            W3 = W.view(Fin, K, Fout)
             terms = [dict(src=g, op=site.opsT[k], F=Fout, src_rows=site.rows_out, src_stride=Fout, w=Wt[:, k, :],
-                          w_stride=K * Fin) for k in range(K)]
+                          w_stride=K * Fin, wT=W3[:, k, :], wT_stride=K * Fout) for k in range(K)]
             E.cheb_call(tp, N, site.rows_in, Fin, terms, dx)
         return dx, dW, db, None, None, None
 

@@ -70,6 +70,12 @@ typedef struct {
   const float* w2;    /* -> accumulator 1 (NULL: none) */
   const float* wc;    /* condition rows for accumulator 0 (NULL: none) */
   const float* wc2;   /* condition rows for accumulator 1 (NULL: none) */
+  /* optional K-major copies of w / w2 (element (f, c) = wT[c * wT_stride + f]); when given for every term and the
+   * shapes allow it the contraction runs on the tcgen05 tensor cores (3xTF32, fp32-accurate), else on the fp32 pipe */
+  const float* wT;
+  const float* w2T;
+  int wT_stride;
+  int w2T_stride;
 } cape_term;
 
 enum {
@@ -95,6 +101,9 @@ typedef struct {
   float* out;          /* [N, rows_out, ncols] */
   float* out2;         /* [N, rows_out, ncols] or NULL */
 } cape_conv_args;
+
+/* Process-wide switch for the tcgen05 path of cape_cheb_fwd (default on); returns the previous setting. */
+int cape_set_tensor_cores(int enable);
 
 /* Forward of chebyshev5 (+poolwT, +b1leakyrelu, +fit_cond_dim/concat) -- lib/models.py:69-103,105-109,
  * 129-152,813-832; also the data-gradient pass (same form with transposed operators and weights). */

@@ -195,3 +195,32 @@ def train_step(h, cfg, N=2, ref_compat=False, step=100, seed=123, dtype=torch.fl
         upd = np.abs(params[k].reshape(-1) - v.numpy().reshape(-1)).max()
         out["param-update " + k] = float(d / max(upd, 1e-20))
     return out
+
+
+def set_tensor_cores(on):
+    from cape_b200 import _lib
+    return _lib.load().cape_set_tensor_cores(1 if on else 0)
+
+
+def tc_vs_simt(h):
+    """tcgen05 (3xTF32) path vs the fp32 SIMT path of the same entry point, on layer shapes of the network."""
+    from cape_b200 import ops
+    out = {}
+    g = torch.Generator(device="cuda").manual_seed(5)
+    cases = [("enc conv4 L3 128->128 K=2 +pool", h["L"][3], 2, 128, 128, 4, None, h["D"][3]),
+             ("enc conv8 L7 512->512 K=2", h["L"][7], 2, 512, 512, 3, None, None),
+             ("dec-like L5 320->128 K=2 +unpool", h["L"][5], 2, 320, 128, 3, h["U"][5], None),
+             ("disc conv2 Ld1 64->64 K=3 +pool", h["L_d"][1], 3, 64, 64, 5, None, h["D_d"][1]),
+             ("top L0 64->32 K=2", h["L"][0], 2, 64, 32, 2, None, None)]
+    for tag, L, K, Fin, Fout, N, U, D in cases:
+        Min = U.shape[1] if U is not None else L.shape[0]
+        x = torch.randn(N, Min, Fin, device="cuda", generator=g)
+        W = torch.randn(Fin * K, Fout, device="cuda", generator=g) * 0.1
+        b = torch.randn(Fout, device="cuda", generator=g) * 0.1
+        prev = set_tensor_cores(True)
+        y_tc = ops.chebyshev5(x, L, W, K, bias=b, activation="b1leakyrelu", pool=D, unpool=U)
+        set_tensor_cores(False)
+        y_si = ops.chebyshev5(x, L, W, K, bias=b, activation="b1leakyrelu", pool=D, unpool=U)
+        set_tensor_cores(prev)
+        out["tc-vs-simt " + tag] = rel(y_tc.cpu().numpy(), y_si.cpu().numpy())
+    return out

@@ -53,6 +53,20 @@ def test_train_step_reference_quirks(hierarchy, cfg):
     _assert_all(parity.train_step(hierarchy, cfg, N=2, ref_compat=True))
 
 
+def test_tensor_core_path_matches_simt(hierarchy):
+    """The tcgen05 3xTF32 contraction and the fp32 FFMA contraction are two implementations of one entry point."""
+    _assert_all(parity.tc_vs_simt(hierarchy), tol=2e-5)
+
+
+def test_train_step_simt_only(hierarchy, cfg):
+    """Same full-step parity with the tensor-core path switched off (every layer on the fp32 SIMT kernels)."""
+    prev = parity.set_tensor_cores(False)
+    try:
+        _assert_all(parity.train_step(hierarchy, cfg, N=2))
+    finally:
+        parity.set_tensor_cores(prev)
+
+
 def test_train_step_odd_batch(hierarchy, cfg):
     """Batch that does not divide the 128-row tiles; other seed."""
     _assert_all(parity.train_step(hierarchy, cfg, N=5, seed=7))
