@@ -80,6 +80,28 @@ __device__ __forceinline__ void fma4(float4& a, float s, const float4& x) {
   a.x = fmaf(s, x.x, a.x); a.y = fmaf(s, x.y, a.y); a.z = fmaf(s, x.z, a.z); a.w = fmaf(s, x.w, a.w);
 }
 
+// v += sum_j w[r, j] * src_row(idx[r, j])  for one float4 column group.  Taps are fetched four at a time (the
+// tables are padded to a multiple of 4, empty slots idx = -1 / w = 0) so that four independent neighbour-row loads
+// are in flight per batch instead of one dependent load per tap.
+__device__ __forceinline__ void ell_gather4(const OpView& op, int r, const float* base, size_t stride, float4& v) {
+  const int4* ip = reinterpret_cast<const int4*>(op.idx + (size_t)r * op.width);
+  const float4* wp = reinterpret_cast<const float4*>(op.w + (size_t)r * op.width);
+  const int nb = op.width >> 2;
+  int4 id = __ldg(ip);
+  for (int b = 0; b < nb; ++b) {
+    if (id.x < 0) break;
+    const float4 ww = __ldg(wp + b);
+    int4 idn = make_int4(-1, -1, -1, -1);
+    if (b + 1 < nb) idn = __ldg(ip + b + 1);
+    const float4 x0 = ldg4(base + (size_t)id.x * stride);
+    const float4 x1 = ldg4(base + (size_t)max(id.y, 0) * stride);
+    const float4 x2 = ldg4(base + (size_t)max(id.z, 0) * stride);
+    const float4 x3 = ldg4(base + (size_t)max(id.w, 0) * stride);
+    fma4(v, ww.x, x0); fma4(v, ww.y, x1); fma4(v, ww.z, x2); fma4(v, ww.w, x3);
+    id = idn;
+  }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace cape

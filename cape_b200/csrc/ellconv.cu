@@ -27,14 +27,7 @@ __device__ __forceinline__ void gather_A(const TermDev& tm, int f0, const int* s
         if (tm.op.idx == nullptr) {
           v = ldg4(base + (size_t)r * tm.src_stride);
         } else {
-          const int32_t* ip = tm.op.idx + (size_t)r * tm.op.width;
-          const float* wp = tm.op.w + (size_t)r * tm.op.width;
-          for (int j = 0; j < tm.op.width; ++j) {
-            const int id = __ldg(ip + j);
-            if (id < 0) break;
-            const float ww = __ldg(wp + j);
-            fma4(v, ww, ldg4(base + (size_t)id * tm.src_stride));
-          }
+          ell_gather4(tm.op, r, base, (size_t)tm.src_stride, v);
         }
       }
       ra[4 * i + 0] = v.x; ra[4 * i + 1] = v.y; ra[4 * i + 2] = v.z; ra[4 * i + 3] = v.w;
@@ -356,13 +349,7 @@ __device__ __forceinline__ void dw_gather(const DwParams& p, long long rbase, lo
         if (p.op.idx == nullptr) {
           v = ldg4(base + (size_t)r * p.src_stride);
         } else {
-          const int32_t* ip = p.op.idx + (size_t)r * p.op.width;
-          const float* wp = p.op.w + (size_t)r * p.op.width;
-          for (int j = 0; j < p.op.width; ++j) {
-            const int id = __ldg(ip + j);
-            if (id < 0) break;
-            fma4(v, __ldg(wp + j), ldg4(base + (size_t)id * p.src_stride));
-          }
+          ell_gather4(p.op, r, base, (size_t)p.src_stride, v);
         }
       }
       ra[4 * i] = v.x; ra[4 * i + 1] = v.y; ra[4 * i + 2] = v.z; ra[4 * i + 3] = v.w;
@@ -560,11 +547,7 @@ __global__ void __launch_bounds__(256) resample_kernel(OpView op, const float* _
   if (vec) {
     for (int f = lane * 4; f < F; f += 128) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int j = 0; j < op.width; ++j) {
-        const int id = __ldg(ip + j);
-        if (id < 0) break;
-        fma4(v, __ldg(wp + j), ldg4(base + (size_t)id * F + f));
-      }
+      ell_gather4(op, r, base + f, (size_t)F, v);
       *reinterpret_cast<float4*>(out + f) = v;
     }
   } else {

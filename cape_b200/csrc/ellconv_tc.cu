@@ -176,13 +176,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ellconv_tc_kernel(const __grid_
             if (tm.op.idx == nullptr) {
               v = ldg4(base + (size_t)r * tm.src_stride);
             } else {
-              const int32_t* ip = tm.op.idx + (size_t)r * tm.op.width;
-              const float* wp = tm.op.w + (size_t)r * tm.op.width;
-              for (int j = 0; j < tm.op.width; ++j) {
-                const int id = __ldg(ip + j);
-                if (id < 0) break;
-                fma4(v, __ldg(wp + j), ldg4(base + (size_t)id * tm.src_stride));
-              }
+              ell_gather4(tm.op, r, base, (size_t)tm.src_stride, v);
             }
           }
           split_store(v, a_hi, a_lo, (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4)));

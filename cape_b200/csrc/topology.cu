@@ -49,7 +49,11 @@ extern "C" int cape_topology_add_operator(cape_topology* t, int rows_out, int ro
                                           const int32_t* idx_host, const float* w_host) {
   CAPE_REQUIRE(t && idx_host && w_host, "null pointer");
   CAPE_REQUIRE(rows_out > 0 && rows_in > 0 && width > 0, "bad operator shape");
-  const size_t n = (size_t)rows_out * width;
+  // device tables are padded to a width that is a multiple of 4 so kernels can fetch 4 taps with one 16-byte load
+  const int width4 = (width + 3) / 4 * 4;
+  const size_t n = (size_t)rows_out * width4;
+  std::vector<int32_t> idx_p(n, -1);
+  std::vector<float> w_p(n, 0.f);
   std::vector<float> rowsum(rows_out, 0.f);
   for (int r = 0; r < rows_out; ++r) {
     double s = 0.0;
@@ -60,17 +64,19 @@ extern "C" int cape_topology_add_operator(cape_topology* t, int rows_out, int ro
       CAPE_REQUIRE(!ended, "ELL rows must be left-packed (no valid slot after an empty one)");
       CAPE_REQUIRE(id < rows_in, "ELL column index out of range");
       s += (double)w_host[(size_t)r * width + j];
+      idx_p[(size_t)r * width4 + j] = id;
+      w_p[(size_t)r * width4 + j] = w_host[(size_t)r * width + j];
     }
     rowsum[r] = (float)s;
   }
   EllOp o;
-  o.rows_out = rows_out; o.rows_in = rows_in; o.width = width;
+  o.rows_out = rows_out; o.rows_in = rows_in; o.width = width4;
   CAPE_CHECK_CUDA(cudaSetDevice(t->device));
   CAPE_CHECK_CUDA(cudaMalloc(&o.idx, n * sizeof(int32_t)));
   CAPE_CHECK_CUDA(cudaMalloc(&o.w, n * sizeof(float)));
   CAPE_CHECK_CUDA(cudaMalloc(&o.rowsum, rows_out * sizeof(float)));
-  CAPE_CHECK_CUDA(cudaMemcpy(o.idx, idx_host, n * sizeof(int32_t), cudaMemcpyHostToDevice));
-  CAPE_CHECK_CUDA(cudaMemcpy(o.w, w_host, n * sizeof(float), cudaMemcpyHostToDevice));
+  CAPE_CHECK_CUDA(cudaMemcpy(o.idx, idx_p.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CAPE_CHECK_CUDA(cudaMemcpy(o.w, w_p.data(), n * sizeof(float), cudaMemcpyHostToDevice));
   CAPE_CHECK_CUDA(cudaMemcpy(o.rowsum, rowsum.data(), rows_out * sizeof(float), cudaMemcpyHostToDevice));
   t->ops.push_back(o);
   return (int)t->ops.size() - 1;

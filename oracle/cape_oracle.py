@@ -83,6 +83,13 @@ class Oracle:
         rd = cfg.get("reduce_dim", 64)
         self.reduce_rate = self.F[-1] // rd if rd > 0 else 1  # models.py:254-257
         self.reduce_dim = rd
+        # Optional {site name: bool tensor}: branch decisions (pre-activation > 0) imposed on the (leaky-)ReLUs.
+        # Two fp32 implementations round pre-activations differently, so ~1e-6 of them change sign; with the
+        # masks of the implementation under test imposed, the gradient comparison is exact up to rounding
+        # instead of being dominated by a handful of flipped units.  Entries may contain only some rows
+        # (pooled sites): `mask_rows[name]` then lists the rows they refer to.
+        self.masks = None
+        self.mask_rows = {}
 
     # ---- ops ---------------------------------------------------------------------------------------
     def chebyshev5(self, x, Lt, W, K):
@@ -101,9 +108,22 @@ class Oracle:
         xk = xk.permute(3, 1, 2, 0).reshape(N * M, Fin * K)     # :98-99
         return (xk @ W).reshape(N, M, -1)                       # :102-103
 
-    def b1leakyrelu(self, x, b):
+    def _act(self, v, slope, site):
+        """(leaky-)ReLU of the pre-activation v; honours an imposed branch mask for `site` if one was given."""
+        pos = v > 0
+        if self.masks is not None and site in self.masks:
+            m = self.masks[site]
+            rows = self.mask_rows.get(site)
+            if rows is None:
+                pos = m
+            else:
+                pos = pos.clone()
+                pos[:, rows] = m
+        return torch.where(pos, v, slope * v)
+
+    def b1leakyrelu(self, x, b, site=None):
         """models.py:105-109 (tf.nn.leaky_relu default alpha=0.2)."""
-        return torch.nn.functional.leaky_relu(x + b.reshape(1, 1, -1), 0.2)
+        return self._act(x + b.reshape(1, 1, -1), 0.2, site)
 
     def poolwT(self, x, S):
         """models.py:129-152."""
@@ -117,10 +137,10 @@ class Oracle:
         """models.py:813-832."""
         return y.reshape(x.shape[0], 1, -1) * torch.ones(x.shape[0], x.shape[1], y.shape[-1], dtype=x.dtype)
 
-    def dense(self, x, P, scope, act=None):
+    def dense(self, x, P, scope, act=None, site=None):
         y = x @ P[scope + "/dense/kernel"] + P[scope + "/dense/bias"]
         if act == "leaky":
-            y = torch.nn.functional.leaky_relu(y, 0.2)
+            y = self._act(y, 0.2, site)
         return y
 
     def gn(self, x, gamma, beta, G=32, eps=1e-5):
@@ -136,19 +156,18 @@ class Oracle:
         return out.permute(0, 2, 1)
 
     # ---- network -----------------------------------------------------------------------------------
-    def condition(self, y, P, name, nz_cond, nlayers):
+    def condition(self, y, P, name, nz_cond, nlayers, tag=""):
         """models.py:479-511."""
         scope = "condition_%s" % name
-        y_dim = y.shape[-1]
         if nlayers == 1:
             return self.dense(y, P, scope + "/fc1")
-        y = self.dense(y, P, scope + "/fc1", act="leaky")
+        y = self.dense(y, P, scope + "/fc1", act="leaky", site="cond_%s%s" % (name, tag))
         return self.dense(y, P, scope + "/fc2")
 
-    def cond_embeddings(self, cond, cond2, P):
+    def cond_embeddings(self, cond, cond2, P, tag=""):
         """models.py:284-286: pose net has nlayers=2 hard-coded, clothing net n_layer_cond."""
-        y = self.condition(cond, P, "pose", self.cfg["nz_cond"], 2)
-        y2 = self.condition(cond2, P, "clo_label", self.cfg["nz_cond2"], self.cfg.get("n_layer_cond", 1))
+        y = self.condition(cond, P, "pose", self.cfg["nz_cond"], 2, tag)
+        y2 = self.condition(cond2, P, "clo_label", self.cfg["nz_cond2"], self.cfg.get("n_layer_cond", 1), tag)
         return y, y2
 
     def encoder(self, x, P):
@@ -157,7 +176,7 @@ class Oracle:
         for i in range(len(self.F)):
             sc = s + "encoder_conv%d" % (i + 1)
             x = self.chebyshev5(x, self.Lt[i], P[sc + "/weights"], self.K[i])     # cnp :164
-            x = self.b1leakyrelu(x, P[sc + "/bias"])                              # :166
+            x = self.b1leakyrelu(x, P[sc + "/bias"], site="enc%d" % (i + 1))      # :166
             x = self.poolwT(x, self.Dm[i])                                        # :168
         if self.reduce_dim > 0:
             x = self.chebyshev5(x, self.Lt[-1], P[s + "1x1-conv/weights"], 1)      # :551
@@ -171,7 +190,7 @@ class Oracle:
         x = self.poolwT(x, self.Um[-i - 1])
         Lt = self.Lt[-i - 2]
         x_gc = self.chebyshev5(x, Lt, P[scope + "/graph_conv/weights"], self.K[-i - 1])
-        x_gc = torch.relu(x_gc)
+        x_gc = self._act(x_gc, 0.0, "dec%d" % (i + 1))                             # tf.nn.relu, :785
         x_aff = self.chebyshev5(x, Lt, P[scope + "/affine/weights"], 1)
         return x_aff + x_gc
 
@@ -193,7 +212,7 @@ class Oracle:
     def decoder_cond_vert(self, z_total, y, y2, P):
         """models.py:564-617 with use_res_block_dec=1."""
         s = "generator/decoder/"
-        x = self.dense(z_total, P, s + "fc1", act="leaky")                       # :582
+        x = self.dense(z_total, P, s + "fc1", act="leaky", site="dec_fc1")        # :582
         x = x.reshape(x.shape[0], self.p[-1], -1)                                # :584
         if self.reduce_dim > 0:
             x = self.chebyshev5(x, self.Lt[-1], P[s + "1x1-conv/weights"], 1)     # :588
@@ -214,13 +233,13 @@ class Oracle:
         z_total = torch.cat([z, y, y2], 1)                                        # :641
         return self.decoder_cond_vert(z_total, y, y2, P), z_mean, z_logvar
 
-    def discriminator(self, x, y, y2, P):
+    def discriminator(self, x, y, y2, P, tag=""):
         """models.py:648-678 (pred_map uses self.poly_order[-1], not Kd: :676)."""
         x = torch.cat([x, self.fit_cond_dim(x, y), self.fit_cond_dim(x, y2)], -1)
         for i in range(len(self.Dm_d)):
             sc = "discriminator/shared/conv%d" % (i + 1)
             x = self.chebyshev5(x, self.Lt_d[i], P[sc + "/weights"], self.Kd)     # cnp_d :803
-            x = self.b1leakyrelu(x, P[sc + "/bias"])
+            x = self.b1leakyrelu(x, P[sc + "/bias"], site="disc%d%s" % (i + 1, tag))
             x = self.poolwT(x, self.Dm_d[i])
         return self.chebyshev5(x, self.Lt_d[-1], P["discriminator/prediction_map/weights"], self.K[-1])
 
@@ -290,11 +309,11 @@ def train_update(oracle, P, mom, batch, step, edges, ref_compat=False, clip=5.0)
     """
     cfg = oracle.cfg
     Pg = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
-    y, y2 = oracle.cond_embeddings(batch["cond_g"], batch["cond2_g"], Pg)
-    yd, y2d = oracle.cond_embeddings(batch["cond_d"], batch["cond2_d"], Pg)
+    y, y2 = oracle.cond_embeddings(batch["cond_g"], batch["cond2_g"], Pg, tag="_g")
+    yd, y2d = oracle.cond_embeddings(batch["cond_d"], batch["cond2_d"], Pg, tag="_d")
     x_hat, zm, zl = oracle.generator(batch["x_g"], y, y2, batch["eps"], Pg)
-    d_real = oracle.discriminator(batch["x_d"], yd, y2d, Pg)
-    d_fake = oracle.discriminator(x_hat, y, y2, Pg)
+    d_real = oracle.discriminator(batch["x_d"], yd, y2d, Pg, tag="_real")
+    d_fake = oracle.discriminator(x_hat, y, y2, Pg, tag="_fake")
     L = oracle.losses(x_hat, batch["gt"], zm, zl, d_real, d_fake, Pg, edges)
     gn = g_var_names(Pg, cfg.get("optim_condnet", True))
     dn = d_var_names(Pg)
@@ -314,5 +333,6 @@ def train_update(oracle, P, mom, batch, step, edges, ref_compat=False, clip=5.0)
             P[k] = P[k] - lr * mom[k]
     out = {k: float(v) for k, v in L.items()}
     out["grads"] = {k: g.detach() for k, g in zip(gn + dn, list(grads_g) + list(grads_d))}
+    out["mom"] = {k: mom[k].detach() for k in gn + dn}
     out["x_hat"] = x_hat.detach()
     return out

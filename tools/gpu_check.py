@@ -27,6 +27,7 @@ def main():
             ("step", lambda: parity.train_step(h, cfg, N=2)),
             ("step_ref", lambda: parity.train_step(h, cfg, N=2, ref_compat=True)),
             ("step_rawinit", lambda: parity.train_step(h, cfg, N=2, fc_scale=1.0)),
+            ("step_nomask", lambda: parity.train_step(h, cfg, N=2, impose_masks=False)),
             ("step_n5", lambda: parity.train_step(h, cfg, N=5, seed=7))]
     allres = {}
     for name, fn in jobs:
