@@ -5,7 +5,7 @@
 // exact remainder), acc += a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32 accumulation in TMEM; the dropped a_lo*b_lo
 // term is ~2^-22 relative, so results stay within the 1e-4 parity gate with a wide margin.
 //
-// CTA = 9 warps.  Warps 0-7 build operand tiles: the Chebyshev-basis chunk A[128 rows x 32 k] is gathered from
+// CTA = 9 warps owning 128 output rows x ALL output columns.  Warps 0-7 build operand tiles: the Chebyshev-basis chunk A[128 rows x 32 k] is gathered from
 // neighbour rows with float4 loads (same ELL tables as the SIMT path), split into hi/lo and written to shared
 // memory in the canonical K-major SWIZZLE_128B UMMA layout; the weight chunk B[BN x 32 k] (K-major copy of W) is
 // loaded and split the same way.  Warp 8 issues tcgen05.mma (kind::tf32, M=128, N=BN, K=8; 12 per chunk, 24
@@ -98,34 +98,39 @@ __device__ __forceinline__ void split_store(float4 v, char* hi_tile, char* lo_ti
 
 template <int BN, bool DUAL>
 struct TcCfg {
-  static constexpr int B_TILE_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + (DUAL ? 4 : 2) * B_TILE_BYTES;
-  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > MAX_STAGES ? MAX_STAGES : STAGES_RAW;
-  static constexpr int TMEM_COLS = DUAL ? 2 * BN : BN;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + QS_FLOATS * 4 + 2 * BM * 4 + 256;
-  static_assert(STAGES >= 2, "need at least a double buffer");
+  static constexpr int B_TILE_BYTES = BN * 128;                       // one hi or lo tile of BN weight rows x 32 k
+  static constexpr int A_STAGE_BYTES = 2 * A_TILE_BYTES;              // hi + lo
+  static constexpr int B_STAGE_BYTES = (DUAL ? 4 : 2) * B_TILE_BYTES;  // hi + lo (+ second weight set)
+  static constexpr int A_STAGES = 2;
+  static constexpr int B_STAGES = (B_STAGE_BYTES * 3 <= 96 * 1024) ? 3 : 2;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES +
+                                    QS_FLOATS * 4 + 2 * BM * 4 + 256;
 };
 
+// One CTA = 128 output rows x ALL output columns (ncols <= 512, or <= 256 with two accumulators): the gathered
+// basis chunk A is built once and reused by every BN-wide column sub-tile, whose weight chunks stream through
+// their own ring.  TMEM holds the whole [128 x ncols] fp32 accumulator (x2 for the affine block).
 template <int BN, bool DUAL>
-__global__ void __launch_bounds__(TC_THREADS, 1) ellconv_tc_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) ellconv_tc_kernel(const __grid_constant__ ConvParams p, int nct,
+                                                                   int tmem_cols) {
   using Cfg = TcCfg<BN, DUAL>;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int SA = Cfg::A_STAGES, SB = Cfg::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: required by SWIZZLE_128B operand tiles
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  char* stage_base = smem;
-  float* qs = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  char* a_ring = smem;
+  char* b_ring = smem + SA * Cfg::A_STAGE_BYTES;
+  float* qs = reinterpret_cast<float*>(b_ring + SB * Cfg::B_STAGE_BYTES);
   int* s_n = reinterpret_cast<int*>(qs + QS_FLOATS);
   int* s_r = s_n + BM;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_r + BM);        // full[STAGES], empty[STAGES], accum
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_r + BM);   // a_full[4] a_empty[4] b_full[4] b_empty[4] accum
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * MAX_STAGES + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long row0 = (long long)blockIdx.x * BM;
-  const int col0 = blockIdx.y * BN;
-
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES), bar_accum = smem_u32(bars + 2 * MAX_STAGES);
+  const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + MAX_STAGES);
+  const uint32_t bar_bfull = smem_u32(bars + 2 * MAX_STAGES), bar_bempty = smem_u32(bars + 3 * MAX_STAGES);
+  const uint32_t bar_accum = smem_u32(bars + 4 * MAX_STAGES);
 
   if (tid < BM) {
     const long long R = row0 + tid;
@@ -134,95 +139,100 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ellconv_tc_kernel(const __grid_
   }
   if (warp == TC_PROD_WARPS) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, TC_PROD_WARPS); mbar_init(bar_empty + 8 * s, 1); }
+      for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, TC_PROD_WARPS); mbar_init(bar_aempty + 8 * s, 1); }
+      for (int s = 0; s < SB; ++s) { mbar_init(bar_bfull + 8 * s, TC_PROD_WARPS); mbar_init(bar_bempty + 8 * s, 1); }
       mbar_init(bar_accum, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+                 "r"((uint32_t)tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc1_col = (uint32_t)(nct * BN);            // second accumulator starts after the first
 
-  // chunk sequence: for each term, ceil(F/32) chunks
   if (warp < TC_PROD_WARPS) {
     // =========================== producers ===========================
     const int l8 = tid & 7, rs = tid >> 3;       // 8 lanes per 128-byte row, 32 row slots
-    int stage = 0;
-    uint32_t phase = 0;
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
     for (int t = 0; t < p.nterms; ++t) {
       const TermDev& tm = p.terms[t];
       const bool has2 = DUAL && tm.w2T != nullptr;
       for (int f0 = 0; f0 < tm.F; f0 += BK) {
-        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        char* st = stage_base + (size_t)stage * Cfg::STAGE_BYTES;
-        char* a_hi = st;
-        char* a_lo = st + A_TILE_BYTES;
-        char* b_hi = st + 2 * A_TILE_BYTES;
-        char* b_lo = b_hi + Cfg::B_TILE_BYTES;
         const int f = f0 + l8 * 4;
-        // ---- A: gather 4 rows per thread
+        // ---- A chunk: gather 4 rows per thread, split, store swizzled
+        mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
+        {
+          char* a_hi = a_ring + (size_t)sa * Cfg::A_STAGE_BYTES;
+          char* a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = rs + 32 * i;
-          const int n = s_n[row], r = s_r[row];
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (n >= 0 && f < tm.F) {
-            const float* base = tm.src + (size_t)n * tm.src_rows * tm.src_stride + f;
-            if (tm.op.idx == nullptr) {
-              v = ldg4(base + (size_t)r * tm.src_stride);
-            } else {
-              ell_gather4(tm.op, r, base, (size_t)tm.src_stride, v);
+          for (int i = 0; i < 4; ++i) {
+            const int row = rs + 32 * i;
+            const int n = s_n[row], r = s_r[row];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n >= 0 && f < tm.F) {
+              const float* base = tm.src + (size_t)n * tm.src_rows * tm.src_stride + f;
+              if (tm.op.idx == nullptr) v = ldg4(base + (size_t)r * tm.src_stride);
+              else ell_gather4(tm.op, r, base, (size_t)tm.src_stride, v);
+            }
+            split_store(v, a_hi, a_lo, (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4)));
+          }
+          fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
+          if (++sa == SA) { sa = 0; pha ^= 1; }
+        }
+        // ---- B chunks: one [BN x 32] K-major weight tile (hi/lo) per column sub-tile
+        for (int cs = 0; cs < nct; ++cs) {
+          mbar_wait(bar_bempty + 8 * sb, phb ^ 1);
+          char* b_hi = b_ring + (size_t)sb * Cfg::B_STAGE_BYTES;
+          char* b_lo = b_hi + Cfg::B_TILE_BYTES;
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i) {
+            const int cl = rs + 32 * i;
+            const int c = cs * BN + cl;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < p.ncols && f < tm.F) v = ldg4(tm.wT + (size_t)c * tm.wT_stride + f);
+            const uint32_t off = (uint32_t)(cl * 128 + ((l8 ^ (cl & 7)) << 4));
+            split_store(v, b_hi, b_lo, off);
+            if (DUAL) {
+              if (has2) {
+                float4 v2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < p.ncols && f < tm.F) v2 = ldg4(tm.w2T + (size_t)c * tm.w2T_stride + f);
+                split_store(v2, b_lo + Cfg::B_TILE_BYTES, b_lo + 2 * Cfg::B_TILE_BYTES, off);
+              }
             }
           }
-          split_store(v, a_hi, a_lo, (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4)));
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_bfull + 8 * sb);
+          if (++sb == SB) { sb = 0; phb ^= 1; }
         }
-        // ---- B (and B2): rows = output columns, K-major copy of the weights
-#pragma unroll
-        for (int i = 0; i < BN / 32; ++i) {
-          const int c = rs + 32 * i;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (col0 + c < p.ncols && f < tm.F) v = ldg4(tm.wT + (size_t)(col0 + c) * tm.wT_stride + f);
-          const uint32_t off = (uint32_t)(c * 128 + ((l8 ^ (c & 7)) << 4));
-          split_store(v, b_hi, b_lo, off);
-          if (DUAL) {
-            if (has2) {
-              float4 v2 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (col0 + c < p.ncols && f < tm.F) v2 = ldg4(tm.w2T + (size_t)(col0 + c) * tm.w2T_stride + f);
-              split_store(v2, b_lo + Cfg::B_TILE_BYTES, b_lo + 2 * Cfg::B_TILE_BYTES, off);
-            }
-          }
-        }
-        fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
 
-    // ---- condition broadcast vectors (same as the SIMT kernel): q[s][slot][c] = cond[n0+s,:] @ Wc_slot[:, col0+c]
+    // ---- condition broadcast vectors: q[s][slot][c] = cond[n0+s,:] @ Wc_slot[:, c]
     const int n_first = s_n[0];
     if (p.nslots > 0) {
       int n_last = n_first;
       for (int i = BM - 1; i > 0; --i)
         if (s_n[i] >= 0) { n_last = s_n[i]; break; }
       const int S = n_last - n_first + 1;
-      const int total = S * p.nslots * BN;
+      const int total = S * p.nslots * p.ncols;
       for (int o = tid; o < total; o += TC_PROD_THREADS) {
-        const int c = o % BN;
-        const int slot = (o / BN) % p.nslots;
-        const int s = o / (BN * p.nslots);
+        const int c = o % p.ncols;
+        const int slot = (o / p.ncols) % p.nslots;
+        const int s = o / (p.ncols * p.nslots);
+        const float* y = p.cond + (size_t)(n_first + s) * p.C;
+        const float* wc = p.slot_w[slot] + c;
+        const int ws = p.slot_acc[slot] ? p.terms[p.slot_term[slot]].w2_stride : p.terms[p.slot_term[slot]].w_stride;
         float q = 0.f;
-        if (col0 + c < p.ncols) {
-          const float* y = p.cond + (size_t)(n_first + s) * p.C;
-          const float* wc = p.slot_w[slot] + col0 + c;
-          const int ws = p.slot_acc[slot] ? p.terms[p.slot_term[slot]].w2_stride : p.terms[p.slot_term[slot]].w_stride;
-          for (int j = 0; j < p.C; ++j) q = fmaf(__ldg(y + j), __ldg(wc + (size_t)j * ws), q);
-        }
+        for (int j = 0; j < p.C; ++j) q = fmaf(__ldg(y + j), __ldg(wc + (size_t)j * ws), q);
         qs[o] = q;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
@@ -234,22 +244,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ellconv_tc_kernel(const __grid_
     const int quad = warp & 3, half = warp >> 2;          // TMEM lane quadrant of this warp; column half
     const int row = quad * 32 + lane;
     const int n = s_n[row], r = s_r[row];
-    constexpr int CPW = BN / 2;                           // columns per warp
+    const int cpw = p.ncols >> 1;                         // columns per warp (ncols is a multiple of 32)
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16);
     const size_t orow = (size_t)(row0 + row) * p.ncols;
 #pragma unroll 1
-    for (int g = 0; g < CPW / 16; ++g) {
-      const int cl = half * CPW + g * 16;                 // column within the tile
+    for (int g = 0; g < cpw / 16; ++g) {
+      const int c0 = half * cpw + g * 16;                 // first of 16 output columns
       float v0[16], v1[16];
-      tmem_ld16(taddr_row + (uint32_t)cl, v0);             // warp-collective: executed by every lane
-      if (DUAL) tmem_ld16(taddr_row + (uint32_t)(BN + cl), v1);
+      tmem_ld16(taddr_row + (uint32_t)c0, v0);             // warp-collective: executed by every lane
+      if (DUAL) tmem_ld16(taddr_row + acc1_col + (uint32_t)c0, v1);
       if (n < 0) continue;
-      const int c0 = col0 + cl;
-      if (c0 >= p.ncols) continue;
       for (int slot = 0; slot < p.nslots; ++slot) {
         const TermDev& tm = p.terms[p.slot_term[slot]];
         const float coef = tm.op.rowsum ? __ldg(tm.op.rowsum + r) : 1.f;
-        const float* q = qs + ((size_t)(n - n_first) * p.nslots + slot) * BN + cl;
+        const float* q = qs + ((size_t)(n - n_first) * p.nslots + slot) * p.ncols + c0;
         if (p.slot_acc[slot] == 0) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v0[j] = fmaf(coef, q[j], v0[j]);
@@ -306,34 +314,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ellconv_tc_kernel(const __grid_
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N=BN, M=128
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0, acc0_on = 0, acc1_on = 0;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0, acc0_on = 0, acc1_on = 0;
       for (int t = 0; t < p.nterms; ++t) {
         const bool has2 = DUAL && p.terms[t].w2T != nullptr;
         for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + (size_t)stage * Cfg::STAGE_BYTES);
-          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
-          const uint64_t b_hi = make_desc(sa + 2 * A_TILE_BYTES), b_lo = make_desc(sa + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES);
-          const uint64_t b2_hi = make_desc(sa + 2 * A_TILE_BYTES + 2 * Cfg::B_TILE_BYTES);
-          const uint64_t b2_lo = make_desc(sa + 2 * A_TILE_BYTES + 3 * Cfg::B_TILE_BYTES);
+          mbar_wait(bar_afull + 8 * sa, pha);
+          const uint32_t aaddr = smem_u32(a_ring + (size_t)sa * Cfg::A_STAGE_BYTES);
+          const uint64_t a_hi = make_desc(aaddr), a_lo = make_desc(aaddr + A_TILE_BYTES);
+          for (int cs = 0; cs < nct; ++cs) {
+            mbar_wait(bar_bfull + 8 * sb, phb);
+            tc_fence_after();
+            const uint32_t baddr = smem_u32(b_ring + (size_t)sb * Cfg::B_STAGE_BYTES);
+            const uint64_t b_hi = make_desc(baddr), b_lo = make_desc(baddr + Cfg::B_TILE_BYTES);
+            const uint64_t b2_hi = make_desc(baddr + 2 * Cfg::B_TILE_BYTES), b2_lo = make_desc(baddr + 3 * Cfg::B_TILE_BYTES);
+            const uint32_t d0 = tmem_base + (uint32_t)(cs * BN), d1 = d0 + acc1_col;
 #pragma unroll
-          for (int ks = 0; ks < BK / 8; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * 2);      // +32 bytes along K inside the 128-byte swizzle row
-            umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, acc0_on);
-            acc0_on = 1;
-            umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
-            umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
-            if (has2) {
-              umma_tf32(tmem_base + BN, a_hi + adv, b2_hi + adv, idesc, acc1_on);
-              acc1_on = 1;
-              umma_tf32(tmem_base + BN, a_lo + adv, b2_hi + adv, idesc, 1);
-              umma_tf32(tmem_base + BN, a_hi + adv, b2_lo + adv, idesc, 1);
+            for (int ks = 0; ks < BK / 8; ++ks) {
+              const uint64_t adv = (uint64_t)(ks * 2);    // +32 bytes along K inside the 128-byte swizzle row
+              // the very first MMA into a sub-tile's TMEM columns overwrites (TMEM is not zero-initialised)
+              umma_tf32(d0, a_hi + adv, b_hi + adv, idesc, ks == 0 ? acc0_on : 1u);
+              umma_tf32(d0, a_lo + adv, b_hi + adv, idesc, 1);
+              umma_tf32(d0, a_hi + adv, b_lo + adv, idesc, 1);
+              if (has2) {
+                umma_tf32(d1, a_hi + adv, b2_hi + adv, idesc, ks == 0 ? acc1_on : 1u);
+                umma_tf32(d1, a_lo + adv, b2_hi + adv, idesc, 1);
+                umma_tf32(d1, a_hi + adv, b2_lo + adv, idesc, 1);
+              }
             }
+            umma_commit(bar_bempty + 8 * sb);              // weight stage reusable once these MMAs have read it
+            if (++sb == SB) { sb = 0; phb ^= 1; }
           }
-          umma_commit(bar_empty + 8 * stage);              // stage reusable once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(bar_aempty + 8 * sa);                // basis stage reusable
+          if (++sa == SA) { sa = 0; pha ^= 1; }
+          acc0_on = 1;
+          if (has2) acc1_on = 1;
         }
       }
       umma_commit(bar_accum);                              // accumulators complete
@@ -344,7 +359,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ellconv_tc_kernel(const __grid_
   __syncthreads();
   if (warp == TC_PROD_WARPS) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols) : "memory");
   }
 }
 
@@ -357,8 +372,11 @@ int launch_one(const ConvParams& p, cudaStream_t st) {
                                          Cfg::SMEM_BYTES));
     configured = true;
   }
-  dim3 grid((unsigned)((p.total_rows + BM - 1) / BM), (unsigned)((p.ncols + BN - 1) / BN));
-  ellconv_tc_kernel<BN, DUAL><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+  const int nct = (p.ncols + BN - 1) / BN;
+  int cols = (DUAL ? 2 : 1) * nct * BN, tmem_cols = 32;
+  while (tmem_cols < cols) tmem_cols *= 2;
+  dim3 grid((unsigned)((p.total_rows + BM - 1) / BM), 1);
+  ellconv_tc_kernel<BN, DUAL><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, nct, tmem_cols);
   CAPE_CHECK_CUDA(cudaGetLastError());
   count_launches(1);
   return 1;
@@ -372,7 +390,9 @@ bool tensor_cores_enabled() { return g_tc_enabled; }
 int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaStream_t st) {
   (void)t;
   if (!g_tc_enabled) return 0;
-  if (p.ncols % 16 != 0 || p.ncols < 32 || !p.ovec) return 0;
+  if (p.ncols % 32 != 0 || p.ncols < 32 || !p.ovec) return 0;
+  if ((dual ? 2 : 1) * p.ncols > 512) return 0;              // the whole accumulator row must fit the 512 TMEM columns
+  if (p.ncols > 128 && p.ncols % 128 != 0) return 0;
   long long kred = 0;
   for (int i = 0; i < p.nterms; ++i) {
     const TermDev& tm = p.terms[i];
@@ -382,9 +402,8 @@ int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cu
   }
   if (kred < 64) return 0;                       // tiny reductions: the SIMT kernel is as good and simpler
   if (p.nslots > 0) {
-    const int bn = p.ncols >= 128 ? 128 : (p.ncols >= 64 ? 64 : 32);
     const long long max_samples = (BM - 1) / p.rows_out + 2;
-    if (max_samples * p.nslots * bn > QS_FLOATS) return 0;
+    if (max_samples * p.nslots * p.ncols > QS_FLOATS) return 0;
   }
   if (dual) {
     if (p.ncols >= 128) return launch_one<128, true>(p, st);

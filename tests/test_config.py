@@ -1,0 +1,66 @@
+"""parse_config: reference flags/defaults/precedence; the reference's own yaml files load unchanged."""
+import os
+
+import pytest
+
+from cape_b200.config_parser import model_params, parse_config
+
+REF_CFG = "/root/reference/configs"
+
+AFFINE_YAML = """dataset: dataset_male_4clotypes
+name: CAPE-affineconv_nz64_pose32_clotype32_male
+lambda_latent: 0.0008
+lambda_edge: 1.0
+num_conv_layers: 8
+nf: 64
+nz: 64
+nz_cond: 32
+nz_cond2: 32
+pose_type: rot
+cond_encoder: 0
+reduce_dim: 64
+lr: 0.008
+use_res_block: 0
+use_res_block_dec: 1
+affine: 1
+num_epochs: 60
+lr_warmup: 1
+decay_every: 2
+gender: male
+mode: demo
+vis_demo: 1
+some_unknown_key: 7
+"""
+
+
+def test_yaml_and_cli_precedence(tmp_path):
+    f = tmp_path / "c.yaml"
+    f.write_text(AFFINE_YAML)
+    args, d = parse_config(["--config", str(f)])
+    assert args.nz == 64 and args.affine == 1 and args.lr == 0.008 and args.mode == "demo"
+    assert args.batch_size == 16 and args.Kd == 3 and args.regularization == 2e-3      # argparse defaults
+    assert d is vars(args)
+    args, _ = parse_config(["--config", str(f), "--nz", "32", "--mode", "train", "--unknown_flag", "1"])
+    assert args.nz == 32 and args.mode == "train"                                      # CLI > file
+    p = model_params(args, n_train=1000)
+    assert p["F"] == [64, 64, 128, 128, 256, 256, 512, 512] and p["K"] == [2] * 8      # --K is ignored (main.py:65)
+    assert p["cond_dim"] == 126 and p["affine"] is True and p["decay_steps"] == 2 * 1000 / 16
+    assert "mode" not in p and "nf" not in p
+
+
+def test_defaults_without_file(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)                      # no configs/default_config.yaml here
+    args, _ = parse_config([])
+    assert args.nz == 18 and args.use_res_block_dec == 1 and args.optimizer == "sgd"
+    with pytest.raises(FileNotFoundError):
+        parse_config(["--config", "missing.yaml"])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG), reason="reference tree not present (GPU box)")
+def test_reference_configs_load_unchanged():
+    for fn in sorted(os.listdir(REF_CFG)):
+        args, _ = parse_config(["--config", os.path.join(REF_CFG, fn)])
+        if fn.startswith("CAPE-affineconv_nz64"):
+            assert (args.nz, args.nz_cond, args.nz_cond2, args.affine) == (64, 32, 32, 1)
+        if fn.startswith("CAPE_nz18"):
+            assert (args.nz, args.nz_cond, args.nz_cond2, args.affine) == (18, 24, 8, 0)
