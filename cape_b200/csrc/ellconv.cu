@@ -479,16 +479,27 @@ __global__ void __launch_bounds__(NT, 2) ellconv_dw_kernel(const __grid_constant
   }
 }
 
-__global__ void reduce_splits_kernel(const float* __restrict__ ws, int nsplit, int F, int ncols, float* __restrict__ dw,
-                                     long long dw_stride, int accumulate) {
+__global__ void __launch_bounds__(256) reduce_splits_kernel(const float* __restrict__ ws, int nsplit, int F, int ncols,
+                                                            float* __restrict__ dw, long long dw_stride,
+                                                            int accumulate) {
+  // 64 consecutive elements x 4 split lanes per CTA; fixed summation order (deterministic)
+  __shared__ float red[4][64];
   const long long total = (long long)F * ncols;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
+  const int el = threadIdx.x & 63, zl = threadIdx.x >> 6;
+  for (long long e0 = (long long)blockIdx.x * 64; e0 < total; e0 += (long long)gridDim.x * 64) {
+    const long long e = e0 + el;
     float s = 0.f;
-    for (int z = 0; z < nsplit; ++z) s += ws[(size_t)z * total + e];
-    const int f = (int)(e / ncols), c = (int)(e % ncols);
-    float* o = dw + (size_t)f * dw_stride + c;
-    *o = accumulate ? (*o + s) : s;
+    if (e < total)
+      for (int z = zl; z < nsplit; z += 4) s += ws[(size_t)z * total + e];
+    red[zl][el] = s;
+    __syncthreads();
+    if (zl == 0 && e < total) {
+      s = (red[0][el] + red[1][el]) + (red[2][el] + red[3][el]);
+      const int f = (int)(e / ncols), c = (int)(e % ncols);
+      float* o = dw + (size_t)f * dw_stride + c;
+      *o = accumulate ? (*o + s) : s;
+    }
+    __syncthreads();
   }
 }
 
@@ -657,6 +668,24 @@ extern "C" int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* strea
   CAPE_REQUIRE(a->src_stride >= a->F && a->dw_stride >= a->ncols, "bad strides");
   DwParams p{};
   if (get_op(t, a->op, a->rows_out, a->src_rows, &p.op) != 0) return -1;
+  {
+    int ns = 1;
+    const int rc = launch_ellconv_dw_tc(t, a, p.op, &ns, (cudaStream_t)stream);   // tcgen05 path when eligible
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      if (ns > 1) {
+        const long long total = (long long)a->F * a->ncols;
+        long long blocks = (total + 63) / 64;
+        if (blocks > 8LL * t->sm_count) blocks = 8LL * t->sm_count;
+        reduce_splits_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)t->workspace, ns, a->F,
+                                                                                 a->ncols, a->dw, a->dw_stride,
+                                                                                 a->accumulate);
+        CAPE_CHECK_CUDA(cudaGetLastError());
+        cape::count_launches(1);
+      }
+      return 0;
+    }
+  }
   p.N = a->N; p.rows_out = a->rows_out; p.ncols = a->ncols;
   p.total_rows = (long long)a->N * a->rows_out;
   p.src = a->src; p.F = a->F; p.src_rows = a->src_rows; p.src_stride = a->src_stride;
@@ -684,9 +713,9 @@ extern "C" int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* strea
   cape::count_launches(1);
   if (nsplit > 1) {
     const long long total = (long long)a->F * a->ncols;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 4 * t->sm_count) blocks = 4 * t->sm_count;
-    reduce_splits_kernel<<<blocks, 256, 0, st>>>((const float*)t->workspace, (int)nsplit, a->F, a->ncols, a->dw,
+    long long blocks = (total + 63) / 64;
+    if (blocks > 8LL * t->sm_count) blocks = 8LL * t->sm_count;
+    reduce_splits_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float*)t->workspace, (int)nsplit, a->F, a->ncols, a->dw,
                                                   a->dw_stride, a->accumulate);
     CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);

@@ -1,0 +1,326 @@
+// tcgen05 weight-gradient kernel:  dW_t[f, c] = sum_{n,v} A_t[n,v,f] * G[n,v,c]   (3xTF32, fp32 accumulate in TMEM)
+//
+// The reduction runs over the rows (up to N*6890 = 441k), so rows are the MMA K dimension and both operands are
+// "MN-major": the gathered basis rows A[row, f0..f0+127] (M = f contiguous) and the upstream-gradient rows
+// G[row, c..] (N = c contiguous) are written to shared memory exactly as they are read from HBM -- 128-byte
+// row segments -- in the canonical MN-major SWIZZLE_128B layout (8 k-rows x 32 floats per 1 KB atom).
+// One CTA owns a 128-wide slice of f, ALL output columns (<= 512 TMEM columns) and one split of the rows; the
+// basis chunk is gathered once per 32 rows and reused by every 128-column sub-tile of G.  Partial sums of the row
+// splits go to the topology workspace and are reduced deterministically (reduce_splits_kernel).
+#include "common.cuh"
+#include "ellconv_params.cuh"
+
+namespace cape {
+
+namespace {
+
+constexpr int DT_PROD_WARPS = 8;
+constexpr int DT_PROD_THREADS = DT_PROD_WARPS * 32;
+constexpr int DT_THREADS = DT_PROD_THREADS + 32;
+constexpr int DT_KCH = 32;                         // rows (K) per pipeline stage = 4 MMAs of K=8
+constexpr int DT_A_TILE = 4 * 4096;                // 128 f x 32 rows, hi or lo
+constexpr int DT_MAX_STAGES = 4;
+constexpr uint32_t DT_SPIN_LIMIT = 1u << 27;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > DT_SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// MN-major SWIZZLE_128B operand descriptor: LBO = 4096 B between consecutive 32-element MN blocks,
+// SBO = 1024 B between consecutive 8-row K groups (cute::UMMA::make_umma_desc<Major::MN>).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void split_store(float4 v, char* hi_tile, char* lo_tile, uint32_t off) {
+  float4 h, l;
+  h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+  h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+  h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+  h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+  *reinterpret_cast<float4*>(hi_tile + off) = h;
+  *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
+struct DwTcParams {
+  int rows_out, ncols, F, src_rows, src_stride;
+  long long total_rows, rows_per_split;
+  const float* src;
+  OpView op;
+  const float* g;
+  float* out;          // dw (nsplit == 1) or workspace [nsplit, F, ncols]
+  long long out_rs;
+  int nsplit, accumulate;
+};
+
+template <int BN>
+struct DtCfg {
+  static constexpr int G_TILE = (BN / 32) * 4096;             // BN columns x 32 rows, hi or lo
+  static constexpr int A_STAGE = 2 * DT_A_TILE;
+  static constexpr int G_STAGE = 2 * G_TILE;
+  static constexpr int A_STAGES = 2;
+  static constexpr int G_STAGES = 3;
+  static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_STAGE + G_STAGES * G_STAGE + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __grid_constant__ DwTcParams p, int nct,
+                                                                      int tmem_cols) {
+  using Cfg = DtCfg<BN>;
+  constexpr int SA = Cfg::A_STAGES, SG = Cfg::G_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  char* a_ring = smem;
+  char* g_ring = smem + SA * Cfg::A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(g_ring + SG * Cfg::G_STAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * DT_MAX_STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ftile = blockIdx.x * 128;
+  const long long rbeg = (long long)blockIdx.y * p.rows_per_split;
+  const long long rend = min(p.total_rows, rbeg + p.rows_per_split);
+  const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + DT_MAX_STAGES);
+  const uint32_t bar_gfull = smem_u32(bars + 2 * DT_MAX_STAGES), bar_gempty = smem_u32(bars + 3 * DT_MAX_STAGES);
+  const uint32_t bar_accum = smem_u32(bars + 4 * DT_MAX_STAGES);
+
+  if (warp == DT_PROD_WARPS) {
+    if (lane == 0) {
+      for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, DT_PROD_WARPS); mbar_init(bar_aempty + 8 * s, 1); }
+      for (int s = 0; s < SG; ++s) { mbar_init(bar_gfull + 8 * s, DT_PROD_WARPS); mbar_init(bar_gempty + 8 * s, 1); }
+      mbar_init(bar_accum, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long nchunks = (rend - rbeg + DT_KCH - 1) / DT_KCH;
+
+  if (warp < DT_PROD_WARPS) {
+    // =========================== producers ===========================
+    const int mb = lane >> 3, ch = lane & 7;       // 32-element MN block and 16-byte chunk of this lane's float4
+    int sa = 0, sg = 0;
+    uint32_t pha = 0, phg = 0;
+    for (long long kc = 0; kc < nchunks; ++kc) {
+      const long long rb = rbeg + kc * DT_KCH;
+      // ---- A: each warp gathers rows warp, warp+8, warp+16, warp+24 of the chunk (512 contiguous bytes per row)
+      mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
+      {
+        char* a_hi = a_ring + (size_t)sa * Cfg::A_STAGE;
+        char* a_lo = a_hi + DT_A_TILE;
+        const int f = ftile + lane * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = warp + 8 * i;
+          const long long R = rb + row;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (R < rend && f < p.F) {
+            const int n = (int)(R / p.rows_out), r = (int)(R % p.rows_out);
+            const float* base = p.src + (size_t)n * p.src_rows * p.src_stride + f;
+            if (p.op.idx == nullptr) v = ldg4(base + (size_t)r * p.src_stride);
+            else ell_gather4(p.op, r, base, (size_t)p.src_stride, v);
+          }
+          const int kg = row >> 3, kr = row & 7;
+          split_store(v, a_hi, a_lo, (uint32_t)(mb * 4096 + kg * 1024 + kr * 128 + ((ch ^ kr) << 4)));
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
+        if (++sa == SA) { sa = 0; pha ^= 1; }
+      }
+      // ---- G: one [32 rows x BN cols] tile per column sub-tile
+      for (int cs = 0; cs < nct; ++cs) {
+        mbar_wait(bar_gempty + 8 * sg, phg ^ 1);
+        char* g_hi = g_ring + (size_t)sg * Cfg::G_STAGE;
+        char* g_lo = g_hi + Cfg::G_TILE;
+        const int cl = lane * 4;
+        if (cl < BN) {
+          const int c = cs * BN + cl;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = warp + 8 * i;
+            const long long R = rb + row;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (R < rend && c < p.ncols) v = ldg4(p.g + (size_t)R * p.ncols + c);
+            const int kg = row >> 3, kr = row & 7;
+            split_store(v, g_hi, g_lo, (uint32_t)(mb * 4096 + kg * 1024 + kr * 128 + ((ch ^ kr) << 4)));
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_gfull + 8 * sg);
+        if (++sg == SG) { sg = 0; phg ^= 1; }
+      }
+    }
+
+    // =========================== epilogue: TMEM -> partial sums ===========================
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
+    const int quad = warp & 3, half = warp >> 2;
+    const int f = ftile + quad * 32 + lane;
+    const int cpw = p.ncols >> 1;
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float* orow = p.out + (p.nsplit > 1 ? (size_t)blockIdx.y * p.F * p.out_rs : 0) + (size_t)f * p.out_rs;
+#pragma unroll 1
+    for (int g = 0; g < cpw / 16; ++g) {
+      const int c0 = half * cpw + g * 16;
+      float v[16];
+      tmem_ld16(taddr_row + (uint32_t)c0, v);
+      if (f >= p.F) continue;
+      if (nchunks == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      }
+      if (p.nsplit == 1 && p.accumulate) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) orow[c0 + j] += v[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) orow[c0 + j] = v[j];
+      }
+    }
+    tc_fence_before();
+  } else {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      // D=F32, A=B=TF32, A and B MN-major (bits 15,16), N=BN, M=128
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int sa = 0, sg = 0;
+      uint32_t pha = 0, phg = 0, acc_on = 0;
+      for (long long kc = 0; kc < nchunks; ++kc) {
+        mbar_wait(bar_afull + 8 * sa, pha);
+        const uint32_t aaddr = smem_u32(a_ring + (size_t)sa * Cfg::A_STAGE);
+        for (int cs = 0; cs < nct; ++cs) {
+          mbar_wait(bar_gfull + 8 * sg, phg);
+          tc_fence_after();
+          const uint32_t gaddr = smem_u32(g_ring + (size_t)sg * Cfg::G_STAGE);
+          const uint32_t d = tmem_base + (uint32_t)(cs * BN);
+#pragma unroll
+          for (int ks = 0; ks < DT_KCH / 8; ++ks) {
+            const uint64_t a_hi = make_desc_mn(aaddr + ks * 1024), a_lo = make_desc_mn(aaddr + DT_A_TILE + ks * 1024);
+            const uint64_t g_hi = make_desc_mn(gaddr + ks * 1024), g_lo = make_desc_mn(gaddr + Cfg::G_TILE + ks * 1024);
+            umma_tf32(d, a_hi, g_hi, idesc, ks == 0 ? acc_on : 1u);
+            umma_tf32(d, a_lo, g_hi, idesc, 1);
+            umma_tf32(d, a_hi, g_lo, idesc, 1);
+          }
+          umma_commit(bar_gempty + 8 * sg);
+          if (++sg == SG) { sg = 0; phg ^= 1; }
+        }
+        umma_commit(bar_aempty + 8 * sa);
+        if (++sa == SA) { sa = 0; pha ^= 1; }
+        acc_on = 1;
+      }
+      umma_commit(bar_accum);
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == DT_PROD_WARPS) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols) : "memory");
+  }
+}
+
+template <int BN>
+int launch_dw(const DwTcParams& p, int ftiles, cudaStream_t st) {
+  using Cfg = DtCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    CAPE_CHECK_CUDA(cudaFuncSetAttribute(ellconv_dw_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int nct = (p.ncols + BN - 1) / BN;
+  int cols = nct * BN, tmem_cols = 32;
+  while (tmem_cols < cols) tmem_cols *= 2;
+  dim3 grid(ftiles, p.nsplit);
+  ellconv_dw_tc_kernel<BN><<<grid, DT_THREADS, Cfg::SMEM_BYTES, st>>>(p, nct, tmem_cols);
+  CAPE_CHECK_CUDA(cudaGetLastError());
+  count_launches(1);
+  return 1;
+}
+
+}  // namespace
+
+// returns 1 if launched (partials in workspace when *nsplit_out > 1), 0 if not eligible, <0 on error
+int launch_ellconv_dw_tc(const cape_topology* t, const cape_dw_args* a, const OpView& op, int* nsplit_out,
+                         cudaStream_t st) {
+  if (!tensor_cores_enabled()) return 0;
+  if (a->ncols % 32 != 0 || a->ncols < 32 || a->ncols > 512 || (a->ncols > 128 && a->ncols % 128 != 0)) return 0;
+  if (a->F % 4 != 0 || a->F < 32 || a->src_stride % 4 != 0 || !aligned16(a->src) || !aligned16(a->g)) return 0;
+  if (a->dw_stride % 4 != 0) { /* scalar stores are used anyway */ }
+  DwTcParams p{};
+  p.rows_out = a->rows_out; p.ncols = a->ncols; p.F = a->F; p.src_rows = a->src_rows; p.src_stride = a->src_stride;
+  p.total_rows = (long long)a->N * a->rows_out;
+  if (p.total_rows < 4096) return 0;
+  p.src = a->src; p.op = op; p.g = a->g;
+  const int ftiles = (a->F + 127) / 128;
+  long long nsplit = (2LL * t->sm_count + ftiles - 1) / ftiles;
+  const long long max_by_rows = (p.total_rows + 511) / 512;
+  if (nsplit > max_by_rows) nsplit = max_by_rows;
+  const long long per = (long long)a->F * a->ncols * (long long)sizeof(float);
+  if (nsplit > 1 && nsplit * per > t->workspace_bytes) nsplit = t->workspace_bytes / per;
+  if (nsplit < 1) nsplit = 1;
+  long long rps = (p.total_rows + nsplit - 1) / nsplit;
+  rps = (rps + DT_KCH - 1) / DT_KCH * DT_KCH;
+  nsplit = (p.total_rows + rps - 1) / rps;
+  p.rows_per_split = rps; p.nsplit = (int)nsplit; p.accumulate = a->accumulate;
+  if (nsplit == 1) { p.out = a->dw; p.out_rs = a->dw_stride; }
+  else { p.out = (float*)t->workspace; p.out_rs = a->ncols; }
+  *nsplit_out = (int)nsplit;
+  if (a->ncols >= 128) return launch_dw<128>(p, ftiles, st);
+  if (a->ncols >= 64) return launch_dw<64>(p, ftiles, st);
+  return launch_dw<32>(p, ftiles, st);
+}
+
+}  // namespace cape

@@ -233,24 +233,33 @@ def set_tensor_cores(on):
 
 
 def tc_vs_simt(h):
-    """tcgen05 (3xTF32) path vs the fp32 SIMT path of the same entry point, on layer shapes of the network."""
+    """tcgen05 (3xTF32) kernels vs the fp32 SIMT kernels of the same entry points (forward, dX, dW), on layer
+    shapes of the network and at row counts large enough to take the tensor-core weight-gradient path."""
     from cape_b200 import ops
     out = {}
     g = torch.Generator(device="cuda").manual_seed(5)
     cases = [("enc conv4 L3 128->128 K=2 +pool", h["L"][3], 2, 128, 128, 4, None, h["D"][3]),
-             ("enc conv8 L7 512->512 K=2", h["L"][7], 2, 512, 512, 3, None, None),
+             ("enc conv8 L7 512->512 K=2", h["L"][7], 2, 512, 512, 8, None, None),
              ("dec-like L5 320->128 K=2 +unpool", h["L"][5], 2, 320, 128, 3, h["U"][5], None),
              ("disc conv2 Ld1 64->64 K=3 +pool", h["L_d"][1], 3, 64, 64, 5, None, h["D_d"][1]),
+             ("enc conv5 L4 128->256 K=2", h["L"][4], 2, 128, 256, 4, None, None),
              ("top L0 64->32 K=2", h["L"][0], 2, 64, 32, 2, None, None)]
     for tag, L, K, Fin, Fout, N, U, D in cases:
         Min = U.shape[1] if U is not None else L.shape[0]
         x = torch.randn(N, Min, Fin, device="cuda", generator=g)
         W = torch.randn(Fin * K, Fout, device="cuda", generator=g) * 0.1
         b = torch.randn(Fout, device="cuda", generator=g) * 0.1
+        res = {}
         prev = set_tensor_cores(True)
-        y_tc = ops.chebyshev5(x, L, W, K, bias=b, activation="b1leakyrelu", pool=D, unpool=U)
-        set_tensor_cores(False)
-        y_si = ops.chebyshev5(x, L, W, K, bias=b, activation="b1leakyrelu", pool=D, unpool=U)
+        for on in (True, False):
+            set_tensor_cores(on)
+            xc, Wc = x.clone().requires_grad_(True), W.clone().requires_grad_(True)
+            y = ops.chebyshev5(xc, L, Wc, K, bias=b, activation="b1leakyrelu", pool=D, unpool=U)
+            if on:
+                dy = torch.randn(y.shape, device="cuda", generator=g)
+            y.backward(dy)
+            res[on] = (y.detach().cpu().numpy(), xc.grad.cpu().numpy(), Wc.grad.cpu().numpy())
         set_tensor_cores(prev)
-        out["tc-vs-simt " + tag] = rel(y_tc.cpu().numpy(), y_si.cpu().numpy())
+        for nm, a, bb in zip(("fwd", "dx", "dW"), res[True], res[False]):
+            out["tc-vs-simt %s %s" % (tag, nm)] = rel(a, bb)
     return out
