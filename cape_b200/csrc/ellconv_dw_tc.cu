@@ -3,7 +3,8 @@
 // The reduction runs over the rows (up to N*6890 = 441k), so rows are the MMA K dimension and both operands are
 // "MN-major": the gathered basis rows A[row, f0..f0+127] (M = f contiguous) and the upstream-gradient rows
 // G[row, c..] (N = c contiguous) are written to shared memory exactly as they are read from HBM -- 128-byte
-// row segments -- in the canonical MN-major SWIZZLE_128B layout (8 k-rows x 32 floats per 1 KB atom).
+// row segments -- in the one MN-major layout tcgen05 accepts for 32-bit operands, SWIZZLE_128B_BASE32B
+// (cute Layout_MN_SW128_32B_Atom: 4 k-rows x 32 floats per 512-byte atom, 32-byte chunks XOR-ed with the k-row).
 // One CTA owns a 128-wide slice of f, ALL output columns (<= 512 TMEM columns) and one split of the rows; the
 // basis chunk is gathered once per 32 rows and reused by every 128-column sub-tile of G.  Partial sums of the row
 // splits go to the topology workspace and are reduced deterministically (reduce_splits_kernel).
@@ -58,11 +59,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// MN-major SWIZZLE_128B operand descriptor: LBO = 4096 B between consecutive 32-element MN blocks,
-// SBO = 1024 B between consecutive 8-row K groups (cute::UMMA::make_umma_desc<Major::MN>).
+// MN-major SWIZZLE_128B_BASE32B operand descriptor (layout_type 1): LBO = 4096 B between consecutive 32-element
+// MN blocks, SBO = 512 B between consecutive 4-row K groups (cute::UMMA::make_umma_desc<Major::MN>).
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         (1ull << 46) | (2ull << 61);
+  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+         (1ull << 46) | (1ull << 61);
+}
+// byte offset of the 16-byte chunk `ch` (0..7) of MN block `mb`, k-row `row` (0..31) inside an operand tile:
+// block stride 4096, 4-row group stride 512, row stride 128, 32-byte chunk index XOR (row & 3)  [Swizzle<2,5,2>]
+__device__ __forceinline__ uint32_t mn_off(int mb, int row, int ch) {
+  const int kr = row & 3;
+  return (uint32_t)(mb * 4096 + (row >> 2) * 512 + kr * 128 + ((((ch >> 1) ^ kr) << 5) | ((ch & 1) << 4)));
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -168,8 +175,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __gr
             if (p.op.idx == nullptr) v = ldg4(base + (size_t)r * p.src_stride);
             else ell_gather4(p.op, r, base, (size_t)p.src_stride, v);
           }
-          const int kg = row >> 3, kr = row & 7;
-          split_store(v, a_hi, a_lo, (uint32_t)(mb * 4096 + kg * 1024 + kr * 128 + ((ch ^ kr) << 4)));
+          split_store(v, a_hi, a_lo, mn_off(mb, row, ch));
         }
         fence_proxy_async();
         __syncwarp();
@@ -190,8 +196,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __gr
             const long long R = rb + row;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (R < rend && c < p.ncols) v = ldg4(p.g + (size_t)R * p.ncols + c);
-            const int kg = row >> 3, kr = row & 7;
-            split_store(v, g_hi, g_lo, (uint32_t)(mb * 4096 + kg * 1024 + kr * 128 + ((ch ^ kr) << 4)));
+            split_store(v, g_hi, g_lo, mn_off(mb, row, ch));
           }
         }
         fence_proxy_async();
