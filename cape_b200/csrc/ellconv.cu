@@ -479,22 +479,24 @@ __global__ void __launch_bounds__(NT, 2) ellconv_dw_kernel(const __grid_constant
   }
 }
 
-__global__ void __launch_bounds__(256) reduce_splits_kernel(const float* __restrict__ ws, int nsplit, int F, int ncols,
-                                                            float* __restrict__ dw, long long dw_stride,
-                                                            int accumulate) {
-  // 64 consecutive elements x 4 split lanes per CTA; fixed summation order (deterministic)
-  __shared__ float red[4][64];
+__global__ void __launch_bounds__(1024) reduce_splits_kernel(const float* __restrict__ ws, int nsplit, int F, int ncols,
+                                                             float* __restrict__ dw, long long dw_stride,
+                                                             int accumulate) {
+  // 64 consecutive elements x 16 split lanes per CTA; fixed summation order (deterministic)
+  __shared__ float red[16][64];
   const long long total = (long long)F * ncols;
   const int el = threadIdx.x & 63, zl = threadIdx.x >> 6;
   for (long long e0 = (long long)blockIdx.x * 64; e0 < total; e0 += (long long)gridDim.x * 64) {
     const long long e = e0 + el;
     float s = 0.f;
     if (e < total)
-      for (int z = zl; z < nsplit; z += 4) s += ws[(size_t)z * total + e];
+      for (int z = zl; z < nsplit; z += 16) s += ws[(size_t)z * total + e];
     red[zl][el] = s;
     __syncthreads();
     if (zl == 0 && e < total) {
-      s = (red[0][el] + red[1][el]) + (red[2][el] + red[3][el]);
+      s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s += red[k][el];
       const int f = (int)(e / ncols), c = (int)(e % ncols);
       float* o = dw + (size_t)f * dw_stride + c;
       *o = accumulate ? (*o + s) : s;
@@ -507,38 +509,69 @@ __global__ void __launch_bounds__(256) reduce_splits_kernel(const float* __restr
 constexpr int CS_MAXOPS = 4;
 struct ColsumParams {
   const float* g;
-  int N, rows, ncols, nops, rows_per_block;
+  int N, rows, ncols, nops, rows_per_block, vec;
   const float* coef[CS_MAXOPS];   // nullptr = ones
   float* out;
 };
 
 __global__ void __launch_bounds__(256) colsum_kernel(const __grid_constant__ ColsumParams p) {
-  // grid: (row blocks, N, col tiles of 32); block: 32 col lanes x 8 row lanes
-  __shared__ float red[CS_MAXOPS][8][33];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  // grid: (row blocks, N).  Threads = (ncols/4 float4 column lanes) x (row lanes); every row is read as one
+  // contiguous ncols*4-byte segment.  Scalar fallback when ncols % 4 != 0.
+  __shared__ float red[CS_MAXOPS][256 * 4 / 32][33];   // [op][row lane (<=32)][col4 lane*4 .. ] reused below
   const int n = blockIdx.y;
-  const int c = blockIdx.z * 32 + cx;
   const int r0 = blockIdx.x * p.rows_per_block;
   const int r1 = min(p.rows, r0 + p.rows_per_block);
-  float s[CS_MAXOPS] = {0.f, 0.f, 0.f, 0.f};
-  if (c < p.ncols) {
-    const float* gp = p.g + (size_t)n * p.rows * p.ncols + c;
-    for (int r = r0 + ry; r < r1; r += 8) {
-      const float gv = __ldg(gp + (size_t)r * p.ncols);
+  const float* gp = p.g + (size_t)n * p.rows * p.ncols;
+  if (p.vec) {
+    const int cl = p.ncols >> 2;                       // float4 lanes per row (<= 128)
+    const int rl = 256 / cl;                           // row lanes
+    const int c4 = threadIdx.x % cl, ry = threadIdx.x / cl;
+    float4 s[CS_MAXOPS];
 #pragma unroll
-      for (int j = 0; j < CS_MAXOPS; ++j)
-        if (j < p.nops) s[j] = fmaf(p.coef[j] ? __ldg(p.coef[j] + r) : 1.f, gv, s[j]);
+    for (int j = 0; j < CS_MAXOPS; ++j) s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ry < rl) {
+      for (int r = r0 + ry; r < r1; r += rl) {
+        const float4 gv = ldg4(gp + (size_t)r * p.ncols + c4 * 4);
+#pragma unroll
+        for (int j = 0; j < CS_MAXOPS; ++j)
+          if (j < p.nops) fma4(s[j], p.coef[j] ? __ldg(p.coef[j] + r) : 1.f, gv);
+      }
     }
-  }
-#pragma unroll
-  for (int j = 0; j < CS_MAXOPS; ++j) red[j][ry][cx] = s[j];
-  __syncthreads();
-  if (ry == 0 && c < p.ncols) {
+    // reduce over row lanes through shared memory (fixed order), then one atomic per (op, column)
+    float* sm = &red[0][0][0];                         // 4 * 32 * 33 floats = 4224 >= nops * 256 * 4 when rl*cl = 256
     for (int j = 0; j < p.nops; ++j) {
-      float tot = 0.f;
+      __syncthreads();
+      if (ry < rl) *reinterpret_cast<float4*>(sm + ((size_t)ry * cl + c4) * 4) = s[j];
+      __syncthreads();
+      for (int c = threadIdx.x; c < p.ncols; c += 256) {
+        float tot = 0.f;
+        for (int k = 0; k < rl; ++k) tot += sm[((size_t)k * cl + (c >> 2)) * 4 + (c & 3)];
+        atomicAdd(p.out + ((size_t)n * p.nops + j) * p.ncols + c, tot);
+      }
+    }
+  } else {
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    for (int c0 = 0; c0 < p.ncols; c0 += 32) {
+      const int c = c0 + cx;
+      float s[CS_MAXOPS] = {0.f, 0.f, 0.f, 0.f};
+      if (c < p.ncols)
+        for (int r = r0 + ry; r < r1; r += 8) {
+          const float gv = __ldg(gp + (size_t)r * p.ncols + c);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) tot += red[j][k][cx];
-      atomicAdd(p.out + ((size_t)n * p.nops + j) * p.ncols + c, tot);
+          for (int j = 0; j < CS_MAXOPS; ++j)
+            if (j < p.nops) s[j] = fmaf(p.coef[j] ? __ldg(p.coef[j] + r) : 1.f, gv, s[j]);
+        }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < CS_MAXOPS; ++j) red[j][ry][cx] = s[j];
+      __syncthreads();
+      if (ry == 0 && c < p.ncols)
+        for (int j = 0; j < p.nops; ++j) {
+          float tot = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) tot += red[j][k][cx];
+          atomicAdd(p.out + ((size_t)n * p.nops + j) * p.ncols + c, tot);
+        }
     }
   }
 }
@@ -677,7 +710,7 @@ extern "C" int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* strea
         const long long total = (long long)a->F * a->ncols;
         long long blocks = (total + 63) / 64;
         if (blocks > 8LL * t->sm_count) blocks = 8LL * t->sm_count;
-        reduce_splits_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)t->workspace, ns, a->F,
+        reduce_splits_kernel<<<(unsigned)blocks, 1024, 0, (cudaStream_t)stream>>>((const float*)t->workspace, ns, a->F,
                                                                                  a->ncols, a->dw, a->dw_stride,
                                                                                  a->accumulate);
         CAPE_CHECK_CUDA(cudaGetLastError());
@@ -715,7 +748,7 @@ extern "C" int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* strea
     const long long total = (long long)a->F * a->ncols;
     long long blocks = (total + 63) / 64;
     if (blocks > 8LL * t->sm_count) blocks = 8LL * t->sm_count;
-    reduce_splits_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float*)t->workspace, (int)nsplit, a->F, a->ncols, a->dw,
+    reduce_splits_kernel<<<(unsigned)blocks, 1024, 0, st>>>((const float*)t->workspace, (int)nsplit, a->F, a->ncols, a->dw,
                                                   a->dw_stride, a->accumulate);
     CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
@@ -737,15 +770,15 @@ extern "C" int cape_colsum(cape_topology* t, const float* g, int N, int rows, in
     CAPE_REQUIRE(t->ops[op].rows_out == rows, "colsum: operator rows mismatch");
     p.coef[j] = t->ops[op].rowsum;
   }
-  const int ctiles = (ncols + 31) / 32;
-  int rblocks = (2 * t->sm_count + N * ctiles - 1) / (N * ctiles);
+  p.vec = (ncols % 4 == 0) && ncols <= 512 && (256 % (ncols / 4) == 0) && aligned16(g);
+  int rblocks = (4 * t->sm_count + N - 1) / N;
   if (rblocks < 1) rblocks = 1;
   int rpb = (rows + rblocks - 1) / rblocks;
   if (rpb < 64) rpb = 64;
   rblocks = (rows + rpb - 1) / rpb;
   p.rows_per_block = rpb;
-  CAPE_REQUIRE(N <= 65535 && ctiles <= 65535, "grid too large");
-  dim3 grid(rblocks, N, ctiles);
+  CAPE_REQUIRE(N <= 65535, "grid too large");
+  dim3 grid(rblocks, N);
   colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);

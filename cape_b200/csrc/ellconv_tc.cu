@@ -5,13 +5,15 @@
 // exact remainder), acc += a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32 accumulation in TMEM; the dropped a_lo*b_lo
 // term is ~2^-22 relative, so results stay within the 1e-4 parity gate with a wide margin.
 //
-// CTA = 9 warps owning 128 output rows x ALL output columns.  Warps 0-7 build operand tiles: the Chebyshev-basis chunk A[128 rows x 32 k] is gathered from
-// neighbour rows with float4 loads (same ELL tables as the SIMT path), split into hi/lo and written to shared
-// memory in the canonical K-major SWIZZLE_128B UMMA layout; the weight chunk B[BN x 32 k] (K-major copy of W) is
-// loaded and split the same way.  Warp 8 issues tcgen05.mma (kind::tf32, M=128, N=BN, K=8; 12 per chunk, 24
-// for the two-accumulator affine block) and releases pipeline stages with tcgen05.commit -> mbarrier.  After the
-// last chunk warps 0-7 become the epilogue: tcgen05.ld the accumulators from TMEM, add the condition broadcast /
-// bias, apply the activation (or the affine-block / backward epilogues) and store rows with float4 writes.
+// Persistent CTAs of 13 warps loop over 128-row output tiles (ALL output columns per tile).  Warps 0-7 build operand
+// tiles: the Chebyshev-basis chunk A[128 rows x 32 k] is gathered from neighbour rows with float4 loads (same ELL
+// tables as the SIMT path), split into hi/lo and written to shared memory in the canonical K-major SWIZZLE_128B
+// UMMA layout; the weight chunks B[BN x 32 k] (K-major copy of W) of every BN-wide column sub-tile are loaded and
+// split the same way.  Warp 8 issues tcgen05.mma (kind::tf32, M=128, N=BN, K=8; 12 per chunk and sub-tile, 24 for
+// the two-accumulator affine block) into one of two TMEM accumulator buffers and releases pipeline stages with
+// tcgen05.commit -> mbarrier.  Warps 9-12 are the epilogue: tcgen05.ld the finished accumulators, add the condition
+// broadcast / bias, apply the activation (or the affine-block / backward epilogues), store rows with float4
+// writes -- overlapping the next tile's main loop.
 #include "common.cuh"
 #include "ellconv_params.cuh"
 
@@ -104,15 +106,21 @@ struct TcCfg {
   static constexpr int A_STAGES = 2;
   static constexpr int B_STAGES = (B_STAGE_BYTES * 3 <= 96 * 1024) ? 3 : 2;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES +
-                                    QS_FLOATS * 4 + 2 * BM * 4 + 256;
+                                    QS_FLOATS * 4 + 512;
 };
 
-// One CTA = 128 output rows x ALL output columns (ncols <= 512, or <= 256 with two accumulators): the gathered
-// basis chunk A is built once and reused by every BN-wide column sub-tile, whose weight chunks stream through
-// their own ring.  TMEM holds the whole [128 x ncols] fp32 accumulator (x2 for the affine block).
+constexpr int TC_EPI_WARPS = 4;
+constexpr int TC_EPI_WARP0 = TC_PROD_WARPS + 1;                        // warps 9..12: TMEM lane quadrants 1,2,3,0
+constexpr int TC_THREADS3 = (TC_PROD_WARPS + 1 + TC_EPI_WARPS) * 32;   // 416
+
+// Persistent kernel.  A CTA loops over 128-row output tiles (all output columns each).  Three roles run
+// concurrently on different tiles: 8 producer warps (gather/split/store the basis chunk A once per chunk, stream the
+// K-major weight chunks B of every BN-wide column sub-tile), 1 MMA warp (tcgen05.mma into one of TWO TMEM
+// accumulator buffers when 2 x accumulator columns <= 512), 4 epilogue warps (tcgen05.ld, condition/bias/
+// activation, stores) -- so the epilogue and start-up of one tile overlap the main loop of the next.
 template <int BN, bool DUAL>
-__global__ void __launch_bounds__(TC_THREADS, 1) ellconv_tc_kernel(const __grid_constant__ ConvParams p, int nct,
-                                                                   int tmem_cols) {
+__global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid_constant__ ConvParams p, int nct,
+                                                                    int tmem_cols, int nbuf, int ntiles) {
   using Cfg = TcCfg<BN, DUAL>;
   constexpr int SA = Cfg::A_STAGES, SB = Cfg::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -120,28 +128,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ellconv_tc_kernel(const __grid_
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   char* a_ring = smem;
   char* b_ring = smem + SA * Cfg::A_STAGE_BYTES;
-  float* qs = reinterpret_cast<float*>(b_ring + SB * Cfg::B_STAGE_BYTES);
-  int* s_n = reinterpret_cast<int*>(qs + QS_FLOATS);
-  int* s_r = s_n + BM;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_r + BM);   // a_full[4] a_empty[4] b_full[4] b_empty[4] accum
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * MAX_STAGES + 1);
+  float* qs_all = reinterpret_cast<float*>(b_ring + SB * Cfg::B_STAGE_BYTES);
+  // a_full[4] a_empty[4] b_full[4] b_empty[4] t_full[2] t_empty[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qs_all + QS_FLOATS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * MAX_STAGES + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long row0 = (long long)blockIdx.x * BM;
   const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + MAX_STAGES);
   const uint32_t bar_bfull = smem_u32(bars + 2 * MAX_STAGES), bar_bempty = smem_u32(bars + 3 * MAX_STAGES);
-  const uint32_t bar_accum = smem_u32(bars + 4 * MAX_STAGES);
+  const uint32_t bar_tfull = smem_u32(bars + 4 * MAX_STAGES), bar_tempty = smem_u32(bars + 4 * MAX_STAGES + 2);
 
-  if (tid < BM) {
-    const long long R = row0 + tid;
-    if (R < p.total_rows) { s_n[tid] = (int)(R / p.rows_out); s_r[tid] = (int)(R % p.rows_out); }
-    else { s_n[tid] = -1; s_r[tid] = 0; }
-  }
   if (warp == TC_PROD_WARPS) {
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, TC_PROD_WARPS); mbar_init(bar_aempty + 8 * s, 1); }
       for (int s = 0; s < SB; ++s) { mbar_init(bar_bfull + 8 * s, TC_PROD_WARPS); mbar_init(bar_bempty + 8 * s, 1); }
-      mbar_init(bar_accum, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, TC_EPI_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -154,206 +155,231 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ellconv_tc_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc1_col = (uint32_t)(nct * BN);            // second accumulator starts after the first
+  const uint32_t buf_cols = (uint32_t)((DUAL ? 2 : 1) * nct * BN);
 
   if (warp < TC_PROD_WARPS) {
     // =========================== producers ===========================
     const int l8 = tid & 7, rs = tid >> 3;       // 8 lanes per 128-byte row, 32 row slots
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
-    for (int t = 0; t < p.nterms; ++t) {
-      const TermDev& tm = p.terms[t];
-      const bool has2 = DUAL && tm.w2T != nullptr;
-      for (int f0 = 0; f0 < tm.F; f0 += BK) {
-        const int f = f0 + l8 * 4;
-        // ---- A chunk: gather 4 rows per thread, split, store swizzled
-        mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
-        {
-          char* a_hi = a_ring + (size_t)sa * Cfg::A_STAGE_BYTES;
-          char* a_lo = a_hi + A_TILE_BYTES;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long row0 = (long long)tile * BM;
+      int rn[4], rr[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = rs + 32 * i;
-            const int n = s_n[row], r = s_r[row];
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n >= 0 && f < tm.F) {
-              const float* base = tm.src + (size_t)n * tm.src_rows * tm.src_stride + f;
-              if (tm.op.idx == nullptr) v = ldg4(base + (size_t)r * tm.src_stride);
-              else ell_gather4(tm.op, r, base, (size_t)tm.src_stride, v);
+      for (int i = 0; i < 4; ++i) {
+        const long long R = row0 + rs + 32 * i;
+        if (R < p.total_rows) { rn[i] = (int)(R / p.rows_out); rr[i] = (int)(R % p.rows_out); }
+        else { rn[i] = -1; rr[i] = 0; }
+      }
+      for (int t = 0; t < p.nterms; ++t) {
+        const TermDev& tm = p.terms[t];
+        const bool has2 = DUAL && tm.w2T != nullptr;
+        for (int f0 = 0; f0 < tm.F; f0 += BK) {
+          const int f = f0 + l8 * 4;
+          // ---- A chunk: gather 4 rows per thread, split, store swizzled
+          mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
+          {
+            char* a_hi = a_ring + (size_t)sa * Cfg::A_STAGE_BYTES;
+            char* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = rs + 32 * i;
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (rn[i] >= 0 && f < tm.F) {
+                const float* base = tm.src + (size_t)rn[i] * tm.src_rows * tm.src_stride + f;
+                if (tm.op.idx == nullptr) v = ldg4(base + (size_t)rr[i] * tm.src_stride);
+                else ell_gather4(tm.op, rr[i], base, (size_t)tm.src_stride, v);
+              }
+              split_store(v, a_hi, a_lo, (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4)));
             }
-            split_store(v, a_hi, a_lo, (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4)));
+            fence_proxy_async();             // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
+            if (++sa == SA) { sa = 0; pha ^= 1; }
           }
-          fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
-          if (++sa == SA) { sa = 0; pha ^= 1; }
-        }
-        // ---- B chunks: one [BN x 32] K-major weight tile (hi/lo) per column sub-tile
-        for (int cs = 0; cs < nct; ++cs) {
-          mbar_wait(bar_bempty + 8 * sb, phb ^ 1);
-          char* b_hi = b_ring + (size_t)sb * Cfg::B_STAGE_BYTES;
-          char* b_lo = b_hi + Cfg::B_TILE_BYTES;
+          // ---- B chunks: one [BN x 32] K-major weight tile (hi/lo) per column sub-tile
+          for (int cs = 0; cs < nct; ++cs) {
+            mbar_wait(bar_bempty + 8 * sb, phb ^ 1);
+            char* b_hi = b_ring + (size_t)sb * Cfg::B_STAGE_BYTES;
+            char* b_lo = b_hi + Cfg::B_TILE_BYTES;
 #pragma unroll
-          for (int i = 0; i < BN / 32; ++i) {
-            const int cl = rs + 32 * i;
-            const int c = cs * BN + cl;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c < p.ncols && f < tm.F) v = ldg4(tm.wT + (size_t)c * tm.wT_stride + f);
-            const uint32_t off = (uint32_t)(cl * 128 + ((l8 ^ (cl & 7)) << 4));
-            split_store(v, b_hi, b_lo, off);
-            if (DUAL) {
-              if (has2) {
-                float4 v2 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c < p.ncols && f < tm.F) v2 = ldg4(tm.w2T + (size_t)c * tm.w2T_stride + f);
-                split_store(v2, b_lo + Cfg::B_TILE_BYTES, b_lo + 2 * Cfg::B_TILE_BYTES, off);
+            for (int i = 0; i < BN / 32; ++i) {
+              const int cl = rs + 32 * i;
+              const int c = cs * BN + cl;
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (c < p.ncols && f < tm.F) v = ldg4(tm.wT + (size_t)c * tm.wT_stride + f);
+              const uint32_t off = (uint32_t)(cl * 128 + ((l8 ^ (cl & 7)) << 4));
+              split_store(v, b_hi, b_lo, off);
+              if (DUAL) {
+                if (has2) {
+                  float4 v2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (c < p.ncols && f < tm.F) v2 = ldg4(tm.w2T + (size_t)c * tm.w2T_stride + f);
+                  split_store(v2, b_lo + Cfg::B_TILE_BYTES, b_lo + 2 * Cfg::B_TILE_BYTES, off);
+                }
               }
             }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_bfull + 8 * sb);
+            if (++sb == SB) { sb = 0; phb ^= 1; }
           }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_bfull + 8 * sb);
-          if (++sb == SB) { sb = 0; phb ^= 1; }
         }
       }
     }
-
-    // ---- condition broadcast vectors: q[s][slot][c] = cond[n0+s,:] @ Wc_slot[:, c]
-    const int n_first = s_n[0];
-    if (p.nslots > 0) {
-      int n_last = n_first;
-      for (int i = BM - 1; i > 0; --i)
-        if (s_n[i] >= 0) { n_last = s_n[i]; break; }
-      const int S = n_last - n_first + 1;
-      const int total = S * p.nslots * p.ncols;
-      for (int o = tid; o < total; o += TC_PROD_THREADS) {
-        const int c = o % p.ncols;
-        const int slot = (o / p.ncols) % p.nslots;
-        const int s = o / (p.ncols * p.nslots);
-        const float* y = p.cond + (size_t)(n_first + s) * p.C;
-        const float* wc = p.slot_w[slot] + c;
-        const int ws = p.slot_acc[slot] ? p.terms[p.slot_term[slot]].w2_stride : p.terms[p.slot_term[slot]].w_stride;
-        float q = 0.f;
-        for (int j = 0; j < p.C; ++j) q = fmaf(__ldg(y + j), __ldg(wc + (size_t)j * ws), q);
-        qs[o] = q;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
-    }
-
-    // =========================== epilogue ===========================
-    mbar_wait(bar_accum, 0);
-    tc_fence_after();
-    const int quad = warp & 3, half = warp >> 2;          // TMEM lane quadrant of this warp; column half
-    const int row = quad * 32 + lane;
-    const int n = s_n[row], r = s_r[row];
-    const int cpw = p.ncols >> 1;                         // columns per warp (ncols is a multiple of 32)
-    const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const size_t orow = (size_t)(row0 + row) * p.ncols;
-#pragma unroll 1
-    for (int g = 0; g < cpw / 16; ++g) {
-      const int c0 = half * cpw + g * 16;                 // first of 16 output columns
-      float v0[16], v1[16];
-      tmem_ld16(taddr_row + (uint32_t)c0, v0);             // warp-collective: executed by every lane
-      if (DUAL) tmem_ld16(taddr_row + acc1_col + (uint32_t)c0, v1);
-      if (n < 0) continue;
-      for (int slot = 0; slot < p.nslots; ++slot) {
-        const TermDev& tm = p.terms[p.slot_term[slot]];
-        const float coef = tm.op.rowsum ? __ldg(tm.op.rowsum + r) : 1.f;
-        const float* q = qs + ((size_t)(n - n_first) * p.nslots + slot) * p.ncols + c0;
-        if (p.slot_acc[slot] == 0) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v0[j] = fmaf(coef, q[j], v0[j]);
-        } else if (DUAL) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v1[j] = fmaf(coef, q[j], v1[j]);
-        }
-      }
-      float o1[16], o2[16];
-      bool write2 = false;
-      if (p.epilogue == CAPE_EPI_LINEAR) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v = v0[j];
-          if (p.bias != nullptr) v += __ldg(p.bias + (p.bias_per_row ? (size_t)r * p.ncols : 0) + c0 + j);
-          if (p.act == CAPE_ACT_LEAKY) v = v > 0.f ? v : p.alpha * v;
-          else if (p.act == CAPE_ACT_RELU) v = fmaxf(v, 0.f);
-          o1[j] = v;
-        }
-      } else if (p.epilogue == CAPE_EPI_AFFINE) {
-        write2 = p.out2 != nullptr;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float rg = fmaxf(v0[j], 0.f);
-          o1[j] = (DUAL ? v1[j] : 0.f) + rg;
-          o2[j] = rg;
-        }
-      } else {
-        float ax[16];
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 a4 = ldg4(p.aux + orow + c0 + j);
-          ax[j] = a4.x; ax[j + 1] = a4.y; ax[j + 2] = a4.z; ax[j + 3] = a4.w;
-        }
-        if (p.epilogue == CAPE_EPI_SLOPE) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o1[j] = v0[j] * (ax[j] > 0.f ? 1.f : p.alpha);
-        } else {
-          write2 = p.out2 != nullptr;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { o1[j] = v0[j]; o2[j] = ax[j] > 0.f ? v0[j] : 0.f; }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        *reinterpret_cast<float4*>(p.out + orow + c0 + j) = make_float4(o1[j], o1[j + 1], o1[j + 2], o1[j + 3]);
-        if (write2)
-          *reinterpret_cast<float4*>(p.out2 + orow + c0 + j) = make_float4(o2[j], o2[j + 1], o2[j + 2], o2[j + 3]);
-      }
-    }
-    tc_fence_before();
-  } else {
+  } else if (warp == TC_PROD_WARPS) {
     // =========================== MMA issuer (one elected lane) ===========================
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N=BN, M=128
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int sa = 0, sb = 0;
-      uint32_t pha = 0, phb = 0, acc0_on = 0, acc1_on = 0;
-      for (int t = 0; t < p.nterms; ++t) {
-        const bool has2 = DUAL && p.terms[t].w2T != nullptr;
-        for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
-          mbar_wait(bar_afull + 8 * sa, pha);
-          const uint32_t aaddr = smem_u32(a_ring + (size_t)sa * Cfg::A_STAGE_BYTES);
-          const uint64_t a_hi = make_desc(aaddr), a_lo = make_desc(aaddr + A_TILE_BYTES);
-          for (int cs = 0; cs < nct; ++cs) {
-            mbar_wait(bar_bfull + 8 * sb, phb);
-            tc_fence_after();
-            const uint32_t baddr = smem_u32(b_ring + (size_t)sb * Cfg::B_STAGE_BYTES);
-            const uint64_t b_hi = make_desc(baddr), b_lo = make_desc(baddr + Cfg::B_TILE_BYTES);
-            const uint64_t b2_hi = make_desc(baddr + 2 * Cfg::B_TILE_BYTES), b2_lo = make_desc(baddr + 3 * Cfg::B_TILE_BYTES);
-            const uint32_t d0 = tmem_base + (uint32_t)(cs * BN), d1 = d0 + acc1_col;
+      int sa = 0, sb = 0, it = 0;
+      uint32_t pha = 0, phb = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it % nbuf;
+        const uint32_t use = (uint32_t)(it / nbuf);
+        mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);       // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t tb = tmem_base + (uint32_t)buf * buf_cols;
+        uint32_t acc0_on = 0, acc1_on = 0;
+        for (int t = 0; t < p.nterms; ++t) {
+          const bool has2 = DUAL && p.terms[t].w2T != nullptr;
+          for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+            mbar_wait(bar_afull + 8 * sa, pha);
+            const uint32_t aaddr = smem_u32(a_ring + (size_t)sa * Cfg::A_STAGE_BYTES);
+            const uint64_t a_hi = make_desc(aaddr), a_lo = make_desc(aaddr + A_TILE_BYTES);
+            for (int cs = 0; cs < nct; ++cs) {
+              mbar_wait(bar_bfull + 8 * sb, phb);
+              tc_fence_after();
+              const uint32_t baddr = smem_u32(b_ring + (size_t)sb * Cfg::B_STAGE_BYTES);
+              const uint64_t b_hi = make_desc(baddr), b_lo = make_desc(baddr + Cfg::B_TILE_BYTES);
+              const uint64_t b2_hi = make_desc(baddr + 2 * Cfg::B_TILE_BYTES), b2_lo = make_desc(baddr + 3 * Cfg::B_TILE_BYTES);
+              const uint32_t d0 = tb + (uint32_t)(cs * BN), d1 = d0 + acc1_col;
 #pragma unroll
-            for (int ks = 0; ks < BK / 8; ++ks) {
-              const uint64_t adv = (uint64_t)(ks * 2);    // +32 bytes along K inside the 128-byte swizzle row
-              // the very first MMA into a sub-tile's TMEM columns overwrites (TMEM is not zero-initialised)
-              umma_tf32(d0, a_hi + adv, b_hi + adv, idesc, ks == 0 ? acc0_on : 1u);
-              umma_tf32(d0, a_lo + adv, b_hi + adv, idesc, 1);
-              umma_tf32(d0, a_hi + adv, b_lo + adv, idesc, 1);
-              if (has2) {
-                umma_tf32(d1, a_hi + adv, b2_hi + adv, idesc, ks == 0 ? acc1_on : 1u);
-                umma_tf32(d1, a_lo + adv, b2_hi + adv, idesc, 1);
-                umma_tf32(d1, a_hi + adv, b2_lo + adv, idesc, 1);
+              for (int ks = 0; ks < BK / 8; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);  // +32 bytes along K inside the 128-byte swizzle row
+                // the very first MMA into a sub-tile's TMEM columns overwrites (TMEM is not zero-initialised)
+                umma_tf32(d0, a_hi + adv, b_hi + adv, idesc, ks == 0 ? acc0_on : 1u);
+                umma_tf32(d0, a_lo + adv, b_hi + adv, idesc, 1);
+                umma_tf32(d0, a_hi + adv, b_lo + adv, idesc, 1);
+                if (has2) {
+                  umma_tf32(d1, a_hi + adv, b2_hi + adv, idesc, ks == 0 ? acc1_on : 1u);
+                  umma_tf32(d1, a_lo + adv, b2_hi + adv, idesc, 1);
+                  umma_tf32(d1, a_hi + adv, b2_lo + adv, idesc, 1);
+                }
               }
+              umma_commit(bar_bempty + 8 * sb);            // weight stage reusable once these MMAs have read it
+              if (++sb == SB) { sb = 0; phb ^= 1; }
             }
-            umma_commit(bar_bempty + 8 * sb);              // weight stage reusable once these MMAs have read it
-            if (++sb == SB) { sb = 0; phb ^= 1; }
+            umma_commit(bar_aempty + 8 * sa);              // basis stage reusable
+            if (++sa == SA) { sa = 0; pha ^= 1; }
+            acc0_on = 1;
+            if (has2) acc1_on = 1;
           }
-          umma_commit(bar_aempty + 8 * sa);                // basis stage reusable
-          if (++sa == SA) { sa = 0; pha ^= 1; }
-          acc0_on = 1;
-          if (has2) acc1_on = 1;
         }
+        umma_commit(bar_tfull + 8 * buf);                  // this tile's accumulators are complete
       }
-      umma_commit(bar_accum);                              // accumulators complete
     }
     __syncwarp();
+  } else {
+    // =========================== epilogue warps ===========================
+    const int et = tid - TC_EPI_WARP0 * 32;               // 0..127
+    const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int buf = it % nbuf;
+      const uint32_t use = (uint32_t)(it / nbuf);
+      const long long row0 = (long long)tile * BM;
+      const long long R = row0 + row;
+      const bool valid = R < p.total_rows;
+      const int n = valid ? (int)(R / p.rows_out) : -1, r = valid ? (int)(R % p.rows_out) : 0;
+      const int n_first = (int)(row0 / p.rows_out);
+      float* qs = qs_all + (size_t)(it & 1) * (QS_FLOATS / 2);   // always double-buffered (independent of nbuf)
+      if (p.nslots > 0) {
+        // condition broadcast vectors of this tile: q[s][slot][c] = cond[n_first+s,:] @ Wc_slot[:, c]
+        const long long rlast = min(p.total_rows, row0 + BM) - 1;
+        const int S = (int)(rlast / p.rows_out) - n_first + 1;
+        const int total = S * p.nslots * p.ncols;
+        for (int o = et; o < total; o += TC_EPI_WARPS * 32) {
+          const int c = o % p.ncols;
+          const int slot = (o / p.ncols) % p.nslots;
+          const int s = o / (p.ncols * p.nslots);
+          const float* y = p.cond + (size_t)(n_first + s) * p.C;
+          const float* wc = p.slot_w[slot] + c;
+          const int ws = p.slot_acc[slot] ? p.terms[p.slot_term[slot]].w2_stride : p.terms[p.slot_term[slot]].w_stride;
+          float q = 0.f;
+          for (int j = 0; j < p.C; ++j) q = fmaf(__ldg(y + j), __ldg(wc + (size_t)j * ws), q);
+          qs[o] = q;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+      }
+      mbar_wait(bar_tfull + 8 * buf, use & 1);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quad * 32) << 16);
+      const size_t orow = (size_t)R * p.ncols;
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.ncols; c0 += 16) {
+        float v0[16], v1[16];
+        tmem_ld16(taddr_row + (uint32_t)c0, v0);           // warp-collective: executed by every lane
+        if (DUAL) tmem_ld16(taddr_row + acc1_col + (uint32_t)c0, v1);
+        if (!valid) continue;
+        for (int slot = 0; slot < p.nslots; ++slot) {
+          const TermDev& tm = p.terms[p.slot_term[slot]];
+          const float coef = tm.op.rowsum ? __ldg(tm.op.rowsum + r) : 1.f;
+          const float* q = qs + ((size_t)(n - n_first) * p.nslots + slot) * p.ncols + c0;
+          if (p.slot_acc[slot] == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v0[j] = fmaf(coef, q[j], v0[j]);
+          } else if (DUAL) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v1[j] = fmaf(coef, q[j], v1[j]);
+          }
+        }
+        float o1[16], o2[16];
+        bool write2 = false;
+        if (p.epilogue == CAPE_EPI_LINEAR) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float v = v0[j];
+            if (p.bias != nullptr) v += __ldg(p.bias + (p.bias_per_row ? (size_t)r * p.ncols : 0) + c0 + j);
+            if (p.act == CAPE_ACT_LEAKY) v = v > 0.f ? v : p.alpha * v;
+            else if (p.act == CAPE_ACT_RELU) v = fmaxf(v, 0.f);
+            o1[j] = v;
+          }
+        } else if (p.epilogue == CAPE_EPI_AFFINE) {
+          write2 = p.out2 != nullptr;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float rg = fmaxf(v0[j], 0.f);
+            o1[j] = (DUAL ? v1[j] : 0.f) + rg;
+            o2[j] = rg;
+          }
+        } else {
+          float ax[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 a4 = ldg4(p.aux + orow + c0 + j);
+            ax[j] = a4.x; ax[j + 1] = a4.y; ax[j + 2] = a4.z; ax[j + 3] = a4.w;
+          }
+          if (p.epilogue == CAPE_EPI_SLOPE) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o1[j] = v0[j] * (ax[j] > 0.f ? 1.f : p.alpha);
+          } else {
+            write2 = p.out2 != nullptr;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { o1[j] = v0[j]; o2[j] = ax[j] > 0.f ? v0[j] : 0.f; }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          *reinterpret_cast<float4*>(p.out + orow + c0 + j) = make_float4(o1[j], o1[j + 1], o1[j + 2], o1[j + 3]);
+          if (write2)
+            *reinterpret_cast<float4*>(p.out2 + orow + c0 + j) = make_float4(o2[j], o2[j + 1], o2[j + 2], o2[j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);    // accumulator buffer free for the MMA warp
+    }
   }
 
   __syncthreads();
@@ -364,7 +390,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ellconv_tc_kernel(const __grid_
 }
 
 template <int BN, bool DUAL>
-int launch_one(const ConvParams& p, cudaStream_t st) {
+int launch_one(const cape_topology* t, const ConvParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, DUAL>;
   static bool configured = false;
   if (!configured) {
@@ -373,10 +399,13 @@ int launch_one(const ConvParams& p, cudaStream_t st) {
     configured = true;
   }
   const int nct = (p.ncols + BN - 1) / BN;
-  int cols = (DUAL ? 2 : 1) * nct * BN, tmem_cols = 32;
-  while (tmem_cols < cols) tmem_cols *= 2;
-  dim3 grid((unsigned)((p.total_rows + BM - 1) / BM), 1);
-  ellconv_tc_kernel<BN, DUAL><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, nct, tmem_cols);
+  const int acc_cols = (DUAL ? 2 : 1) * nct * BN;
+  const int nbuf = (2 * acc_cols <= 512) ? 2 : 1;
+  int tmem_cols = 32;
+  while (tmem_cols < acc_cols * nbuf) tmem_cols *= 2;
+  const int ntiles = (int)((p.total_rows + BM - 1) / BM);
+  const int grid = ntiles < t->sm_count ? ntiles : t->sm_count;
+  ellconv_tc_kernel<BN, DUAL><<<grid, TC_THREADS3, Cfg::SMEM_BYTES, st>>>(p, nct, tmem_cols, nbuf, ntiles);
   CAPE_CHECK_CUDA(cudaGetLastError());
   count_launches(1);
   return 1;
@@ -388,7 +417,6 @@ static bool g_tc_enabled = true;
 bool tensor_cores_enabled() { return g_tc_enabled; }
 
 int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaStream_t st) {
-  (void)t;
   if (!g_tc_enabled) return 0;
   if (p.ncols % 32 != 0 || p.ncols < 32 || !p.ovec) return 0;
   if ((dual ? 2 : 1) * p.ncols > 512) return 0;              // the whole accumulator row must fit the 512 TMEM columns
@@ -403,16 +431,16 @@ int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cu
   if (kred < 64) return 0;                       // tiny reductions: the SIMT kernel is as good and simpler
   if (p.nslots > 0) {
     const long long max_samples = (BM - 1) / p.rows_out + 2;
-    if (max_samples * p.nslots * p.ncols > QS_FLOATS) return 0;
+    if (max_samples * p.nslots * p.ncols > QS_FLOATS / 2) return 0;
   }
   if (dual) {
-    if (p.ncols >= 128) return launch_one<128, true>(p, st);
-    if (p.ncols >= 64) return launch_one<64, true>(p, st);
-    return launch_one<32, true>(p, st);
+    if (p.ncols >= 128) return launch_one<128, true>(t, p, st);
+    if (p.ncols >= 64) return launch_one<64, true>(t, p, st);
+    return launch_one<32, true>(t, p, st);
   }
-  if (p.ncols >= 128) return launch_one<128, false>(p, st);
-  if (p.ncols >= 64) return launch_one<64, false>(p, st);
-  return launch_one<32, false>(p, st);
+  if (p.ncols >= 128) return launch_one<128, false>(t, p, st);
+  if (p.ncols >= 64) return launch_one<64, false>(t, p, st);
+  return launch_one<32, false>(t, p, st);
 }
 
 }  // namespace cape
