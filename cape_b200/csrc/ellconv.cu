@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(1024) reduce_splits_kernel(const float* __rest
 constexpr int CS_MAXOPS = 4;
 struct ColsumParams {
   const float* g;
-  int N, rows, ncols, nops, rows_per_block, vec;
+  int N, rows, ncols, nops, rows_per_block, vec, gs;   // gs: floats between consecutive rows of g
   const float* coef[CS_MAXOPS];   // nullptr = ones
   float* out;
 };
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __grid_constant__ Col
   const int n = blockIdx.y;
   const int r0 = blockIdx.x * p.rows_per_block;
   const int r1 = min(p.rows, r0 + p.rows_per_block);
-  const float* gp = p.g + (size_t)n * p.rows * p.ncols;
+  const float* gp = p.g + (size_t)n * p.rows * p.gs;
   if (p.vec) {
     const int cl = p.ncols >> 2;                       // float4 lanes per row (<= 128)
     const int rl = 256 / cl;                           // row lanes
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __grid_constant__ Col
     for (int j = 0; j < CS_MAXOPS; ++j) s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ry < rl) {
       for (int r = r0 + ry; r < r1; r += rl) {
-        const float4 gv = ldg4(gp + (size_t)r * p.ncols + c4 * 4);
+        const float4 gv = ldg4(gp + (size_t)r * p.gs + c4 * 4);
 #pragma unroll
         for (int j = 0; j < CS_MAXOPS; ++j)
           if (j < p.nops) fma4(s[j], p.coef[j] ? __ldg(p.coef[j] + r) : 1.f, gv);
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __grid_constant__ Col
       float s[CS_MAXOPS] = {0.f, 0.f, 0.f, 0.f};
       if (c < p.ncols)
         for (int r = r0 + ry; r < r1; r += 8) {
-          const float gv = __ldg(gp + (size_t)r * p.ncols + c);
+          const float gv = __ldg(gp + (size_t)r * p.gs + c);
 #pragma unroll
           for (int j = 0; j < CS_MAXOPS; ++j)
             if (j < p.nops) s[j] = fmaf(p.coef[j] ? __ldg(p.coef[j] + r) : 1.f, gv, s[j]);
@@ -576,34 +576,47 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __grid_constant__ Col
   }
 }
 
-// ---- standalone resampling (poolwT, lib/models.py:129-152): y[n, r, :] = sum_j w[r, j] * x[n, idx[r, j], :] -------
-__global__ void __launch_bounds__(256) resample_kernel(OpView op, const float* __restrict__ x, float* __restrict__ y,
-                                                       long long total_rows, int rows_out, int rows_in, int F,
-                                                       int vec) {
+// ---- standalone resampling (poolwT, lib/models.py:129-152): y[n, r, :F] = sum_j w[r, j] * x[n, idx[r, j], :F] -------
+// x rows are xs floats apart, y rows ys floats apart (so the result can land inside a wider concat buffer);
+// op.idx == nullptr copies rows (identity).  Optionally the condition channels of the concat are written too:
+// y[n, r, F + c] = rowsum(op)[r] * cond[n, c]   (fit_cond_dim + concat + unpool, lib/models.py:606-609,750).
+__global__ void __launch_bounds__(256) resample_kernel(OpView op, const float* __restrict__ x, int xs,
+                                                       float* __restrict__ y, int ys, long long total_rows,
+                                                       int rows_out, int rows_in, int F, int vec,
+                                                       const float* __restrict__ cond, int C) {
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= total_rows) return;
   const int n = (int)(warp / rows_out), r = (int)(warp % rows_out);
-  const float* base = x + (size_t)n * rows_in * F;
-  float* out = y + (size_t)warp * F;
-  const int32_t* ip = op.idx + (size_t)r * op.width;
-  const float* wp = op.w + (size_t)r * op.width;
+  const float* base = x + (size_t)n * rows_in * xs;
+  float* out = y + (size_t)warp * ys;
   if (vec) {
     for (int f = lane * 4; f < F; f += 128) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      ell_gather4(op, r, base + f, (size_t)F, v);
+      if (op.idx == nullptr) v = ldg4(base + (size_t)r * xs + f);
+      else ell_gather4(op, r, base + f, (size_t)xs, v);
       *reinterpret_cast<float4*>(out + f) = v;
     }
   } else {
     for (int f = lane; f < F; f += 32) {
       float v = 0.f;
-      for (int j = 0; j < op.width; ++j) {
-        const int id = __ldg(ip + j);
-        if (id < 0) break;
-        v = fmaf(__ldg(wp + j), __ldg(base + (size_t)id * F + f), v);
+      if (op.idx == nullptr) {
+        v = __ldg(base + (size_t)r * xs + f);
+      } else {
+        const int32_t* ip = op.idx + (size_t)r * op.width;
+        const float* wp = op.w + (size_t)r * op.width;
+        for (int j = 0; j < op.width; ++j) {
+          const int id = __ldg(ip + j);
+          if (id < 0) break;
+          v = fmaf(__ldg(wp + j), __ldg(base + (size_t)id * xs + f), v);
+        }
       }
       out[f] = v;
     }
+  }
+  if (cond != nullptr) {
+    const float coef = op.rowsum ? __ldg(op.rowsum + r) : 1.f;
+    for (int c = lane; c < C; c += 32) out[F + c] = coef * __ldg(cond + (size_t)n * C + c);
   }
 }
 
@@ -611,16 +624,17 @@ __global__ void __launch_bounds__(256) resample_kernel(OpView op, const float* _
 
 using namespace cape;
 
-extern "C" int cape_resample(cape_topology* t, int op, const float* x, float* y, int N, int rows_out, int rows_in,
-                             int F, void* stream) {
+extern "C" int cape_resample(cape_topology* t, int op, const float* x, int x_stride, float* y, int y_stride, int N,
+                             int rows_out, int rows_in, int F, const float* cond, int C, void* stream) {
   CAPE_REQUIRE(t && x && y && N > 0 && F > 0, "bad arguments");
-  CAPE_REQUIRE(op >= 0, "resample needs a registered operator");
+  CAPE_REQUIRE(x_stride >= F && y_stride >= F + (cond ? C : 0), "bad strides");
   OpView v;
   if (get_op(t, op, rows_out, rows_in, &v) != 0) return -1;
   const long long total = (long long)N * rows_out;
-  const int vec = (F % 4 == 0) && aligned16(x) && aligned16(y);
+  const int vec = (F % 4 == 0) && (x_stride % 4 == 0) && (y_stride % 4 == 0) && aligned16(x) && aligned16(y);
   const long long blocks = (total * 32 + 255) / 256;
-  resample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(v, x, y, total, rows_out, rows_in, F, vec);
+  resample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(v, x, x_stride, y, y_stride, total, rows_out,
+                                                                      rows_in, F, vec, cond, C);
   CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
   return 0;
@@ -678,7 +692,9 @@ extern "C" int cape_cheb_fwd(cape_topology* t, const cape_conv_args* a, void* st
   }
   cudaStream_t st = (cudaStream_t)stream;
   {
-    const int rc = launch_ellconv_tc(t, p, dual, st);     // tcgen05 path when eligible
+    int rc = launch_thin_fwd(t, p, dual, st);             // <= 4 input channels: streaming kernel
+    if (rc != 0) return rc < 0 ? rc : 0;
+    rc = launch_ellconv_tc(t, p, dual, st);               // tcgen05 path when eligible
     if (rc != 0) return rc < 0 ? rc : 0;
   }
   dim3 grid((unsigned)((p.total_rows + BM - 1) / BM), (unsigned)((a->ncols + BNsel - 1) / BNsel));
@@ -703,10 +719,14 @@ extern "C" int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* strea
   if (get_op(t, a->op, a->rows_out, a->src_rows, &p.op) != 0) return -1;
   {
     int ns = 1;
-    const int rc = launch_ellconv_dw_tc(t, a, p.op, &ns, (cudaStream_t)stream);   // tcgen05 path when eligible
+    bool always_reduce = false;
+    int rc = launch_thin_dw(t, a, p.op, &ns, (cudaStream_t)stream);               // <= 4 input channels
+    if (rc < 0) return rc;
+    if (rc == 1) always_reduce = true;                                            // partials always in the workspace
+    else rc = launch_ellconv_dw_tc(t, a, p.op, &ns, (cudaStream_t)stream);        // tcgen05 path when eligible
     if (rc < 0) return rc;
     if (rc == 1) {
-      if (ns > 1) {
+      if (ns > 1 || always_reduce) {
         const long long total = (long long)a->F * a->ncols;
         long long blocks = (total + 63) / 64;
         if (blocks > 8LL * t->sm_count) blocks = 8LL * t->sm_count;
@@ -756,13 +776,14 @@ extern "C" int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* strea
   return 0;
 }
 
-extern "C" int cape_colsum(cape_topology* t, const float* g, int N, int rows, int ncols, const int* ops, int nops,
-                           float* out, void* stream) {
+extern "C" int cape_colsum(cape_topology* t, const float* g, int g_stride, int N, int rows, int ncols, const int* ops,
+                           int nops, float* out, void* stream) {
   CAPE_REQUIRE(t && g && out, "null pointer");
   CAPE_REQUIRE(nops >= 1 && nops <= CS_MAXOPS, "nops out of range");
   CAPE_REQUIRE(N > 0 && rows > 0 && ncols > 0, "empty problem");
   ColsumParams p{};
-  p.g = g; p.N = N; p.rows = rows; p.ncols = ncols; p.nops = nops; p.out = out;
+  CAPE_REQUIRE(g_stride >= ncols, "bad g_stride");
+  p.g = g; p.N = N; p.rows = rows; p.ncols = ncols; p.nops = nops; p.out = out; p.gs = g_stride;
   for (int j = 0; j < nops; ++j) {
     const int op = ops ? ops[j] : -1;
     if (op < 0) { p.coef[j] = nullptr; continue; }
@@ -770,7 +791,7 @@ extern "C" int cape_colsum(cape_topology* t, const float* g, int N, int rows, in
     CAPE_REQUIRE(t->ops[op].rows_out == rows, "colsum: operator rows mismatch");
     p.coef[j] = t->ops[op].rowsum;
   }
-  p.vec = (ncols % 4 == 0) && ncols <= 512 && (256 % (ncols / 4) == 0) && aligned16(g);
+  p.vec = (ncols % 4 == 0) && (g_stride % 4 == 0) && ncols <= 512 && (256 % (ncols / 4) == 0) && aligned16(g);
   int rblocks = (4 * t->sm_count + N - 1) / N;
   if (rblocks < 1) rblocks = 1;
   int rpb = (rows + rblocks - 1) / rblocks;

@@ -47,6 +47,9 @@ struct ConvParams {
 // tcgen05 path (ellconv_tc.cu): returns 1 if it launched, 0 if the problem is not eligible, <0 on error.
 int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaStream_t st);
 bool tensor_cores_enabled();
+// thin-input layers (thin.cu): sources with <= 4 channels.  1 = launched, 0 = not eligible, <0 = error
+int launch_thin_fwd(const cape_topology* t, const ConvParams& p, bool dual, cudaStream_t st);
+int launch_thin_dw(const cape_topology* t, const cape_dw_args* a, const OpView& op, int* nsplit_out, cudaStream_t st);
 // tcgen05 weight-gradient path (ellconv_dw_tc.cu): 1 = launched (partials in the workspace if *nsplit_out > 1)
 int launch_ellconv_dw_tc(const cape_topology* t, const cape_dw_args* a, const OpView& op, int* nsplit_out,
                          cudaStream_t st);

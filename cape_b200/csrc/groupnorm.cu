@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const float* __restri
 __global__ void gn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                     const float* __restrict__ dy, long long total, int rows, int C, int G,
                                     const float* __restrict__ gamma, const float* __restrict__ stats,
-                                    const double* __restrict__ acc, double inv_cnt, float* __restrict__ dx) {
+                                    const double* __restrict__ acc, double inv_cnt, float* __restrict__ dx,
+                                    int accumulate) {
   const int cpg = C / G;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -110,7 +111,8 @@ __global__ void gn_bwd_apply_kernel(const float* __restrict__ x, const float* __
     const float m1 = (float)(acc[sg * 2] * inv_cnt), m2 = (float)(acc[sg * 2 + 1] * inv_cnt);
     const float gy = (y[i] > 0.f) ? dy[i] : 0.f;
     const float xh = (x[i] - mean) * rstd;
-    dx[i] = rstd * (__ldg(gamma + c) * gy - m1 - xh * m2);
+    const float d = rstd * (__ldg(gamma + c) * gy - m1 - xh * m2);
+    dx[i] = accumulate ? dx[i] + d : d;
   }
 }
 
@@ -151,8 +153,8 @@ extern "C" int cape_gn_relu_fwd(cape_topology* t, const float* x, int N, int row
 }
 
 extern "C" int cape_gn_relu_bwd(cape_topology* t, const float* x, const float* y, const float* dy, int N, int rows,
-                                int C, int G, const float* gamma, const float* stats, float* dx, float* dgamma,
-                                float* dbeta, void* stream) {
+                                int C, int G, const float* gamma, const float* stats, float* dx, int accumulate_dx,
+                                float* dgamma, float* dbeta, void* stream) {
   if (gn_check(t, N, rows, C, G) != 0) return -1;
   CAPE_REQUIRE(x && y && dy && gamma && stats && dx && dgamma && dbeta, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
@@ -166,7 +168,7 @@ extern "C" int cape_gn_relu_bwd(cape_topology* t, const float* x, const float* y
   const long long total = (long long)N * rows * C;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, dy, total, rows, C, G, gamma, stats, acc, inv_cnt, dx);
+  gn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, dy, total, rows, C, G, gamma, stats, acc, inv_cnt, dx, accumulate_dx);
   CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
   return 0;

@@ -190,9 +190,10 @@ def cheb_dw(tp, N, rows_out, ncols, src, op, F, src_rows, src_stride, g, dw, dw_
         check(tp.lib.cape_cheb_dw(tp.h, C.byref(a), _stream()))
 
 
-def colsum(tp, g, N, rows, ncols, ops, out):
+def colsum(tp, g, N, rows, ncols, ops, out, g_stride=None):
     arr = (C.c_int * len(ops))(*ops)
-    check(tp.lib.cape_colsum(tp.h, _ptr(g), N, rows, ncols, arr, len(ops), _ptr(out), _stream()))
+    check(tp.lib.cape_colsum(tp.h, _ptr(g), ncols if g_stride is None else g_stride, N, rows, ncols, arr, len(ops),
+                             _ptr(out), _stream()))
 
 
 def weight_transpose(tp, w, Fin, K, Fout, wt):
@@ -207,5 +208,19 @@ def axpy(tp, y, x, a):
     check(tp.lib.cape_axpy(_ptr(y), _ptr(x), float(a), y.numel(), _stream()))
 
 
-def resample(tp, op, x, y, N, rows_out, rows_in, F):
-    check(tp.lib.cape_resample(tp.h, op, _ptr(x), _ptr(y), N, rows_out, rows_in, F, _stream()))
+def resample(tp, op, x, y, N, rows_out, rows_in, F, x_stride=None, y_stride=None, cond=None):
+    check(tp.lib.cape_resample(tp.h, op, _ptr(x), F if x_stride is None else x_stride, _ptr(y),
+                               F if y_stride is None else y_stride, N, rows_out, rows_in, F, _ptr(cond),
+                               cond.shape[1] if cond is not None else 0, _stream()))
+
+
+def gn_relu_fwd(tp, x, gamma, beta, y, stats, G, eps=1e-5):
+    N, rows, Cc = x.shape
+    check(tp.lib.cape_gn_relu_fwd(tp.h, _ptr(x), N, rows, Cc, G, eps, _ptr(gamma), _ptr(beta), _ptr(y), _ptr(stats),
+                                  _stream()))
+
+
+def gn_relu_bwd(tp, x, y, dy, gamma, stats, dx, dgamma, dbeta, G, accumulate_dx=False):
+    N, rows, Cc = x.shape
+    check(tp.lib.cape_gn_relu_bwd(tp.h, _ptr(x), _ptr(y), _ptr(dy), N, rows, Cc, G, _ptr(gamma), _ptr(stats), _ptr(dx),
+                                  1 if accumulate_dx else 0, _ptr(dgamma), _ptr(dbeta), _stream()))

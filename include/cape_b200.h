@@ -120,10 +120,11 @@ typedef struct {
 } cape_dw_args;
 int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* stream);
 
-/* Per-sample weighted column sums: out[n, j, c] = sum_r rowsum(op_j)[r] * g[n, r, c]  (op_j < 0: ones).
- * Gives the bias gradient (models.py:105-109) and the gradient of the condition broadcast
- * (the reduce-over-vertices implied by fit_cond_dim, models.py:829-830).  out must be zeroed by the caller. */
-int cape_colsum(cape_topology* t, const float* g, int N, int rows, int ncols,
+/* Per-sample weighted column sums: out[n, j, c] = sum_r rowsum(op_j)[r] * g[n, r, c]  (op_j < 0: ones); rows of g
+ * are g_stride floats apart (>= ncols).  Gives the bias gradient (models.py:105-109) and the gradient of the
+ * condition broadcast (the reduce-over-vertices implied by fit_cond_dim, models.py:829-830).  out is ACCUMULATED
+ * into (zero it first). */
+int cape_colsum(cape_topology* t, const float* g, int g_stride, int N, int rows, int ncols,
                 const int* ops, int nops, float* out, void* stream);
 
 /* ---- dense layers (tf.layers.dense, lib/models.py:496,506,510,557,560,582) ------------------------
@@ -134,10 +135,12 @@ int cape_gemm(cape_topology* t, int M, int N, int K,
               float* c, int64_t c_rs,
               const float* bias, int act, float leaky_alpha, float alpha, float beta, void* stream);
 
-/* Stand-alone mesh resampling y[n] = S x[n] (poolwT, lib/models.py:129-152) for an operator registered in the
- * topology (D: row selection, U: 3-tap barycentric); the backward pass is the same call with S^T. */
-int cape_resample(cape_topology* t, int op, const float* x, float* y, int N, int rows_out, int rows_in, int F,
-                  void* stream);
+/* Stand-alone mesh resampling y[n, :, :F] = S x[n, :, :F] (poolwT, lib/models.py:129-152) for an operator registered
+ * in the topology (D: row selection, U: 3-tap barycentric; op < 0: identity copy); rows of x / y are x_stride /
+ * y_stride floats apart.  If cond != NULL the condition channels of the reference's concat-then-unpool are written
+ * as well: y[n, r, F + c] = rowsum(S)[r] * cond[n, c] (lib/models.py:606-609,750).  Backward: same call with S^T. */
+int cape_resample(cape_topology* t, int op, const float* x, int x_stride, float* y, int y_stride, int N, int rows_out,
+                  int rows_in, int F, const float* cond, int C, void* stream);
 
 /* Weight re-layout for the data-gradient pass of chebyshev5: wt[(c*K + k)*Fin + f] = w[(f*K + k)*Fout + c]
  * for f < Fin (rows of w beyond Fin*K -- the condition channels -- are not touched). */
@@ -180,12 +183,14 @@ int cape_sgd_clip_update(float* w, const float* g, float* mom, int64_t n, const 
 /* ---- group norm (CAPE.gn, lib/models.py:681-712) + ReLU, for the non-affine decoder blocks ------------
  * x: [N, rows, C], G groups of C/G contiguous channels; stats over (C/G x rows) per (n, g), biased variance,
  * y = relu(gamma*(x-mean)*rstd + beta).  stats: [N, G, 2] = (mean, rstd), saved for the backward pass.
- * Backward: dy is the gradient w.r.t. y (after the ReLU); dgamma/dbeta are ACCUMULATED (zero them first).
+ * Backward: dy is the gradient w.r.t. y (after the ReLU); dgamma/dbeta are ACCUMULATED (zero them first); dx is
+ * overwritten, or added to when accumulate_dx != 0 (residual branches meeting at the block input).
  * Both use the topology workspace (N*G*2 doubles) for fp64 group sums. */
 int cape_gn_relu_fwd(cape_topology* t, const float* x, int N, int rows, int C, int G, float eps,
                      const float* gamma, const float* beta, float* y, float* stats, void* stream);
 int cape_gn_relu_bwd(cape_topology* t, const float* x, const float* y, const float* dy, int N, int rows, int C, int G,
-                     const float* gamma, const float* stats, float* dx, float* dgamma, float* dbeta, void* stream);
+                     const float* gamma, const float* stats, float* dx, int accumulate_dx, float* dgamma, float* dbeta,
+                     void* stream);
 
 #ifdef __cplusplus
 }

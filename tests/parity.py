@@ -139,7 +139,7 @@ def gn_case(N=2, rows=862, C=544, seed=0):
     dx = torch.empty_like(xc)
     dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     _lib.check(tp.lib.cape_gn_relu_bwd(tp.h, E._ptr(xc), E._ptr(y), E._ptr(dyc), N, rows, C, G, E._ptr(gc),
-                                       E._ptr(stats), E._ptr(dx), E._ptr(dg), E._ptr(db), E._stream()))
+                                       E._ptr(stats), E._ptr(dx), 0, E._ptr(dg), E._ptr(db), E._stream()))
     t = "gn C=%d rows=%d " % (C, rows)
     return {t + "fwd": rel(y.cpu().numpy(), yt.detach().numpy()), t + "dx": rel(dx.cpu().numpy(), xt.grad.numpy()),
             t + "dgamma": rel(dg.cpu().numpy(), gt.grad.numpy()), t + "dbeta": rel(db.cpu().numpy(), btt.grad.numpy())}
