@@ -102,6 +102,34 @@ __device__ __forceinline__ void ell_gather4(const OpView& op, int r, const float
   }
 }
 
+// Two rows at once: eight independent neighbour-row loads in flight per thread (the gather is latency-bound on L2).
+__device__ __forceinline__ void ell_gather4_pair(const OpView& op, int ra, int rb, const float* base_a,
+                                                 const float* base_b, size_t stride, float4& va, float4& vb) {
+  const int4* ipa = reinterpret_cast<const int4*>(op.idx + (size_t)ra * op.width);
+  const int4* ipb = reinterpret_cast<const int4*>(op.idx + (size_t)rb * op.width);
+  const float4* wpa = reinterpret_cast<const float4*>(op.w + (size_t)ra * op.width);
+  const float4* wpb = reinterpret_cast<const float4*>(op.w + (size_t)rb * op.width);
+  const int nb = op.width >> 2;
+  int4 ia = __ldg(ipa), ib = __ldg(ipb);
+  for (int b = 0; b < nb; ++b) {
+    const bool da = ia.x >= 0, db = ib.x >= 0;
+    if (!da && !db) break;
+    // w of an exhausted row is irrelevant: its loads are redirected to row 0 and multiplied by 0
+    float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (da) wa = __ldg(wpa + b);
+    if (db) wb = __ldg(wpb + b);
+    int4 na = make_int4(-1, -1, -1, -1), nbx = make_int4(-1, -1, -1, -1);
+    if (b + 1 < nb) { na = __ldg(ipa + b + 1); nbx = __ldg(ipb + b + 1); }
+    const float4 a0 = ldg4(base_a + (size_t)max(ia.x, 0) * stride), a1 = ldg4(base_a + (size_t)max(ia.y, 0) * stride);
+    const float4 a2 = ldg4(base_a + (size_t)max(ia.z, 0) * stride), a3 = ldg4(base_a + (size_t)max(ia.w, 0) * stride);
+    const float4 b0 = ldg4(base_b + (size_t)max(ib.x, 0) * stride), b1 = ldg4(base_b + (size_t)max(ib.y, 0) * stride);
+    const float4 b2 = ldg4(base_b + (size_t)max(ib.z, 0) * stride), b3 = ldg4(base_b + (size_t)max(ib.w, 0) * stride);
+    fma4(va, wa.x, a0); fma4(va, wa.y, a1); fma4(va, wa.z, a2); fma4(va, wa.w, a3);
+    fma4(vb, wb.x, b0); fma4(vb, wb.y, b1); fma4(vb, wb.z, b2); fma4(vb, wb.w, b3);
+    ia = na; ib = nbx;
+  }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace cape

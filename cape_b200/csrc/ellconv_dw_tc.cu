@@ -165,17 +165,28 @@ __global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __gr
         char* a_lo = a_hi + DT_A_TILE;
         const int f = ftile + lane * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = warp + 8 * i;
-          const long long R = rb + row;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (R < rend && f < p.F) {
-            const int n = (int)(R / p.rows_out), r = (int)(R % p.rows_out);
-            const float* base = p.src + (size_t)n * p.src_rows * p.src_stride + f;
-            if (p.op.idx == nullptr) v = ldg4(base + (size_t)r * p.src_stride);
-            else ell_gather4(p.op, r, base, (size_t)p.src_stride, v);
+        for (int i = 0; i < 4; i += 2) {
+          const int row_a = warp + 8 * i, row_b = row_a + 8;
+          const long long Ra = rb + row_a, Rb = rb + row_b;
+          float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (f < p.F) {
+            // rows beyond the end of this split gather row 0 and are zeroed afterwards
+            const long long Qa = Ra < rend ? Ra : 0, Qb = Rb < rend ? Rb : 0;
+            const int na = (int)(Qa / p.rows_out), ra = (int)(Qa % p.rows_out);
+            const int nb2 = (int)(Qb / p.rows_out), rb2 = (int)(Qb % p.rows_out);
+            const float* base_a = p.src + (size_t)na * p.src_rows * p.src_stride + f;
+            const float* base_b = p.src + (size_t)nb2 * p.src_rows * p.src_stride + f;
+            if (p.op.idx == nullptr) {
+              va = ldg4(base_a + (size_t)ra * p.src_stride);
+              vb = ldg4(base_b + (size_t)rb2 * p.src_stride);
+            } else {
+              ell_gather4_pair(p.op, ra, rb2, base_a, base_b, (size_t)p.src_stride, va, vb);
+            }
+            if (Ra >= rend) va = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (Rb >= rend) vb = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          split_store(v, a_hi, a_lo, mn_off(mb, row, ch));
+          split_store(va, a_hi, a_lo, mn_off(mb, row_a, ch));
+          split_store(vb, a_hi, a_lo, mn_off(mb, row_b, ch));
         }
         fence_proxy_async();
         __syncwarp();

@@ -182,15 +182,24 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
             char* a_hi = a_ring + (size_t)sa * Cfg::A_STAGE_BYTES;
             char* a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int row = rs + 32 * i;
-              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (rn[i] >= 0 && f < tm.F) {
-                const float* base = tm.src + (size_t)rn[i] * tm.src_rows * tm.src_stride + f;
-                if (tm.op.idx == nullptr) v = ldg4(base + (size_t)rr[i] * tm.src_stride);
-                else ell_gather4(tm.op, rr[i], base, (size_t)tm.src_stride, v);
+            for (int i = 0; i < 4; i += 2) {
+              const int row_a = rs + 32 * i, row_b = row_a + 32;
+              float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (f < tm.F) {
+                // invalid (beyond-the-end) rows gather sample 0 / row 0 and are zeroed afterwards
+                const float* base_a = tm.src + (size_t)max(rn[i], 0) * tm.src_rows * tm.src_stride + f;
+                const float* base_b = tm.src + (size_t)max(rn[i + 1], 0) * tm.src_rows * tm.src_stride + f;
+                if (tm.op.idx == nullptr) {
+                  va = ldg4(base_a + (size_t)rr[i] * tm.src_stride);
+                  vb = ldg4(base_b + (size_t)rr[i + 1] * tm.src_stride);
+                } else {
+                  ell_gather4_pair(tm.op, rr[i], rr[i + 1], base_a, base_b, (size_t)tm.src_stride, va, vb);
+                }
+                if (rn[i] < 0) va = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rn[i + 1] < 0) vb = make_float4(0.f, 0.f, 0.f, 0.f);
               }
-              split_store(v, a_hi, a_lo, (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4)));
+              split_store(va, a_hi, a_lo, (uint32_t)(row_a * 128 + ((l8 ^ (row_a & 7)) << 4)));
+              split_store(vb, a_hi, a_lo, (uint32_t)(row_b * 128 + ((l8 ^ (row_b & 7)) << 4)));
             }
             fence_proxy_async();             // generic-proxy smem writes -> visible to the tensor-core (async) proxy
             __syncwarp();

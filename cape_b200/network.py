@@ -248,6 +248,83 @@ class Dense:
             gemm(self.tp, g, self.W.t(), dx, beta=dx_beta)
 
 
+class GNBlock:
+    """GraphCMR-style decoder residual block with group norm (res_block_decoder, lib/models.py:744-774):
+    Z = unpool([x ; cond]); h = lin1(relu(GN(Z))); h = cheb_K(relu(GN(h))); out = lin2(relu(GN(h))) + lin_in(Z).
+    The concat+unpool is one gather kernel (condition channels = rowsum(U) * y, never read from HBM), every
+    GN+ReLU is one fused pass each way, lin2 + lin_in is a single two-term contraction."""
+
+    def __init__(self, net, idx, L, U, Fin, Cc, Fo, K, scope, maxN):
+        import scipy.sparse as sp
+        self.net, self.tp = net, net.tp
+        tp, dev = net.tp, net.device
+        w, g = net._w, net._g
+        self.Fin, self.Cc, self.Ft, self.mid, self.Fo = Fin, Cc, Fin + Cc, Fo // 2, Fo
+        self.rows, self.rows_in = L.shape[0], U.shape[1]
+        if topo.is_identity(U, tol=1e-6):
+            self.op_u = self.op_uT = -1
+        else:
+            self.op_u, self.op_uT = tp.add_operator(sp.csr_matrix(U)), tp.add_operator(sp.csr_matrix(U.T))
+        lin, conv = ConvSite(tp, L, 1), ConvSite(tp, L, K)
+        nm = "dec/res%d" % (idx + 1)
+        mk = lambda site, F, Fout, sc, tag: ChebLayer(net, site, F, 0, Fout, w(scope + "/" + sc + "/weights"),
+                                                      g(scope + "/" + sc + "/weights"), maxN=maxN, name=nm + "/" + tag)
+        self.lin1 = mk(lin, self.Ft, self.mid, "graph_linear_1", "lin1")
+        self.conv = mk(conv, self.mid, self.mid, "graph_conv", "graph_conv")
+        self.lin2 = mk(lin, self.mid, Fo, "graph_linear_2", "lin2")
+        self.lin_in = mk(lin, self.Ft, Fo, "graph_linear_input", "lin_in")
+        self.gn = []
+        for sc, C in (("group_norm", self.Ft), ("group_norm_1", self.mid), ("group_norm_2", self.mid)):
+            self.gn.append(dict(C=C, G=min(32, C), gamma=w(scope + "/" + sc + "/gamma"), beta=w(scope + "/" + sc + "/beta"),
+                                dgamma=g(scope + "/" + sc + "/gamma"), dbeta=g(scope + "/" + sc + "/beta"),
+                                stats=torch.zeros(maxN, min(32, C), 2, device=dev)))
+        z = lambda *sh: torch.zeros(*sh, device=dev)
+        N, M = maxN, self.rows
+        self.Z, self.A1 = z(N, M, self.Ft), z(N, M, self.Ft)
+        self.H1, self.A2, self.H2, self.A3 = z(N, M, self.mid), z(N, M, self.mid), z(N, M, self.mid), z(N, M, self.mid)
+        self.dZ, self.dA1 = z(N, M, self.Ft), z(N, M, self.Ft)
+        self.dH1, self.dA2, self.dH2, self.dA3 = z(N, M, self.mid), z(N, M, self.mid), z(N, M, self.mid), z(N, M, self.mid)
+
+    def layers(self):
+        return [self.lin1, self.conv, self.lin2, self.lin_in]
+
+    def fwd(self, x, ycat, out):
+        tp, N = self.tp, x.shape[0]
+        E.resample(tp, self.op_u, x, self.Z, N, self.rows, self.rows_in, self.Fin, x_stride=x.shape[2],
+                   y_stride=self.Ft, cond=ycat)
+        g0, g1, g2 = self.gn
+        E.gn_relu_fwd(tp, self.Z, g0["gamma"], g0["beta"], self.A1, g0["stats"], g0["G"])
+        self.lin1.fwd(self.A1, None, self.H1)
+        E.gn_relu_fwd(tp, self.H1, g1["gamma"], g1["beta"], self.A2, g1["stats"], g1["G"])
+        self.conv.fwd(self.A2, None, self.H2)
+        E.gn_relu_fwd(tp, self.H2, g2["gamma"], g2["beta"], self.A3, g2["stats"], g2["G"])
+        l2, li = self.lin2, self.lin_in
+        terms = [dict(src=self.A3, op=-1, F=self.mid, src_rows=self.rows, src_stride=self.mid, w=l2.W3[:, 0, :],
+                      w_stride=self.Fo, wT=l2.Wt[:, 0, :], wT_stride=self.mid),
+                 dict(src=self.Z, op=-1, F=self.Ft, src_rows=self.rows, src_stride=self.Ft, w=li.W3[:, 0, :],
+                      w_stride=self.Fo, wT=li.Wt[:, 0, :], wT_stride=self.Ft)]
+        cheb_call(tp, N, self.rows, self.Fo, terms, out,
+                  tag=("dec/res:out", l2.alg_bytes(N, "fwd") + li.alg_bytes(N, "fwd")))
+
+    def bwd(self, x, ycat, dout, dx, dycat):
+        """dout: gradient w.r.t. the block output; dx: gradient w.r.t. the block input x (written); dycat +=."""
+        tp, N = self.tp, dout.shape[0]
+        g0, g1, g2 = self.gn
+        self.lin2.bwd(self.A3, None, dout, dx=self.dA3)
+        self.lin_in.bwd(self.Z, None, dout, dx=self.dZ)
+        E.gn_relu_bwd(tp, self.H2, self.A3, self.dA3, g2["gamma"], g2["stats"], self.dH2, g2["dgamma"], g2["dbeta"], g2["G"])
+        self.conv.bwd(self.A2, None, self.dH2, dx=self.dA2)
+        E.gn_relu_bwd(tp, self.H1, self.A2, self.dA2, g1["gamma"], g1["stats"], self.dH1, g1["dgamma"], g1["dbeta"], g1["G"])
+        self.lin1.bwd(self.A1, None, self.dH1, dx=self.dA1)
+        E.gn_relu_bwd(tp, self.Z, self.A1, self.dA1, g0["gamma"], g0["stats"], self.dZ, g0["dgamma"], g0["dbeta"], g0["G"],
+                      accumulate_dx=True)
+        # back through concat + unpool: feature channels with U^T, condition channels reduced over the vertices
+        E.resample(tp, self.op_uT, self.dZ, dx, N, self.rows_in, self.rows, self.Fin, x_stride=self.Ft,
+                   y_stride=dx.shape[2])
+        colsum(tp, self.dZ[:, :, self.Fin:], N, self.rows, self.Cc, [self.op_u], dycat.view(N, 1, self.Cc),
+               g_stride=self.Ft)
+
+
 class CapeNetwork:
     """Encoder/decoder/discriminator + losses + optimiser on one GPU for a fixed batch size."""
 
@@ -261,8 +338,6 @@ class CapeNetwork:
                                       "use_res_block_dec=1, cond_encoder=0, reduce_dim>0")
         if c["optimizer"] != "sgd" or c["loss"] != "l1":
             raise NotImplementedError("only optimizer='sgd' (momentum) and loss='l1' are implemented")
-        if not c["affine"]:
-            raise NotImplementedError("non-affine (GroupNorm) decoder blocks: see cape_b200.network_gn")
         self.tp = tp = Topology(device)
         self.device = dev = tp.device
         torch.cuda.set_device(dev)
@@ -308,14 +383,20 @@ class CapeNetwork:
         self.dec_1x1 = ChebLayer(self, ConvSite(tp, L[-1], 1), red, 0, F[-1], w("generator/decoder/1x1-conv/weights"),
                                  g("generator/decoder/1x1-conv/weights"), maxN=N, name="dec/1x1")
         self.dec = []
+        self.affine = bool(c["affine"])
         fin = F[-1]
         for i in range(nl):
-            Fo = F[-i - 1] // 2
-            site = ConvSite(tp, L[-i - 2], K[-i - 1], U=U[-i - 1])
-            sc = "generator/decoder/decoder_resblock_affine%d" % (i + 1)
-            self.dec.append(ChebLayer(self, site, fin, Cc, Fo, w(sc + "/graph_conv/weights"),
-                                      g(sc + "/graph_conv/weights"), Wa=w(sc + "/affine/weights"),
-                                      gWa=g(sc + "/affine/weights"), maxN=N, name="dec/aff%d" % (i + 1)))
+            if self.affine:
+                Fo = F[-i - 1] // 2
+                site = ConvSite(tp, L[-i - 2], K[-i - 1], U=U[-i - 1])
+                sc = "generator/decoder/decoder_resblock_affine%d" % (i + 1)
+                self.dec.append(ChebLayer(self, site, fin, Cc, Fo, w(sc + "/graph_conv/weights"),
+                                          g(sc + "/graph_conv/weights"), Wa=w(sc + "/affine/weights"),
+                                          gWa=g(sc + "/affine/weights"), maxN=N, name="dec/aff%d" % (i + 1)))
+            else:
+                Fo = F[-i - 1]
+                self.dec.append(GNBlock(self, i, L[-i - 2], U[-i - 1], fin, Cc, Fo, K[-i - 1],
+                                        "generator/decoder/decoder_resblock_cmr%d" % (i + 1), N))
             fin = Fo
         self.dec_out = ChebLayer(self, ConvSite(tp, L[0], K[0]), fin, Cc, c["nn_input_channel"],
                                  w("generator/decoder/outputs/weights"), g("generator/decoder/outputs/weights"),
@@ -365,8 +446,12 @@ class CapeNetwork:
         self.z_total = z(N, nz + Cc)
         self.dec_fc = z(N, flat)
         self.dec_h0 = z(N, self.p[-1], F[-1])
-        self.dec_act = [z(N, l.site.rows_out, l.Fout) for l in self.dec]
-        self.dec_rg = [z(N, l.site.rows_out, l.Fout) for l in self.dec]
+        if self.affine:
+            self.dec_act = [z(N, l.site.rows_out, l.Fout) for l in self.dec]
+            self.dec_rg = [z(N, l.site.rows_out, l.Fout) for l in self.dec]
+        else:
+            self.dec_act = [z(N, b.rows, b.Fo) for b in self.dec]
+            self.dec_rg = []
         self.disc_act = [z(2 * N, l.site.rows_out, l.Fout) for l in self.disc]
         self.logits = z(2 * N, self.p_d[-1], 1)
         # gradients
@@ -375,8 +460,8 @@ class CapeNetwork:
         self.g_disc = [z(2 * N, l.site.rows_out, l.Fout) for l in self.disc]
         self.d_xhat = z(N, P0, 3)
         self.d_ycat = z(N, Cc)
-        self.g_dec = [z(N, l.site.rows_out, l.Fout) for l in self.dec]       # d out of each block
-        self.g_dec_m = [z(N, l.site.rows_out, l.Fout) for l in self.dec]     # masked (graph-conv branch)
+        self.g_dec = [torch.zeros_like(a) for a in self.dec_act]             # d out of each block
+        self.g_dec_m = [torch.zeros_like(a) for a in self.dec_act] if self.affine else []   # masked (graph-conv branch)
         self.g_dec_h0 = z(N, self.p[-1], F[-1])
         self.g_dec_fc = z(N, flat)
         self.g_dec_fc_t = z(N, flat)
@@ -423,7 +508,8 @@ class CapeNetwork:
         self.prep_weights()
 
     def all_layers(self):
-        return self.enc + [self.enc_1x1, self.dec_1x1] + self.dec + [self.dec_out] + self.disc + [self.disc_pred]
+        dec = self.dec if self.affine else [l for b in self.dec for l in b.layers()]
+        return self.enc + [self.enc_1x1, self.dec_1x1] + dec + [self.dec_out] + self.disc + [self.disc_pred]
 
     def prep_weights(self):
         """Re-layouts derived from the weights (transposes for the data-gradient pass); run after every update."""
@@ -478,9 +564,14 @@ class CapeNetwork:
         self.dec_fc1.fwd(z_total, self.dec_fc)
         self.dec_1x1.fwd(self.dec_fc.view(self.N, self.p[-1], self.red), None, self.dec_h0)
         x = self.dec_h0
-        for l, a, rg in zip(self.dec, self.dec_act, self.dec_rg):
-            l.fwd(x, ycat, a, out2=rg)
-            x = a
+        if self.affine:
+            for l, a, rg in zip(self.dec, self.dec_act, self.dec_rg):
+                l.fwd(x, ycat, a, out2=rg)
+                x = a
+        else:
+            for b, a in zip(self.dec, self.dec_act):
+                b.fwd(x, ycat, a)
+                x = a
         self.dec_out.fwd(x, ycat, out)
 
     def disc_fwd(self, lo, hi):
@@ -511,9 +602,15 @@ class CapeNetwork:
         N, nl = self.N, len(self.dec)
         yc = self.ycat_g
         last = self.dec_act[-1]
-        self.dec_out.bwd(last, yc, self.d_xhat, dx=self.g_dec[-1], dx2=self.g_dec_m[-1], dx_epi=EPI_DUALMASK,
-                         dx_aux=self.dec_rg[-1], dycat=self.d_ycat)
-        for i in range(nl - 1, -1, -1):
+        if not self.affine:
+            self.dec_out.bwd(last, yc, self.d_xhat, dx=self.g_dec[-1], dycat=self.d_ycat)
+            for i in range(nl - 1, -1, -1):
+                x = self.dec_act[i - 1] if i > 0 else self.dec_h0
+                self.dec[i].bwd(x, yc, self.g_dec[i], self.g_dec[i - 1] if i > 0 else self.g_dec_h0, self.d_ycat)
+        else:
+            self.dec_out.bwd(last, yc, self.d_xhat, dx=self.g_dec[-1], dx2=self.g_dec_m[-1], dx_epi=EPI_DUALMASK,
+                             dx_aux=self.dec_rg[-1], dycat=self.d_ycat)
+        for i in range(nl - 1 if self.affine else -1, -1, -1):
             x = self.dec_act[i - 1] if i > 0 else self.dec_h0
             if i > 0:
                 self.dec[i].bwd(x, yc, self.g_dec_m[i], g_aff=self.g_dec[i], dx=self.g_dec[i - 1],
@@ -591,6 +688,8 @@ class CapeNetwork:
         self.arena.zero()
         self.losses.zero_()
         self.d_ycat.zero_()
+        if not self.affine:
+            self.PG.grad.zero_()          # group-norm gamma/beta gradients are accumulated by their kernels
         # forward: both condition batches at once, generator, discriminator on [real ; fake]
         self.cond_fwd(0, 2 * N)
         self.encoder_fwd()

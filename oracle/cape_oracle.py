@@ -199,11 +199,14 @@ class Oracle:
         x_unpooled = self.poolwT(x_in, self.Um[-i - 1])
         Lt = self.Lt[-i - 2]
         Fo = self.F[-i - 1]
-        x = torch.relu(self.gn(x_unpooled, P[scope + "/group_norm/gamma"], P[scope + "/group_norm/beta"]))
+        x = self._act(self.gn(x_unpooled, P[scope + "/group_norm/gamma"], P[scope + "/group_norm/beta"]), 0.0,
+                      "gn%d_0" % (i + 1))                                          # tf.nn.relu, :752
         x = self.chebyshev5(x, Lt, P[scope + "/graph_linear_1/weights"], 1)
-        x = torch.relu(self.gn(x, P[scope + "/group_norm_1/gamma"], P[scope + "/group_norm_1/beta"]))
+        x = self._act(self.gn(x, P[scope + "/group_norm_1/gamma"], P[scope + "/group_norm_1/beta"]), 0.0,
+                      "gn%d_1" % (i + 1))
         x = self.chebyshev5(x, Lt, P[scope + "/graph_conv/weights"], self.K[-i - 1])
-        x = torch.relu(self.gn(x, P[scope + "/group_norm_2/gamma"], P[scope + "/group_norm_2/beta"]))
+        x = self._act(self.gn(x, P[scope + "/group_norm_2/gamma"], P[scope + "/group_norm_2/beta"]), 0.0,
+                      "gn%d_2" % (i + 1))
         x = self.chebyshev5(x, Lt, P[scope + "/graph_linear_2/weights"], 1)
         if x_unpooled.shape[-1] != Fo:
             x_unpooled = self.chebyshev5(x_unpooled, Lt, P[scope + "/graph_linear_input/weights"], 1)

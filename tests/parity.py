@@ -202,6 +202,10 @@ def train_step(h, cfg, N=2, ref_compat=False, step=100, seed=123, dtype=torch.fl
                 rows["enc%d" % (i + 1)] = r
         for i, a in enumerate(net.dec_rg):
             masks["dec%d" % (i + 1)] = (a > 0).cpu()
+        if not net.affine:                                # GroupNorm blocks: three ReLUs each (lib/models.py:752-760)
+            for i, b in enumerate(net.dec):
+                for j, a in enumerate((b.A1, b.A2, b.A3)):
+                    masks["gn%d_%d" % (i + 1, j)] = (a > 0).cpu()
         masks["dec_fc1"] = (net.dec_fc > 0).cpu()
         for i, a in enumerate(net.disc_act):
             r = sel(h["D_d"][i])

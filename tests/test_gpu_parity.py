@@ -72,6 +72,13 @@ def test_train_step_odd_batch(hierarchy, cfg):
     _assert_all(parity.train_step(hierarchy, cfg, N=5, seed=7))
 
 
+def test_train_step_groupnorm_decoder(hierarchy):
+    """BASELINE configs[4]: CAPE nz18_pose24_clotype8, non-affine decoder (GroupNorm residual blocks,
+    lib/models.py:744-774) -- the plain chebyshev5 path; full update vs the oracle."""
+    from cape_b200.params import NZ18_PLAIN
+    _assert_all(parity.train_step(hierarchy, dict(NZ18_PLAIN, decay_steps=10), N=2))
+
+
 def test_size_independent_properties(hierarchy, cfg):
     """Full-size (batch 64) checks that need no oracle: linearity of the conv in x and W, batch-permutation
     equivariance of the generator, CUDA-graph replay == eager."""

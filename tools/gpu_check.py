@@ -28,7 +28,9 @@ def main():
             ("step_ref", lambda: parity.train_step(h, cfg, N=2, ref_compat=True)),
             ("step_rawinit", lambda: parity.train_step(h, cfg, N=2, fc_scale=1.0)),
             ("step_nomask", lambda: parity.train_step(h, cfg, N=2, impose_masks=False)),
-            ("step_n5", lambda: parity.train_step(h, cfg, N=5, seed=7))]
+            ("step_n5", lambda: parity.train_step(h, cfg, N=5, seed=7)),
+            ("step_gn", lambda: parity.train_step(h, dict(__import__("cape_b200.params", fromlist=["x"]).NZ18_PLAIN,
+                                                          decay_steps=10), N=2))]
     allres = {}
     for name, fn in jobs:
         if only and name not in only:
