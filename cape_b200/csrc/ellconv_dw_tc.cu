@@ -108,8 +108,8 @@ struct DtCfg {
   static constexpr int G_TILE = (BN / 32) * 4096;             // BN columns x 32 rows, hi or lo
   static constexpr int A_STAGE = 2 * DT_A_TILE;
   static constexpr int G_STAGE = 2 * G_TILE;
-  static constexpr int A_STAGES = 2;
-  static constexpr int G_STAGES = 3;
+  static constexpr int A_STAGES = 3;
+  static constexpr int G_STAGES = (3 * G_STAGE <= 96 * 1024) ? 3 : 2;
   static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_STAGE + G_STAGES * G_STAGE + 256;
 };
 
@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __gr
 
   if (warp == DT_PROD_WARPS) {
     if (lane == 0) {
-      for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, DT_PROD_WARPS); mbar_init(bar_aempty + 8 * s, 1); }
-      for (int s = 0; s < SG; ++s) { mbar_init(bar_gfull + 8 * s, DT_PROD_WARPS); mbar_init(bar_gempty + 8 * s, 1); }
+      for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, DT_PROD_WARPS / 2); mbar_init(bar_aempty + 8 * s, 1); }
+      for (int s = 0; s < SG; ++s) { mbar_init(bar_gfull + 8 * s, DT_PROD_WARPS / 2); mbar_init(bar_gempty + 8 * s, 1); }
       mbar_init(bar_accum, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -153,20 +153,22 @@ __global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __gr
 
   if (warp < DT_PROD_WARPS) {
     // =========================== producers ===========================
+    // Two specialised groups run concurrently (each hides its own L2 latency and runs ahead as far as its ring
+    // allows): warps 0-3 gather the basis rows A (8 rows per thread, two at a time), warps 4-7 stream the gradient
+    // rows G of every column sub-tile (8 independent 16-byte loads in flight per thread).
     const int mb = lane >> 3, ch = lane & 7;       // 32-element MN block and 16-byte chunk of this lane's float4
-    int sa = 0, sg = 0;
-    uint32_t pha = 0, phg = 0;
-    for (long long kc = 0; kc < nchunks; ++kc) {
-      const long long rb = rbeg + kc * DT_KCH;
-      // ---- A: each warp gathers rows warp, warp+8, warp+16, warp+24 of the chunk (512 contiguous bytes per row)
-      mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
-      {
+    if (warp < DT_PROD_WARPS / 2) {
+      int sa = 0;
+      uint32_t pha = 0;
+      const int f = ftile + lane * 4;
+      for (long long kc = 0; kc < nchunks; ++kc) {
+        const long long rb = rbeg + kc * DT_KCH;
+        mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
         char* a_hi = a_ring + (size_t)sa * Cfg::A_STAGE;
         char* a_lo = a_hi + DT_A_TILE;
-        const int f = ftile + lane * 4;
 #pragma unroll
-        for (int i = 0; i < 4; i += 2) {
-          const int row_a = warp + 8 * i, row_b = row_a + 8;
+        for (int i = 0; i < 8; i += 2) {
+          const int row_a = warp + 4 * i, row_b = row_a + 4;
           const long long Ra = rb + row_a, Rb = rb + row_b;
           float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = make_float4(0.f, 0.f, 0.f, 0.f);
           if (f < p.F) {
@@ -193,27 +195,34 @@ __global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __gr
         if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
         if (++sa == SA) { sa = 0; pha ^= 1; }
       }
-      // ---- G: one [32 rows x BN cols] tile per column sub-tile
-      for (int cs = 0; cs < nct; ++cs) {
-        mbar_wait(bar_gempty + 8 * sg, phg ^ 1);
-        char* g_hi = g_ring + (size_t)sg * Cfg::G_STAGE;
-        char* g_lo = g_hi + Cfg::G_TILE;
-        const int cl = lane * 4;
-        if (cl < BN) {
-          const int c = cs * BN + cl;
+    } else {
+      int sg = 0;
+      uint32_t phg = 0;
+      const int gw = warp - DT_PROD_WARPS / 2;
+      const int cl = lane * 4;
+      for (long long kc = 0; kc < nchunks; ++kc) {
+        const long long rb = rbeg + kc * DT_KCH;
+        for (int cs = 0; cs < nct; ++cs) {
+          mbar_wait(bar_gempty + 8 * sg, phg ^ 1);
+          char* g_hi = g_ring + (size_t)sg * Cfg::G_STAGE;
+          char* g_lo = g_hi + Cfg::G_TILE;
+          if (cl < BN) {
+            const int c = cs * BN + cl;
+            float4 v[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = warp + 8 * i;
-            const long long R = rb + row;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (R < rend && c < p.ncols) v = ldg4(p.g + (size_t)R * p.ncols + c);
-            split_store(v, g_hi, g_lo, mn_off(mb, row, ch));
+            for (int i = 0; i < 8; ++i) {
+              const long long R = rb + gw + 4 * i;
+              v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (R < rend && c < p.ncols) v[i] = ldg4(p.g + (size_t)R * p.ncols + c);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split_store(v[i], g_hi, g_lo, mn_off(mb, gw + 4 * i, ch));
           }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_gfull + 8 * sg);
+          if (++sg == SG) { sg = 0; phg ^= 1; }
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_gfull + 8 * sg);
-        if (++sg == SG) { sg = 0; phg ^= 1; }
       }
     }
 
