@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=4, help="meshes per step of the CPU arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--tune", default="", help="experiment knobs key=value,... passed to cape_set_tuning")
     return ap.parse_args()
 
 
@@ -163,6 +164,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        lib.cape_set_tuning(int(k), int(v))
     cfg, h = config_and_hierarchy()
     N = args.batch
     net = CapeNetwork(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], cfg, N, device=local)

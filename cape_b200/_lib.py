@@ -43,6 +43,7 @@ SIGNATURES = {
     "cape_topology_add_operator": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cape_topology_reserve_workspace": (C.c_int, [C.c_void_p, C.c_int64]),
     "cape_set_tensor_cores": (C.c_int, [C.c_int]),
+    "cape_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "cape_cheb_fwd": (C.c_int, [C.c_void_p, C.POINTER(ConvArgs), C.c_void_p]),
     "cape_cheb_dw": (C.c_int, [C.c_void_p, C.POINTER(DwArgs), C.c_void_p]),
     "cape_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int,

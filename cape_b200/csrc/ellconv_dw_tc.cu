@@ -115,7 +115,7 @@ struct DtCfg {
 
 template <int BN>
 __global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __grid_constant__ DwTcParams p, int nct,
-                                                                      int tmem_cols) {
+                                                                      int tmem_cols, int split_roles) {
   using Cfg = DtCfg<BN>;
   constexpr int SA = Cfg::A_STAGES, SG = Cfg::G_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __gr
 
   if (warp == DT_PROD_WARPS) {
     if (lane == 0) {
-      for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, DT_PROD_WARPS / 2); mbar_init(bar_aempty + 8 * s, 1); }
-      for (int s = 0; s < SG; ++s) { mbar_init(bar_gfull + 8 * s, DT_PROD_WARPS / 2); mbar_init(bar_gempty + 8 * s, 1); }
+      for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, split_roles ? DT_PROD_WARPS / 2 : DT_PROD_WARPS); mbar_init(bar_aempty + 8 * s, 1); }
+      for (int s = 0; s < SG; ++s) { mbar_init(bar_gfull + 8 * s, split_roles ? DT_PROD_WARPS / 2 : DT_PROD_WARPS); mbar_init(bar_gempty + 8 * s, 1); }
       mbar_init(bar_accum, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -153,36 +153,41 @@ __global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __gr
 
   if (warp < DT_PROD_WARPS) {
     // =========================== producers ===========================
-    // Two specialised groups run concurrently (each hides its own L2 latency and runs ahead as far as its ring
-    // allows): warps 0-3 gather the basis rows A (8 rows per thread, two at a time), warps 4-7 stream the gradient
-    // rows G of every column sub-tile (8 independent 16-byte loads in flight per thread).
+    // Producer roles.  split_roles (wide outputs, ncols >= 256: the G stream is as heavy as the gather): warps 0-3
+    // gather the basis rows A, warps 4-7 stream the gradient rows G, concurrently, each running ahead as far as its
+    // ring allows.  Otherwise (narrow outputs: the gather dominates) all 8 warps do A and then G of each chunk.
     const int mb = lane >> 3, ch = lane & 7;       // 32-element MN block and 16-byte chunk of this lane's float4
-    if (warp < DT_PROD_WARPS / 2) {
-      int sa = 0;
-      uint32_t pha = 0;
-      const int f = ftile + lane * 4;
-      for (long long kc = 0; kc < nchunks; ++kc) {
-        const long long rb = rbeg + kc * DT_KCH;
+    const int na = split_roles ? DT_PROD_WARPS / 2 : DT_PROD_WARPS;       // warps (and row stride) of the A group
+    const int ng = split_roles ? DT_PROD_WARPS / 2 : DT_PROD_WARPS;       // same for the G group
+    const bool do_a = !split_roles || warp < na;
+    const bool do_g = !split_roles || warp >= na;
+    const int wa = warp, wg = split_roles ? warp - na : warp;
+    int sa = 0, sg = 0;
+    uint32_t pha = 0, phg = 0;
+    const int fa = ftile + lane * 4;
+    const int cl = lane * 4;
+    for (long long kc = 0; kc < nchunks; ++kc) {
+      const long long rb = rbeg + kc * DT_KCH;
+      if (do_a) {
         mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
         char* a_hi = a_ring + (size_t)sa * Cfg::A_STAGE;
         char* a_lo = a_hi + DT_A_TILE;
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          const int row_a = warp + 4 * i, row_b = row_a + 4;
+        for (int row_a = wa; row_a < DT_KCH; row_a += 2 * na) {
+          const int row_b = row_a + na;
           const long long Ra = rb + row_a, Rb = rb + row_b;
           float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (f < p.F) {
+          if (fa < p.F) {
             // rows beyond the end of this split gather row 0 and are zeroed afterwards
             const long long Qa = Ra < rend ? Ra : 0, Qb = Rb < rend ? Rb : 0;
-            const int na = (int)(Qa / p.rows_out), ra = (int)(Qa % p.rows_out);
-            const int nb2 = (int)(Qb / p.rows_out), rb2 = (int)(Qb % p.rows_out);
-            const float* base_a = p.src + (size_t)na * p.src_rows * p.src_stride + f;
-            const float* base_b = p.src + (size_t)nb2 * p.src_rows * p.src_stride + f;
+            const int n_a = (int)(Qa / p.rows_out), r_a = (int)(Qa % p.rows_out);
+            const int n_b = (int)(Qb / p.rows_out), r_b = (int)(Qb % p.rows_out);
+            const float* base_a = p.src + (size_t)n_a * p.src_rows * p.src_stride + fa;
+            const float* base_b = p.src + (size_t)n_b * p.src_rows * p.src_stride + fa;
             if (p.op.idx == nullptr) {
-              va = ldg4(base_a + (size_t)ra * p.src_stride);
-              vb = ldg4(base_b + (size_t)rb2 * p.src_stride);
+              va = ldg4(base_a + (size_t)r_a * p.src_stride);
+              vb = ldg4(base_b + (size_t)r_b * p.src_stride);
             } else {
-              ell_gather4_pair(p.op, ra, rb2, base_a, base_b, (size_t)p.src_stride, va, vb);
+              ell_gather4_pair(p.op, r_a, r_b, base_a, base_b, (size_t)p.src_stride, va, vb);
             }
             if (Ra >= rend) va = make_float4(0.f, 0.f, 0.f, 0.f);
             if (Rb >= rend) vb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -195,28 +200,28 @@ __global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __gr
         if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
         if (++sa == SA) { sa = 0; pha ^= 1; }
       }
-    } else {
-      int sg = 0;
-      uint32_t phg = 0;
-      const int gw = warp - DT_PROD_WARPS / 2;
-      const int cl = lane * 4;
-      for (long long kc = 0; kc < nchunks; ++kc) {
-        const long long rb = rbeg + kc * DT_KCH;
+      if (do_g) {
         for (int cs = 0; cs < nct; ++cs) {
           mbar_wait(bar_gempty + 8 * sg, phg ^ 1);
           char* g_hi = g_ring + (size_t)sg * Cfg::G_STAGE;
           char* g_lo = g_hi + Cfg::G_TILE;
           if (cl < BN) {
             const int c = cs * BN + cl;
-            float4 v[8];
+            for (int r0 = wg; r0 < DT_KCH; r0 += 4 * ng) {            // 4 independent loads in flight per pass
+              float4 v[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const long long R = rb + gw + 4 * i;
-              v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (R < rend && c < p.ncols) v[i] = ldg4(p.g + (size_t)R * p.ncols + c);
+              for (int i = 0; i < 4; ++i) {
+                const int row = r0 + i * ng;
+                const long long R = rb + row;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < DT_KCH && R < rend && c < p.ncols) v[i] = ldg4(p.g + (size_t)R * p.ncols + c);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int row = r0 + i * ng;
+                if (row < DT_KCH) split_store(v[i], g_hi, g_lo, mn_off(mb, row, ch));
+              }
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) split_store(v[i], g_hi, g_lo, mn_off(mb, gw + 4 * i, ch));
           }
           fence_proxy_async();
           __syncwarp();
@@ -309,7 +314,7 @@ int launch_dw(const DwTcParams& p, int ftiles, cudaStream_t st) {
   int cols = nct * BN, tmem_cols = 32;
   while (tmem_cols < cols) tmem_cols *= 2;
   dim3 grid(ftiles, p.nsplit);
-  ellconv_dw_tc_kernel<BN><<<grid, DT_THREADS, Cfg::SMEM_BYTES, st>>>(p, nct, tmem_cols);
+  ellconv_dw_tc_kernel<BN><<<grid, DT_THREADS, Cfg::SMEM_BYTES, st>>>(p, nct, tmem_cols, nct >= 2 ? 1 : 0);
   CAPE_CHECK_CUDA(cudaGetLastError());
   count_launches(1);
   return 1;
