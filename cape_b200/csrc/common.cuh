@@ -28,19 +28,11 @@ void count_launches(int n);   // bookkeeping for cape_launch_count()
     }                                                                                      \
   } while (0)
 
-constexpr int HALO_TILE = 128;   // output rows per tile of the tcgen05 conv kernel
-constexpr int HALO_CAP = 512;    // max distinct source rows of a tile that are staged in shared memory
-
 struct EllOp {
   int rows_out = 0, rows_in = 0, width = 0;
   int32_t* idx = nullptr;   // device [rows_out, width], -1 = empty slot
   float* w = nullptr;       // device [rows_out, width]
   float* rowsum = nullptr;  // device [rows_out]
-  // "halo" tables per 128-row tile (only if every tile touches <= HALO_CAP distinct source rows):
-  int32_t* hrows = nullptr;   // device [ntiles, hcap]: sorted distinct source rows of the tile
-  int32_t* hcount = nullptr;  // device [ntiles]
-  uint16_t* lidx = nullptr;   // device [rows_out, width]: position of each tap's source row in its tile's list (0xFFFF = empty)
-  int hcap = 0;
 };
 
 }  // namespace cape
@@ -61,10 +53,6 @@ struct OpView {
   const float* w;
   const float* rowsum;
   int width;
-  const int32_t* hrows;
-  const int32_t* hcount;
-  const uint16_t* lidx;
-  int hcap;
 };
 
 inline int get_op(const cape_topology* t, int op, int rows_out, int rows_in, OpView* v) {
@@ -74,7 +62,6 @@ inline int get_op(const cape_topology* t, int op, int rows_out, int rows_in, OpV
       return -1;
     }
     v->idx = nullptr; v->w = nullptr; v->rowsum = nullptr; v->width = 0;
-    v->hrows = nullptr; v->hcount = nullptr; v->lidx = nullptr; v->hcap = 0;
     return 0;
   }
   if (op >= (int)t->ops.size()) { set_error("operator id out of range"); return -1; }
@@ -85,7 +72,6 @@ inline int get_op(const cape_topology* t, int op, int rows_out, int rows_in, OpV
     return -1;
   }
   v->idx = o.idx; v->w = o.w; v->rowsum = o.rowsum; v->width = o.width;
-  v->hrows = o.hrows; v->hcount = o.hcount; v->lidx = o.lidx; v->hcap = o.hcap;
   return 0;
 }
 
@@ -116,17 +102,9 @@ __device__ __forceinline__ void ell_gather4(const OpView& op, int r, const float
   }
 }
 
-__device__ __forceinline__ void prefetch_line(const float* p, int mode) {
-  if (mode == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-  else if (mode == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
-
 // Two rows at once: eight independent neighbour-row loads in flight per thread (the gather is latency-bound on L2).
-// pf != 0: also prefetch the next 128-byte segment of every neighbour row (the next reduction chunk of this term),
-// so that only the first chunk of a term pays the full memory latency.
 __device__ __forceinline__ void ell_gather4_pair(const OpView& op, int ra, int rb, const float* base_a,
-                                                 const float* base_b, size_t stride, float4& va, float4& vb,
-                                                 int pf = 0) {
+                                                 const float* base_b, size_t stride, float4& va, float4& vb) {
   const int4* ipa = reinterpret_cast<const int4*>(op.idx + (size_t)ra * op.width);
   const int4* ipb = reinterpret_cast<const int4*>(op.idx + (size_t)rb * op.width);
   const float4* wpa = reinterpret_cast<const float4*>(op.w + (size_t)ra * op.width);
@@ -146,20 +124,6 @@ __device__ __forceinline__ void ell_gather4_pair(const OpView& op, int ra, int r
     const float4 a2 = ldg4(base_a + (size_t)max(ia.z, 0) * stride), a3 = ldg4(base_a + (size_t)max(ia.w, 0) * stride);
     const float4 b0 = ldg4(base_b + (size_t)max(ib.x, 0) * stride), b1 = ldg4(base_b + (size_t)max(ib.y, 0) * stride);
     const float4 b2 = ldg4(base_b + (size_t)max(ib.z, 0) * stride), b3 = ldg4(base_b + (size_t)max(ib.w, 0) * stride);
-    if (pf) {
-      if (da) {
-        prefetch_line(base_a + (size_t)ia.x * stride + 32, pf);
-        if (ia.y >= 0) prefetch_line(base_a + (size_t)ia.y * stride + 32, pf);
-        if (ia.z >= 0) prefetch_line(base_a + (size_t)ia.z * stride + 32, pf);
-        if (ia.w >= 0) prefetch_line(base_a + (size_t)ia.w * stride + 32, pf);
-      }
-      if (db) {
-        prefetch_line(base_b + (size_t)ib.x * stride + 32, pf);
-        if (ib.y >= 0) prefetch_line(base_b + (size_t)ib.y * stride + 32, pf);
-        if (ib.z >= 0) prefetch_line(base_b + (size_t)ib.z * stride + 32, pf);
-        if (ib.w >= 0) prefetch_line(base_b + (size_t)ib.w * stride + 32, pf);
-      }
-    }
     fma4(va, wa.x, a0); fma4(va, wa.y, a1); fma4(va, wa.z, a2); fma4(va, wa.w, a3);
     fma4(vb, wb.x, b0); fma4(vb, wb.y, b1); fma4(vb, wb.z, b2); fma4(vb, wb.w, b3);
     ia = na; ib = nbx;

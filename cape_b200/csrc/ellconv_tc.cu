@@ -19,8 +19,6 @@
 
 namespace cape {
 
-extern int g_tuning[8];
-
 namespace {
 
 constexpr int TC_PROD_WARPS = 8;
@@ -100,20 +98,15 @@ __device__ __forceinline__ void split_store(float4 v, char* hi_tile, char* lo_ti
   *reinterpret_cast<float4*>(lo_tile + off) = l;
 }
 
-constexpr int HALO_BYTES = HALO_CAP * 128;                           // 512 source rows x 128 bytes of one reduction chunk
-
 template <int BN, bool DUAL>
 struct TcCfg {
   static constexpr int B_TILE_BYTES = BN * 128;                       // one hi or lo tile of BN weight rows x 32 k
   static constexpr int A_STAGE_BYTES = 2 * A_TILE_BYTES;              // hi + lo
   static constexpr int B_STAGE_BYTES = (DUAL ? 4 : 2) * B_TILE_BYTES;  // hi + lo (+ second weight set)
   static constexpr int A_STAGES = 2;
-  static constexpr int B_BUDGET = 226 * 1024 - 1024 - A_STAGES * A_STAGE_BYTES - HALO_BYTES - QS_FLOATS * 4 - 512;
-  static constexpr int B_STAGES_RAW = B_BUDGET / B_STAGE_BYTES;
-  static constexpr int B_STAGES = B_STAGES_RAW > 3 ? 3 : B_STAGES_RAW;
-  static_assert(B_STAGES >= 2, "weight ring needs two stages");
+  static constexpr int B_STAGES = (B_STAGE_BYTES * 3 <= 96 * 1024) ? 3 : 2;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES +
-                                    HALO_BYTES + QS_FLOATS * 4 + 512;
+                                    QS_FLOATS * 4 + 512;
 };
 
 constexpr int TC_EPI_WARPS = 4;
@@ -127,8 +120,7 @@ constexpr int TC_THREADS3 = (TC_PROD_WARPS + 1 + TC_EPI_WARPS) * 32;   // 416
 // activation, stores) -- so the epilogue and start-up of one tile overlap the main loop of the next.
 template <int BN, bool DUAL>
 __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid_constant__ ConvParams p, int nct,
-                                                                    int tmem_cols, int nbuf, int ntiles, int tps,
-                                                                    int pf_mode) {
+                                                                    int tmem_cols, int nbuf, int ntiles) {
   using Cfg = TcCfg<BN, DUAL>;
   constexpr int SA = Cfg::A_STAGES, SB = Cfg::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -136,8 +128,7 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   char* a_ring = smem;
   char* b_ring = smem + SA * Cfg::A_STAGE_BYTES;
-  char* halo = b_ring + SB * Cfg::B_STAGE_BYTES;              // staged neighbour rows of the current chunk
-  float* qs_all = reinterpret_cast<float*>(halo + HALO_BYTES);
+  float* qs_all = reinterpret_cast<float*>(b_ring + SB * Cfg::B_STAGE_BYTES);
   // a_full[4] a_empty[4] b_full[4] b_empty[4] t_full[2] t_empty[2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(qs_all + QS_FLOATS);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * MAX_STAGES + 4);
@@ -172,92 +163,43 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      // tiles never straddle samples: tile -> (sample n, 128-row block tb); the last block of a sample is partial
-      const int n = tile / tps, tb = tile - n * tps;
-      int rr[4];
-      bool rv[4];
+      const long long row0 = (long long)tile * BM;
+      int rn[4], rr[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        rr[i] = tb * BM + rs + 32 * i;
-        rv[i] = rr[i] < p.rows_out;
-        if (!rv[i]) rr[i] = 0;
+        const long long R = row0 + rs + 32 * i;
+        if (R < p.total_rows) { rn[i] = (int)(R / p.rows_out); rr[i] = (int)(R % p.rows_out); }
+        else { rn[i] = -1; rr[i] = 0; }
       }
       for (int t = 0; t < p.nterms; ++t) {
         const TermDev& tm = p.terms[t];
         const bool has2 = DUAL && tm.w2T != nullptr;
-        const float* src_n = tm.src + (size_t)n * tm.src_rows * tm.src_stride;
-        const bool use_halo = tm.op.idx != nullptr && tm.op.hrows != nullptr;
-        const int H = use_halo ? __ldg(tm.op.hcount + tb) : 0;
-        const int32_t* hr = use_halo ? tm.op.hrows + (size_t)tb * tm.op.hcap : nullptr;
         for (int f0 = 0; f0 < tm.F; f0 += BK) {
           const int f = f0 + l8 * 4;
-          if (use_halo) {
-            // ---- stage the distinct neighbour rows of this tile (this chunk's 128 bytes of each) in shared memory:
-            // all loads are independent, so the whole chunk costs ONE memory round trip instead of one per tap batch
-            asm volatile("bar.sync 2, %0;" ::"n"(TC_PROD_THREADS) : "memory");      // previous chunk's readers are done
-            for (int h0 = 0; h0 < H; h0 += 32 * 8) {
-              float4 hv[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const int h = h0 + rs + 32 * u;
-                hv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (h < H && f < tm.F) hv[u] = ldg4(src_n + (size_t)__ldg(hr + h) * tm.src_stride + f);
-              }
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const int h = h0 + rs + 32 * u;
-                if (h < H) *reinterpret_cast<float4*>(halo + h * 128 + l8 * 16) = hv[u];
-              }
-            }
-            asm volatile("bar.sync 2, %0;" ::"n"(TC_PROD_THREADS) : "memory");      // halo complete
-          }
-          // ---- A chunk: 4 rows per thread, split, store swizzled
+          // ---- A chunk: gather 4 rows per thread, split, store swizzled
           mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
           {
             char* a_hi = a_ring + (size_t)sa * Cfg::A_STAGE_BYTES;
             char* a_lo = a_hi + A_TILE_BYTES;
-            if (use_halo) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int row = rs + 32 * i;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rv[i]) {
-                  const uint2* lp = reinterpret_cast<const uint2*>(tm.op.lidx + (size_t)rr[i] * tm.op.width);
-                  const float4* wp = reinterpret_cast<const float4*>(tm.op.w + (size_t)rr[i] * tm.op.width);
-                  const int nb = tm.op.width >> 2;
-                  for (int b = 0; b < nb; ++b) {
-                    const uint2 li = __ldg(lp + b);
-                    const uint32_t i0 = li.x & 0xffffu, i1 = li.x >> 16, i2 = li.y & 0xffffu, i3 = li.y >> 16;
-                    if (i0 == 0xffffu) break;
-                    const float4 ww = __ldg(wp + b);
-                    fma4(v, ww.x, *reinterpret_cast<const float4*>(halo + i0 * 128 + l8 * 16));
-                    if (i1 != 0xffffu) fma4(v, ww.y, *reinterpret_cast<const float4*>(halo + i1 * 128 + l8 * 16));
-                    if (i2 != 0xffffu) fma4(v, ww.z, *reinterpret_cast<const float4*>(halo + i2 * 128 + l8 * 16));
-                    if (i3 != 0xffffu) fma4(v, ww.w, *reinterpret_cast<const float4*>(halo + i3 * 128 + l8 * 16));
-                  }
+            for (int i = 0; i < 4; i += 2) {
+              const int row_a = rs + 32 * i, row_b = row_a + 32;
+              float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (f < tm.F) {
+                // invalid (beyond-the-end) rows gather sample 0 / row 0 and are zeroed afterwards
+                const float* base_a = tm.src + (size_t)max(rn[i], 0) * tm.src_rows * tm.src_stride + f;
+                const float* base_b = tm.src + (size_t)max(rn[i + 1], 0) * tm.src_rows * tm.src_stride + f;
+                if (tm.op.idx == nullptr) {
+                  va = ldg4(base_a + (size_t)rr[i] * tm.src_stride);
+                  vb = ldg4(base_b + (size_t)rr[i + 1] * tm.src_stride);
+                } else {
+                  ell_gather4_pair(tm.op, rr[i], rr[i + 1], base_a, base_b, (size_t)tm.src_stride, va, vb);
                 }
-                split_store(v, a_hi, a_lo, (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4)));
+                if (rn[i] < 0) va = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rn[i + 1] < 0) vb = make_float4(0.f, 0.f, 0.f, 0.f);
               }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 4; i += 2) {
-                const int row_a = rs + 32 * i, row_b = row_a + 32;
-                float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (f < tm.F) {
-                  const float* base = src_n + f;
-                  if (tm.op.idx == nullptr) {
-                    va = ldg4(base + (size_t)rr[i] * tm.src_stride);
-                    vb = ldg4(base + (size_t)rr[i + 1] * tm.src_stride);
-                  } else {
-                    ell_gather4_pair(tm.op, rr[i], rr[i + 1], base, base, (size_t)tm.src_stride, va, vb,
-                                     (f0 + BK < tm.F) ? pf_mode : 0);
-                  }
-                  if (!rv[i]) va = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (!rv[i + 1]) vb = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                split_store(va, a_hi, a_lo, (uint32_t)(row_a * 128 + ((l8 ^ (row_a & 7)) << 4)));
-                split_store(vb, a_hi, a_lo, (uint32_t)(row_b * 128 + ((l8 ^ (row_b & 7)) << 4)));
-              }
+              split_store(va, a_hi, a_lo, (uint32_t)(row_a * 128 + ((l8 ^ (row_a & 7)) << 4)));
+              split_store(vb, a_hi, a_lo, (uint32_t)(row_b * 128 + ((l8 ^ (row_b & 7)) << 4)));
             }
             fence_proxy_async();             // generic-proxy smem writes -> visible to the tensor-core (async) proxy
             __syncwarp();
@@ -355,16 +297,16 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int buf = it % nbuf;
       const uint32_t use = (uint32_t)(it / nbuf);
-      const int n_t = tile / tps, tb = tile - n_t * tps;
-      const int r = tb * BM + row;
-      const bool valid = r < p.rows_out;
-      const int n = valid ? n_t : -1;
-      const int n_first = n_t;
-      const long long R = (long long)n_t * p.rows_out + r;
+      const long long row0 = (long long)tile * BM;
+      const long long R = row0 + row;
+      const bool valid = R < p.total_rows;
+      const int n = valid ? (int)(R / p.rows_out) : -1, r = valid ? (int)(R % p.rows_out) : 0;
+      const int n_first = (int)(row0 / p.rows_out);
       float* qs = qs_all + (size_t)(it & 1) * (QS_FLOATS / 2);   // always double-buffered (independent of nbuf)
       if (p.nslots > 0) {
         // condition broadcast vectors of this tile: q[s][slot][c] = cond[n_first+s,:] @ Wc_slot[:, c]
-        const int S = 1;                                   // a tile belongs to one sample
+        const long long rlast = min(p.total_rows, row0 + BM) - 1;
+        const int S = (int)(rlast / p.rows_out) - n_first + 1;
         const int total = S * p.nslots * p.ncols;
         for (int o = et; o < total; o += TC_EPI_WARPS * 32) {
           const int c = o % p.ncols;
@@ -470,11 +412,9 @@ int launch_one(const cape_topology* t, const ConvParams& p, cudaStream_t st) {
   const int nbuf = (2 * acc_cols <= 512) ? 2 : 1;
   int tmem_cols = 32;
   while (tmem_cols < acc_cols * nbuf) tmem_cols *= 2;
-  const int tps = (p.rows_out + BM - 1) / BM;                 // tiles per sample
-  const int ntiles = p.N * tps;
+  const int ntiles = (int)((p.total_rows + BM - 1) / BM);
   const int grid = ntiles < t->sm_count ? ntiles : t->sm_count;
-  ellconv_tc_kernel<BN, DUAL><<<grid, TC_THREADS3, Cfg::SMEM_BYTES, st>>>(p, nct, tmem_cols, nbuf, ntiles, tps,
-                                                                          g_tuning[0]);
+  ellconv_tc_kernel<BN, DUAL><<<grid, TC_THREADS3, Cfg::SMEM_BYTES, st>>>(p, nct, tmem_cols, nbuf, ntiles);
   CAPE_CHECK_CUDA(cudaGetLastError());
   count_launches(1);
   return 1;
@@ -483,7 +423,7 @@ int launch_one(const cape_topology* t, const ConvParams& p, cudaStream_t st) {
 }  // namespace
 
 static bool g_tc_enabled = true;
-int g_tuning[8] = {1, 0, 0, 0, 0, 0, 0, 0};   // [0] gather prefetch: 0 off, 1 L2, 2 L1
+int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // experiment knobs (cape_set_tuning); none is read by the shipped kernels
 bool tensor_cores_enabled() { return g_tc_enabled; }
 
 int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaStream_t st) {
@@ -500,9 +440,11 @@ int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cu
   }
   if (kred < 64) return 0;                       // tiny reductions: the SIMT kernel is as good and simpler
   if (p.nslots > 0) {
-    if ((long long)p.nslots * p.ncols > QS_FLOATS / 2) return 0;
+    const long long max_samples = (BM - 1) / p.rows_out + 2;
+    if (max_samples * p.nslots * p.ncols > QS_FLOATS / 2) return 0;
   }
-  if (dual) {                                    // two weight sets per stage: 64-wide sub-tiles keep the ring in shared memory
+  if (dual) {
+    if (p.ncols >= 128) return launch_one<128, true>(t, p, st);
     if (p.ncols >= 64) return launch_one<64, true>(t, p, st);
     return launch_one<32, true>(t, p, st);
   }

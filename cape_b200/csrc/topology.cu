@@ -1,7 +1,6 @@
 // Topology handle: device-resident ELL operators (the fixed SMPL mesh hierarchy) + workspace.
 // Replaces the per-graph tf.SparseTensor construction of lib/models.py:74-79,141-145.
 #include "common.cuh"
-#include <algorithm>
 #include <atomic>
 #include <cstring>
 
@@ -41,9 +40,6 @@ extern "C" void cape_topology_destroy(cape_topology* t) {
     cudaFree(o.idx);
     cudaFree(o.w);
     cudaFree(o.rowsum);
-    cudaFree(o.hrows);
-    cudaFree(o.hcount);
-    cudaFree(o.lidx);
   }
   if (t->workspace) cudaFree(t->workspace);
   delete t;
@@ -82,45 +78,6 @@ extern "C" int cape_topology_add_operator(cape_topology* t, int rows_out, int ro
   CAPE_CHECK_CUDA(cudaMemcpy(o.idx, idx_p.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
   CAPE_CHECK_CUDA(cudaMemcpy(o.w, w_p.data(), n * sizeof(float), cudaMemcpyHostToDevice));
   CAPE_CHECK_CUDA(cudaMemcpy(o.rowsum, rowsum.data(), rows_out * sizeof(float), cudaMemcpyHostToDevice));
-  // halo tables: distinct source rows per 128-row tile + per-tap position in that list
-  {
-    const int ntiles = (rows_out + HALO_TILE - 1) / HALO_TILE;
-    std::vector<std::vector<int32_t>> lists(ntiles);
-    int hmax = 0;
-    for (int tb = 0; tb < ntiles; ++tb) {
-      std::vector<int32_t>& l = lists[tb];
-      const int r1 = std::min(rows_out, (tb + 1) * HALO_TILE);
-      for (int r = tb * HALO_TILE; r < r1; ++r)
-        for (int j = 0; j < width4; ++j)
-          if (idx_p[(size_t)r * width4 + j] >= 0) l.push_back(idx_p[(size_t)r * width4 + j]);
-      std::sort(l.begin(), l.end());
-      l.erase(std::unique(l.begin(), l.end()), l.end());
-      hmax = std::max(hmax, (int)l.size());
-    }
-    if (hmax <= HALO_CAP) {
-      const int hcap = (hmax + 7) / 8 * 8;
-      std::vector<int32_t> hrows((size_t)ntiles * hcap, 0), hcount(ntiles);
-      std::vector<uint16_t> lidx(n, 0xFFFFu);
-      for (int tb = 0; tb < ntiles; ++tb) {
-        const std::vector<int32_t>& l = lists[tb];
-        hcount[tb] = (int32_t)l.size();
-        std::copy(l.begin(), l.end(), hrows.begin() + (size_t)tb * hcap);
-        const int r1 = std::min(rows_out, (tb + 1) * HALO_TILE);
-        for (int r = tb * HALO_TILE; r < r1; ++r)
-          for (int j = 0; j < width4; ++j) {
-            const int32_t id = idx_p[(size_t)r * width4 + j];
-            if (id >= 0) lidx[(size_t)r * width4 + j] = (uint16_t)(std::lower_bound(l.begin(), l.end(), id) - l.begin());
-          }
-      }
-      CAPE_CHECK_CUDA(cudaMalloc(&o.hrows, hrows.size() * sizeof(int32_t)));
-      CAPE_CHECK_CUDA(cudaMalloc(&o.hcount, hcount.size() * sizeof(int32_t)));
-      CAPE_CHECK_CUDA(cudaMalloc(&o.lidx, lidx.size() * sizeof(uint16_t)));
-      CAPE_CHECK_CUDA(cudaMemcpy(o.hrows, hrows.data(), hrows.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-      CAPE_CHECK_CUDA(cudaMemcpy(o.hcount, hcount.data(), hcount.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-      CAPE_CHECK_CUDA(cudaMemcpy(o.lidx, lidx.data(), lidx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-      o.hcap = hcap;
-    }
-  }
   t->ops.push_back(o);
   return (int)t->ops.size() - 1;
 }

@@ -102,8 +102,8 @@ typedef struct {
   float* out2;         /* [N, rows_out, ncols] or NULL */
 } cape_conv_args;
 
-/* Experiment knobs (process-wide): key 0 = neighbour-gather prefetch of the tcgen05 conv kernel (0 off, 1 into L2,
- * 2 into L1).  Returns the previous value, <0 for an unknown key. */
+/* Experiment knobs (process-wide, 8 integer slots read by experimental kernel variants; none is used by the shipped
+ * kernels).  Returns the previous value, <0 for an unknown key. */
 int cape_set_tuning(int key, int value);
 
 /* Process-wide switch for the tcgen05 path of cape_cheb_fwd (default on); returns the previous setting. */
