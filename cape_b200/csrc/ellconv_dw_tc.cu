@@ -154,79 +154,114 @@ __global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __gr
   if (warp < DT_PROD_WARPS) {
     // =========================== producers ===========================
     // Producer roles.  split_roles (wide outputs, ncols >= 256: the G stream is as heavy as the gather): warps 0-3
-    // gather the basis rows A, warps 4-7 stream the gradient rows G, concurrently, each running ahead as far as its
-    // ring allows.  Otherwise (narrow outputs: the gather dominates) all 8 warps do A and then G of each chunk.
+    // produce the basis rows A, warps 4-7 stream the gradient rows G, concurrently, each running ahead as far as its
+    // ring allows.  Otherwise (narrow outputs, one column sub-tile) all 8 warps do A and G of each chunk.
+    // Both streams are software-pipelined: the global loads of the NEXT tile are issued before the current tile is
+    // written to shared memory, so a thread pays one memory round trip per chunk instead of one per stream
+    // (plain-row A terms; an ELL-gathered A chunk is produced synchronously between the two).
     const int mb = lane >> 3, ch = lane & 7;       // 32-element MN block and 16-byte chunk of this lane's float4
     const int na = split_roles ? DT_PROD_WARPS / 2 : DT_PROD_WARPS;       // warps (and row stride) of the A group
     const int ng = split_roles ? DT_PROD_WARPS / 2 : DT_PROD_WARPS;       // same for the G group
     const bool do_a = !split_roles || warp < na;
     const bool do_g = !split_roles || warp >= na;
     const int wa = warp, wg = split_roles ? warp - na : warp;
-    int sa = 0, sg = 0;
-    uint32_t pha = 0, phg = 0;
     const int fa = ftile + lane * 4;
     const int cl = lane * 4;
+    const bool plain_a = p.op.idx == nullptr;
+    constexpr int RPT = 8;                          // rows per thread per tile in split mode (4 in unified mode)
+    const int nra = DT_KCH / na, nrg = DT_KCH / ng; // 4 or 8
+
+    auto load_a_plain = [&](long long rb, float4 (&v)[RPT]) {
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < nra) {
+          const long long R = rb + wa + na * i;
+          if (R < rend && fa < p.F) {
+            const int n_ = (int)(R / p.rows_out), r_ = (int)(R % p.rows_out);
+            v[i] = ldg4(p.src + ((size_t)n_ * p.src_rows + r_) * p.src_stride + fa);
+          }
+        }
+      }
+    };
+    auto gather_a = [&](long long rb, float4 (&v)[RPT]) {
+#pragma unroll
+      for (int i = 0; i < RPT; i += 2) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < nra && fa < p.F) {
+          const long long Ra = rb + wa + na * i, Rb = Ra + na;
+          // rows beyond the end of this split gather row 0 and are zeroed afterwards
+          const long long Qa = Ra < rend ? Ra : 0, Qb = Rb < rend ? Rb : 0;
+          const int n_a = (int)(Qa / p.rows_out), r_a = (int)(Qa % p.rows_out);
+          const int n_b = (int)(Qb / p.rows_out), r_b = (int)(Qb % p.rows_out);
+          ell_gather4_pair(p.op, r_a, r_b, p.src + (size_t)n_a * p.src_rows * p.src_stride + fa,
+                           p.src + (size_t)n_b * p.src_rows * p.src_stride + fa, (size_t)p.src_stride, v[i], v[i + 1]);
+          if (Ra >= rend) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (Rb >= rend) v[i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    auto load_g = [&](long long rb, int cs, float4 (&v)[RPT]) {
+      const int c = cs * BN + cl;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < nrg) {
+          const long long R = rb + wg + ng * i;
+          if (cl < BN && R < rend && c < p.ncols) v[i] = ldg4(p.g + (size_t)R * p.ncols + c);
+        }
+      }
+    };
+
+    int sa = 0, sg = 0;
+    uint32_t pha = 0, phg = 0;
+    float4 acur[RPT], anxt[RPT], gcur[RPT], gnxt[RPT];
+    // G tiles are enumerated as t = kc * nct + cs
+    const long long ngt = nchunks * nct;
+    long long gt = 0;                                // next G tile to be stored by this thread
+    if (do_g && ngt > 0) load_g(rbeg, 0, gcur);
+    if (do_a && plain_a && nchunks > 0) load_a_plain(rbeg, acur);
     for (long long kc = 0; kc < nchunks; ++kc) {
       const long long rb = rbeg + kc * DT_KCH;
       if (do_a) {
+        if (plain_a) { if (kc + 1 < nchunks) load_a_plain(rb + DT_KCH, anxt); }
+        else gather_a(rb, acur);
         mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
         char* a_hi = a_ring + (size_t)sa * Cfg::A_STAGE;
         char* a_lo = a_hi + DT_A_TILE;
-        for (int row_a = wa; row_a < DT_KCH; row_a += 2 * na) {
-          const int row_b = row_a + na;
-          const long long Ra = rb + row_a, Rb = rb + row_b;
-          float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (fa < p.F) {
-            // rows beyond the end of this split gather row 0 and are zeroed afterwards
-            const long long Qa = Ra < rend ? Ra : 0, Qb = Rb < rend ? Rb : 0;
-            const int n_a = (int)(Qa / p.rows_out), r_a = (int)(Qa % p.rows_out);
-            const int n_b = (int)(Qb / p.rows_out), r_b = (int)(Qb % p.rows_out);
-            const float* base_a = p.src + (size_t)n_a * p.src_rows * p.src_stride + fa;
-            const float* base_b = p.src + (size_t)n_b * p.src_rows * p.src_stride + fa;
-            if (p.op.idx == nullptr) {
-              va = ldg4(base_a + (size_t)r_a * p.src_stride);
-              vb = ldg4(base_b + (size_t)r_b * p.src_stride);
-            } else {
-              ell_gather4_pair(p.op, r_a, r_b, base_a, base_b, (size_t)p.src_stride, va, vb);
-            }
-            if (Ra >= rend) va = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (Rb >= rend) vb = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          split_store(va, a_hi, a_lo, mn_off(mb, row_a, ch));
-          split_store(vb, a_hi, a_lo, mn_off(mb, row_b, ch));
-        }
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+          if (i < nra) split_store(acur[i], a_hi, a_lo, mn_off(mb, wa + na * i, ch));
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
         if (++sa == SA) { sa = 0; pha ^= 1; }
+        if (plain_a) {
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) acur[i] = anxt[i];
+        }
       }
       if (do_g) {
-        for (int cs = 0; cs < nct; ++cs) {
+        for (int cs = 0; cs < nct; ++cs, ++gt) {
+          if (gt + 1 < ngt) {                         // issue the next tile's loads before storing this one
+            const long long t1 = gt + 1;
+            load_g(rbeg + (t1 / nct) * DT_KCH, (int)(t1 % nct), gnxt);
+          }
           mbar_wait(bar_gempty + 8 * sg, phg ^ 1);
           char* g_hi = g_ring + (size_t)sg * Cfg::G_STAGE;
           char* g_lo = g_hi + Cfg::G_TILE;
           if (cl < BN) {
-            const int c = cs * BN + cl;
-            for (int r0 = wg; r0 < DT_KCH; r0 += 4 * ng) {            // 4 independent loads in flight per pass
-              float4 v[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int row = r0 + i * ng;
-                const long long R = rb + row;
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < DT_KCH && R < rend && c < p.ncols) v[i] = ldg4(p.g + (size_t)R * p.ncols + c);
-              }
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int row = r0 + i * ng;
-                if (row < DT_KCH) split_store(v[i], g_hi, g_lo, mn_off(mb, row, ch));
-              }
-            }
+            for (int i = 0; i < RPT; ++i)
+              if (i < nrg) split_store(gcur[i], g_hi, g_lo, mn_off(mb, wg + ng * i, ch));
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_gfull + 8 * sg);
           if (++sg == SG) { sg = 0; phg ^= 1; }
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) gcur[i] = gnxt[i];
         }
       }
     }

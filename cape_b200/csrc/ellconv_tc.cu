@@ -176,6 +176,21 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
         const bool has2 = DUAL && tm.w2T != nullptr;
         for (int f0 = 0; f0 < tm.F; f0 += BK) {
           const int f = f0 + l8 * 4;
+          // ---- issue the weight loads of the first column sub-tile now: they fly while the basis chunk is gathered
+          float4 bw[BN / 32], bw2[DUAL ? BN / 32 : 1];
+          auto load_b = [&](int cs) {
+#pragma unroll
+            for (int i = 0; i < BN / 32; ++i) {
+              const int c = cs * BN + rs + 32 * i;
+              bw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (c < p.ncols && f < tm.F) bw[i] = ldg4(tm.wT + (size_t)c * tm.wT_stride + f);
+              if (DUAL) {
+                bw2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has2 && c < p.ncols && f < tm.F) bw2[i] = ldg4(tm.w2T + (size_t)c * tm.w2T_stride + f);
+              }
+            }
+          };
+          load_b(0);
           // ---- A chunk: gather 4 rows per thread, split, store swizzled
           mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
           {
@@ -208,23 +223,17 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
           }
           // ---- B chunks: one [BN x 32] K-major weight tile (hi/lo) per column sub-tile
           for (int cs = 0; cs < nct; ++cs) {
+            if (cs > 0) load_b(cs);
             mbar_wait(bar_bempty + 8 * sb, phb ^ 1);
             char* b_hi = b_ring + (size_t)sb * Cfg::B_STAGE_BYTES;
             char* b_lo = b_hi + Cfg::B_TILE_BYTES;
 #pragma unroll
             for (int i = 0; i < BN / 32; ++i) {
               const int cl = rs + 32 * i;
-              const int c = cs * BN + cl;
-              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (c < p.ncols && f < tm.F) v = ldg4(tm.wT + (size_t)c * tm.wT_stride + f);
               const uint32_t off = (uint32_t)(cl * 128 + ((l8 ^ (cl & 7)) << 4));
-              split_store(v, b_hi, b_lo, off);
+              split_store(bw[i], b_hi, b_lo, off);
               if (DUAL) {
-                if (has2) {
-                  float4 v2 = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (c < p.ncols && f < tm.F) v2 = ldg4(tm.w2T + (size_t)c * tm.w2T_stride + f);
-                  split_store(v2, b_lo + Cfg::B_TILE_BYTES, b_lo + 2 * Cfg::B_TILE_BYTES, off);
-                }
+                if (has2) split_store(bw2[i], b_lo + Cfg::B_TILE_BYTES, b_lo + 2 * Cfg::B_TILE_BYTES, off);
               }
             }
             fence_proxy_async();
