@@ -100,23 +100,26 @@ struct DwTcParams {
   const float* g;
   float* out;          // dw (nsplit == 1) or workspace [nsplit, F, ncols]
   long long out_rs;
-  int nsplit, accumulate;
+  int nsplit, accumulate, ovec;
 };
 
-template <int BN>
+// OCC = CTAs per SM the configuration is sized for: narrow outputs (ncols <= 128) run two CTAs per SM (twice the warps
+// to hide the load latency; 2 x ~97 KB shared memory, <= 112 registers, <= 256 TMEM columns each); wide outputs
+// (ncols >= 256) need the TMEM and deeper rings of a single CTA (measured: 1.7x slower with two).
+template <int BN, int OCC>
 struct DtCfg {
   static constexpr int G_TILE = (BN / 32) * 4096;             // BN columns x 32 rows, hi or lo
   static constexpr int A_STAGE = 2 * DT_A_TILE;
   static constexpr int G_STAGE = 2 * G_TILE;
-  static constexpr int A_STAGES = 3;
-  static constexpr int G_STAGES = (3 * G_STAGE <= 96 * 1024) ? 3 : 2;
+  static constexpr int A_STAGES = OCC == 2 ? 2 : 3;
+  static constexpr int G_STAGES = OCC == 2 ? 2 : ((3 * G_STAGE <= 96 * 1024) ? 3 : 2);
   static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_STAGE + G_STAGES * G_STAGE + 256;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __grid_constant__ DwTcParams p, int nct,
+template <int BN, int OCC>
+__global__ void __launch_bounds__(DT_THREADS, OCC) ellconv_dw_tc_kernel(const __grid_constant__ DwTcParams p, int nct,
                                                                       int tmem_cols, int split_roles) {
-  using Cfg = DtCfg<BN>;
+  using Cfg = DtCfg<BN, OCC>;
   constexpr int SA = Cfg::A_STAGES, SG = Cfg::G_STAGES;
   extern __shared__ uint8_t smem_raw[];
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -154,114 +157,79 @@ __global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __gr
   if (warp < DT_PROD_WARPS) {
     // =========================== producers ===========================
     // Producer roles.  split_roles (wide outputs, ncols >= 256: the G stream is as heavy as the gather): warps 0-3
-    // produce the basis rows A, warps 4-7 stream the gradient rows G, concurrently, each running ahead as far as its
-    // ring allows.  Otherwise (narrow outputs, one column sub-tile) all 8 warps do A and G of each chunk.
-    // Both streams are software-pipelined: the global loads of the NEXT tile are issued before the current tile is
-    // written to shared memory, so a thread pays one memory round trip per chunk instead of one per stream
-    // (plain-row A terms; an ELL-gathered A chunk is produced synchronously between the two).
+    // gather the basis rows A, warps 4-7 stream the gradient rows G, concurrently, each running ahead as far as its
+    // ring allows.  Otherwise (narrow outputs: the gather dominates) all 8 warps do A and then G of each chunk.
     const int mb = lane >> 3, ch = lane & 7;       // 32-element MN block and 16-byte chunk of this lane's float4
     const int na = split_roles ? DT_PROD_WARPS / 2 : DT_PROD_WARPS;       // warps (and row stride) of the A group
     const int ng = split_roles ? DT_PROD_WARPS / 2 : DT_PROD_WARPS;       // same for the G group
     const bool do_a = !split_roles || warp < na;
     const bool do_g = !split_roles || warp >= na;
     const int wa = warp, wg = split_roles ? warp - na : warp;
-    const int fa = ftile + lane * 4;
-    const int cl = lane * 4;
-    const bool plain_a = p.op.idx == nullptr;
-    constexpr int RPT = 8;                          // rows per thread per tile in split mode (4 in unified mode)
-    const int nra = DT_KCH / na, nrg = DT_KCH / ng; // 4 or 8
-
-    auto load_a_plain = [&](long long rb, float4 (&v)[RPT]) {
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < nra) {
-          const long long R = rb + wa + na * i;
-          if (R < rend && fa < p.F) {
-            const int n_ = (int)(R / p.rows_out), r_ = (int)(R % p.rows_out);
-            v[i] = ldg4(p.src + ((size_t)n_ * p.src_rows + r_) * p.src_stride + fa);
-          }
-        }
-      }
-    };
-    auto gather_a = [&](long long rb, float4 (&v)[RPT]) {
-#pragma unroll
-      for (int i = 0; i < RPT; i += 2) {
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        v[i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < nra && fa < p.F) {
-          const long long Ra = rb + wa + na * i, Rb = Ra + na;
-          // rows beyond the end of this split gather row 0 and are zeroed afterwards
-          const long long Qa = Ra < rend ? Ra : 0, Qb = Rb < rend ? Rb : 0;
-          const int n_a = (int)(Qa / p.rows_out), r_a = (int)(Qa % p.rows_out);
-          const int n_b = (int)(Qb / p.rows_out), r_b = (int)(Qb % p.rows_out);
-          ell_gather4_pair(p.op, r_a, r_b, p.src + (size_t)n_a * p.src_rows * p.src_stride + fa,
-                           p.src + (size_t)n_b * p.src_rows * p.src_stride + fa, (size_t)p.src_stride, v[i], v[i + 1]);
-          if (Ra >= rend) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (Rb >= rend) v[i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    };
-    auto load_g = [&](long long rb, int cs, float4 (&v)[RPT]) {
-      const int c = cs * BN + cl;
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < nrg) {
-          const long long R = rb + wg + ng * i;
-          if (cl < BN && R < rend && c < p.ncols) v[i] = ldg4(p.g + (size_t)R * p.ncols + c);
-        }
-      }
-    };
-
     int sa = 0, sg = 0;
     uint32_t pha = 0, phg = 0;
-    float4 acur[RPT], anxt[RPT], gcur[RPT], gnxt[RPT];
-    // G tiles are enumerated as t = kc * nct + cs
-    const long long ngt = nchunks * nct;
-    long long gt = 0;                                // next G tile to be stored by this thread
-    if (do_g && ngt > 0) load_g(rbeg, 0, gcur);
-    if (do_a && plain_a && nchunks > 0) load_a_plain(rbeg, acur);
+    const int fa = ftile + lane * 4;
+    const int cl = lane * 4;
     for (long long kc = 0; kc < nchunks; ++kc) {
       const long long rb = rbeg + kc * DT_KCH;
       if (do_a) {
-        if (plain_a) { if (kc + 1 < nchunks) load_a_plain(rb + DT_KCH, anxt); }
-        else gather_a(rb, acur);
         mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
         char* a_hi = a_ring + (size_t)sa * Cfg::A_STAGE;
         char* a_lo = a_hi + DT_A_TILE;
-#pragma unroll
-        for (int i = 0; i < RPT; ++i)
-          if (i < nra) split_store(acur[i], a_hi, a_lo, mn_off(mb, wa + na * i, ch));
+        for (int row_a = wa; row_a < DT_KCH; row_a += 2 * na) {
+          const int row_b = row_a + na;
+          const long long Ra = rb + row_a, Rb = rb + row_b;
+          float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (fa < p.F) {
+            // rows beyond the end of this split gather row 0 and are zeroed afterwards
+            const long long Qa = Ra < rend ? Ra : 0, Qb = Rb < rend ? Rb : 0;
+            const int n_a = (int)(Qa / p.rows_out), r_a = (int)(Qa % p.rows_out);
+            const int n_b = (int)(Qb / p.rows_out), r_b = (int)(Qb % p.rows_out);
+            const float* base_a = p.src + (size_t)n_a * p.src_rows * p.src_stride + fa;
+            const float* base_b = p.src + (size_t)n_b * p.src_rows * p.src_stride + fa;
+            if (p.op.idx == nullptr) {
+              va = ldg4(base_a + (size_t)r_a * p.src_stride);
+              vb = ldg4(base_b + (size_t)r_b * p.src_stride);
+            } else {
+              ell_gather4_pair(p.op, r_a, r_b, base_a, base_b, (size_t)p.src_stride, va, vb);
+            }
+            if (Ra >= rend) va = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (Rb >= rend) vb = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          split_store(va, a_hi, a_lo, mn_off(mb, row_a, ch));
+          split_store(vb, a_hi, a_lo, mn_off(mb, row_b, ch));
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
         if (++sa == SA) { sa = 0; pha ^= 1; }
-        if (plain_a) {
-#pragma unroll
-          for (int i = 0; i < RPT; ++i) acur[i] = anxt[i];
-        }
       }
       if (do_g) {
-        for (int cs = 0; cs < nct; ++cs, ++gt) {
-          if (gt + 1 < ngt) {                         // issue the next tile's loads before storing this one
-            const long long t1 = gt + 1;
-            load_g(rbeg + (t1 / nct) * DT_KCH, (int)(t1 % nct), gnxt);
-          }
+        for (int cs = 0; cs < nct; ++cs) {
           mbar_wait(bar_gempty + 8 * sg, phg ^ 1);
           char* g_hi = g_ring + (size_t)sg * Cfg::G_STAGE;
           char* g_lo = g_hi + Cfg::G_TILE;
           if (cl < BN) {
+            const int c = cs * BN + cl;
+            for (int r0 = wg; r0 < DT_KCH; r0 += 4 * ng) {            // 4 independent loads in flight per pass
+              float4 v[4];
 #pragma unroll
-            for (int i = 0; i < RPT; ++i)
-              if (i < nrg) split_store(gcur[i], g_hi, g_lo, mn_off(mb, wg + ng * i, ch));
+              for (int i = 0; i < 4; ++i) {
+                const int row = r0 + i * ng;
+                const long long R = rb + row;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < DT_KCH && R < rend && c < p.ncols) v[i] = ldg4(p.g + (size_t)R * p.ncols + c);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int row = r0 + i * ng;
+                if (row < DT_KCH) split_store(v[i], g_hi, g_lo, mn_off(mb, row, ch));
+              }
+            }
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_gfull + 8 * sg);
           if (++sg == SG) { sg = 0; phg ^= 1; }
-#pragma unroll
-          for (int i = 0; i < RPT; ++i) gcur[i] = gnxt[i];
         }
       }
     }
@@ -287,6 +255,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __gr
       if (p.nsplit == 1 && p.accumulate) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) orow[c0 + j] += v[j];
+      } else if (p.ovec) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) orow[c0 + j] = v[j];
@@ -336,12 +308,12 @@ __global__ void __launch_bounds__(DT_THREADS, 1) ellconv_dw_tc_kernel(const __gr
   }
 }
 
-template <int BN>
+template <int BN, int OCC>
 int launch_dw(const DwTcParams& p, int ftiles, cudaStream_t st) {
-  using Cfg = DtCfg<BN>;
+  using Cfg = DtCfg<BN, OCC>;
   static bool configured = false;
   if (!configured) {
-    CAPE_CHECK_CUDA(cudaFuncSetAttribute(ellconv_dw_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CAPE_CHECK_CUDA(cudaFuncSetAttribute(ellconv_dw_tc_kernel<BN, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES));
     configured = true;
   }
@@ -349,7 +321,7 @@ int launch_dw(const DwTcParams& p, int ftiles, cudaStream_t st) {
   int cols = nct * BN, tmem_cols = 32;
   while (tmem_cols < cols) tmem_cols *= 2;
   dim3 grid(ftiles, p.nsplit);
-  ellconv_dw_tc_kernel<BN><<<grid, DT_THREADS, Cfg::SMEM_BYTES, st>>>(p, nct, tmem_cols, nct >= 2 ? 1 : 0);
+  ellconv_dw_tc_kernel<BN, OCC><<<grid, DT_THREADS, Cfg::SMEM_BYTES, st>>>(p, nct, tmem_cols, p.ncols >= 256 ? 1 : 0);
   CAPE_CHECK_CUDA(cudaGetLastError());
   count_launches(1);
   return 1;
@@ -370,7 +342,7 @@ int launch_ellconv_dw_tc(const cape_topology* t, const cape_dw_args* a, const Op
   if (p.total_rows < 4096) return 0;
   p.src = a->src; p.op = op; p.g = a->g;
   const int ftiles = (a->F + 127) / 128;
-  long long nsplit = (2LL * t->sm_count + ftiles - 1) / ftiles;
+  long long nsplit = ((a->ncols >= 256 ? 2LL : 4LL) * t->sm_count + ftiles - 1) / ftiles;
   const long long max_by_rows = (p.total_rows + 511) / 512;
   if (nsplit > max_by_rows) nsplit = max_by_rows;
   const long long per = (long long)a->F * a->ncols * (long long)sizeof(float);
@@ -382,10 +354,11 @@ int launch_ellconv_dw_tc(const cape_topology* t, const cape_dw_args* a, const Op
   p.rows_per_split = rps; p.nsplit = (int)nsplit; p.accumulate = a->accumulate;
   if (nsplit == 1) { p.out = a->dw; p.out_rs = a->dw_stride; }
   else { p.out = (float*)t->workspace; p.out_rs = a->ncols; }
+  p.ovec = (p.out_rs % 4 == 0) && aligned16(p.out);
   *nsplit_out = (int)nsplit;
-  if (a->ncols >= 128) return launch_dw<128>(p, ftiles, st);
-  if (a->ncols >= 64) return launch_dw<64>(p, ftiles, st);
-  return launch_dw<32>(p, ftiles, st);
+  if (a->ncols >= 256) return launch_dw<128, 1>(p, ftiles, st);
+  if (a->ncols >= 64) return launch_dw<64, 2>(p, ftiles, st);    // 64-wide sub-tiles keep the G ring small
+  return launch_dw<32, 2>(p, ftiles, st);
 }
 
 }  // namespace cape
