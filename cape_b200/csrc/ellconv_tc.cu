@@ -429,6 +429,302 @@ int launch_one(const cape_topology* t, const ConvParams& p, cudaStream_t st) {
   return 1;
 }
 
+constexpr int QS2_FLOATS = 2048;
+
+template <int BN, bool DUAL>
+struct Tc2Cfg {
+  static constexpr int B_TILE_BYTES = BN * 128;                       // one hi or lo tile of BN weight rows x 32 k
+  static constexpr int A_STAGE_BYTES = 2 * A_TILE_BYTES;              // hi + lo
+  static constexpr int B_STAGE_BYTES = (DUAL ? 4 : 2) * B_TILE_BYTES;  // hi + lo (+ second weight set)
+  static constexpr int A_STAGES = 2;
+  static constexpr int B_STAGES = 2;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES +
+                                    QS2_FLOATS * 4 + 2 * BM * 4 + 256;
+};
+
+// Variant for NARROW outputs (accumulator <= 256 TMEM columns): one 128-row tile per CTA, 9 warps (the producer
+// warps double as the epilogue), <= 112 registers and ~106 KB of shared memory, so that TWO CTAs share an SM: twice
+// the warps hide the latency of the neighbour gather, and one CTA's epilogue overlaps the other's main loop.
+template <int BN, bool DUAL>
+__global__ void __launch_bounds__(TC_THREADS, 2) ellconv_tc2_kernel(const __grid_constant__ ConvParams p, int nct,
+                                                                   int tmem_cols) {
+  using Cfg = Tc2Cfg<BN, DUAL>;
+  constexpr int SA = Cfg::A_STAGES, SB = Cfg::B_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: required by SWIZZLE_128B operand tiles
+  char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  char* a_ring = smem;
+  char* b_ring = smem + SA * Cfg::A_STAGE_BYTES;
+  float* qs = reinterpret_cast<float*>(b_ring + SB * Cfg::B_STAGE_BYTES);
+  int* s_n = reinterpret_cast<int*>(qs + QS2_FLOATS);
+  int* s_r = s_n + BM;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_r + BM);   // a_full[4] a_empty[4] b_full[4] b_empty[4] accum
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * MAX_STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long row0 = (long long)blockIdx.x * BM;
+  const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + MAX_STAGES);
+  const uint32_t bar_bfull = smem_u32(bars + 2 * MAX_STAGES), bar_bempty = smem_u32(bars + 3 * MAX_STAGES);
+  const uint32_t bar_accum = smem_u32(bars + 4 * MAX_STAGES);
+
+  if (tid < BM) {
+    const long long R = row0 + tid;
+    if (R < p.total_rows) { s_n[tid] = (int)(R / p.rows_out); s_r[tid] = (int)(R % p.rows_out); }
+    else { s_n[tid] = -1; s_r[tid] = 0; }
+  }
+  if (warp == TC_PROD_WARPS) {
+    if (lane == 0) {
+      for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, TC_PROD_WARPS); mbar_init(bar_aempty + 8 * s, 1); }
+      for (int s = 0; s < SB; ++s) { mbar_init(bar_bfull + 8 * s, TC_PROD_WARPS); mbar_init(bar_bempty + 8 * s, 1); }
+      mbar_init(bar_accum, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc1_col = (uint32_t)(nct * BN);            // second accumulator starts after the first
+
+  if (warp < TC_PROD_WARPS) {
+    // =========================== producers ===========================
+    const int l8 = tid & 7, rs = tid >> 3;       // 8 lanes per 128-byte row, 32 row slots
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    for (int t = 0; t < p.nterms; ++t) {
+      const TermDev& tm = p.terms[t];
+      const bool has2 = DUAL && tm.w2T != nullptr;
+      for (int f0 = 0; f0 < tm.F; f0 += BK) {
+        const int f = f0 + l8 * 4;
+        // ---- A chunk: gather 4 rows per thread, split, store swizzled
+        mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
+        {
+          char* a_hi = a_ring + (size_t)sa * Cfg::A_STAGE_BYTES;
+          char* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+          for (int i = 0; i < 4; i += 2) {
+            const int row_a = rs + 32 * i, row_b = row_a + 32;
+            const int n_a = s_n[row_a], n_b = s_n[row_b];
+            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (f < tm.F) {
+              const float* base_a = tm.src + (size_t)max(n_a, 0) * tm.src_rows * tm.src_stride + f;
+              const float* base_b = tm.src + (size_t)max(n_b, 0) * tm.src_rows * tm.src_stride + f;
+              if (tm.op.idx == nullptr) {
+                va = ldg4(base_a + (size_t)s_r[row_a] * tm.src_stride);
+                vb = ldg4(base_b + (size_t)s_r[row_b] * tm.src_stride);
+              } else {
+                ell_gather4_pair(tm.op, s_r[row_a], s_r[row_b], base_a, base_b, (size_t)tm.src_stride, va, vb);
+              }
+              if (n_a < 0) va = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (n_b < 0) vb = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            split_store(va, a_hi, a_lo, (uint32_t)(row_a * 128 + ((l8 ^ (row_a & 7)) << 4)));
+            split_store(vb, a_hi, a_lo, (uint32_t)(row_b * 128 + ((l8 ^ (row_b & 7)) << 4)));
+          }
+          fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
+          if (++sa == SA) { sa = 0; pha ^= 1; }
+        }
+        // ---- B chunks: one [BN x 32] K-major weight tile (hi/lo) per column sub-tile
+        for (int cs = 0; cs < nct; ++cs) {
+          mbar_wait(bar_bempty + 8 * sb, phb ^ 1);
+          char* b_hi = b_ring + (size_t)sb * Cfg::B_STAGE_BYTES;
+          char* b_lo = b_hi + Cfg::B_TILE_BYTES;
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i) {
+            const int cl = rs + 32 * i;
+            const int c = cs * BN + cl;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < p.ncols && f < tm.F) v = ldg4(tm.wT + (size_t)c * tm.wT_stride + f);
+            const uint32_t off = (uint32_t)(cl * 128 + ((l8 ^ (cl & 7)) << 4));
+            split_store(v, b_hi, b_lo, off);
+            if (DUAL) {
+              if (has2) {
+                float4 v2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < p.ncols && f < tm.F) v2 = ldg4(tm.w2T + (size_t)c * tm.w2T_stride + f);
+                split_store(v2, b_lo + Cfg::B_TILE_BYTES, b_lo + 2 * Cfg::B_TILE_BYTES, off);
+              }
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_bfull + 8 * sb);
+          if (++sb == SB) { sb = 0; phb ^= 1; }
+        }
+      }
+    }
+
+    // ---- condition broadcast vectors: q[s][slot][c] = cond[n0+s,:] @ Wc_slot[:, c]
+    const int n_first = s_n[0];
+    if (p.nslots > 0) {
+      int n_last = n_first;
+      for (int i = BM - 1; i > 0; --i)
+        if (s_n[i] >= 0) { n_last = s_n[i]; break; }
+      const int S = n_last - n_first + 1;
+      const int total = S * p.nslots * p.ncols;
+      for (int o = tid; o < total; o += TC_PROD_THREADS) {
+        const int c = o % p.ncols;
+        const int slot = (o / p.ncols) % p.nslots;
+        const int s = o / (p.ncols * p.nslots);
+        const float* y = p.cond + (size_t)(n_first + s) * p.C;
+        const float* wc = p.slot_w[slot] + c;
+        const int ws = p.slot_acc[slot] ? p.terms[p.slot_term[slot]].w2_stride : p.terms[p.slot_term[slot]].w_stride;
+        float q = 0.f;
+        for (int j = 0; j < p.C; ++j) q = fmaf(__ldg(y + j), __ldg(wc + (size_t)j * ws), q);
+        qs[o] = q;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
+    }
+
+    // =========================== epilogue ===========================
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
+    const int quad = warp & 3, half = warp >> 2;          // TMEM lane quadrant of this warp; column half
+    const int row = quad * 32 + lane;
+    const int n = s_n[row], r = s_r[row];
+    const int cpw = p.ncols >> 1;                         // columns per warp (ncols is a multiple of 32)
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const size_t orow = (size_t)(row0 + row) * p.ncols;
+#pragma unroll 1
+    for (int g = 0; g < cpw / 16; ++g) {
+      const int c0 = half * cpw + g * 16;                 // first of 16 output columns
+      float v0[16], v1[16];
+      tmem_ld16(taddr_row + (uint32_t)c0, v0);             // warp-collective: executed by every lane
+      if (DUAL) tmem_ld16(taddr_row + acc1_col + (uint32_t)c0, v1);
+      if (n < 0) continue;
+      for (int slot = 0; slot < p.nslots; ++slot) {
+        const TermDev& tm = p.terms[p.slot_term[slot]];
+        const float coef = tm.op.rowsum ? __ldg(tm.op.rowsum + r) : 1.f;
+        const float* q = qs + ((size_t)(n - n_first) * p.nslots + slot) * p.ncols + c0;
+        if (p.slot_acc[slot] == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v0[j] = fmaf(coef, q[j], v0[j]);
+        } else if (DUAL) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v1[j] = fmaf(coef, q[j], v1[j]);
+        }
+      }
+      float o1[16], o2[16];
+      bool write2 = false;
+      if (p.epilogue == CAPE_EPI_LINEAR) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v = v0[j];
+          if (p.bias != nullptr) v += __ldg(p.bias + (p.bias_per_row ? (size_t)r * p.ncols : 0) + c0 + j);
+          if (p.act == CAPE_ACT_LEAKY) v = v > 0.f ? v : p.alpha * v;
+          else if (p.act == CAPE_ACT_RELU) v = fmaxf(v, 0.f);
+          o1[j] = v;
+        }
+      } else if (p.epilogue == CAPE_EPI_AFFINE) {
+        write2 = p.out2 != nullptr;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float rg = fmaxf(v0[j], 0.f);
+          o1[j] = (DUAL ? v1[j] : 0.f) + rg;
+          o2[j] = rg;
+        }
+      } else {
+        float ax[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 a4 = ldg4(p.aux + orow + c0 + j);
+          ax[j] = a4.x; ax[j + 1] = a4.y; ax[j + 2] = a4.z; ax[j + 3] = a4.w;
+        }
+        if (p.epilogue == CAPE_EPI_SLOPE) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o1[j] = v0[j] * (ax[j] > 0.f ? 1.f : p.alpha);
+        } else {
+          write2 = p.out2 != nullptr;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { o1[j] = v0[j]; o2[j] = ax[j] > 0.f ? v0[j] : 0.f; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        *reinterpret_cast<float4*>(p.out + orow + c0 + j) = make_float4(o1[j], o1[j + 1], o1[j + 2], o1[j + 3]);
+        if (write2)
+          *reinterpret_cast<float4*>(p.out2 + orow + c0 + j) = make_float4(o2[j], o2[j + 1], o2[j + 2], o2[j + 3]);
+      }
+    }
+    tc_fence_before();
+  } else {
+    // =========================== MMA issuer (one elected lane) ===========================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N=BN, M=128
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0, acc0_on = 0, acc1_on = 0;
+      for (int t = 0; t < p.nterms; ++t) {
+        const bool has2 = DUAL && p.terms[t].w2T != nullptr;
+        for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+          mbar_wait(bar_afull + 8 * sa, pha);
+          const uint32_t aaddr = smem_u32(a_ring + (size_t)sa * Cfg::A_STAGE_BYTES);
+          const uint64_t a_hi = make_desc(aaddr), a_lo = make_desc(aaddr + A_TILE_BYTES);
+          for (int cs = 0; cs < nct; ++cs) {
+            mbar_wait(bar_bfull + 8 * sb, phb);
+            tc_fence_after();
+            const uint32_t baddr = smem_u32(b_ring + (size_t)sb * Cfg::B_STAGE_BYTES);
+            const uint64_t b_hi = make_desc(baddr), b_lo = make_desc(baddr + Cfg::B_TILE_BYTES);
+            const uint64_t b2_hi = make_desc(baddr + 2 * Cfg::B_TILE_BYTES), b2_lo = make_desc(baddr + 3 * Cfg::B_TILE_BYTES);
+            const uint32_t d0 = tmem_base + (uint32_t)(cs * BN), d1 = d0 + acc1_col;
+#pragma unroll
+            for (int ks = 0; ks < BK / 8; ++ks) {
+              const uint64_t adv = (uint64_t)(ks * 2);    // +32 bytes along K inside the 128-byte swizzle row
+              // the very first MMA into a sub-tile's TMEM columns overwrites (TMEM is not zero-initialised)
+              umma_tf32(d0, a_hi + adv, b_hi + adv, idesc, ks == 0 ? acc0_on : 1u);
+              umma_tf32(d0, a_lo + adv, b_hi + adv, idesc, 1);
+              umma_tf32(d0, a_hi + adv, b_lo + adv, idesc, 1);
+              if (has2) {
+                umma_tf32(d1, a_hi + adv, b2_hi + adv, idesc, ks == 0 ? acc1_on : 1u);
+                umma_tf32(d1, a_lo + adv, b2_hi + adv, idesc, 1);
+                umma_tf32(d1, a_hi + adv, b2_lo + adv, idesc, 1);
+              }
+            }
+            umma_commit(bar_bempty + 8 * sb);              // weight stage reusable once these MMAs have read it
+            if (++sb == SB) { sb = 0; phb ^= 1; }
+          }
+          umma_commit(bar_aempty + 8 * sa);                // basis stage reusable
+          if (++sa == SA) { sa = 0; pha ^= 1; }
+          acc0_on = 1;
+          if (has2) acc1_on = 1;
+        }
+      }
+      umma_commit(bar_accum);                              // accumulators complete
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == TC_PROD_WARPS) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols) : "memory");
+  }
+}
+
+template <int BN, bool DUAL>
+int launch_two(const ConvParams& p, cudaStream_t st) {
+  using Cfg = Tc2Cfg<BN, DUAL>;
+  static bool configured = false;
+  if (!configured) {
+    CAPE_CHECK_CUDA(cudaFuncSetAttribute(ellconv_tc2_kernel<BN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int nct = (p.ncols + BN - 1) / BN;
+  int cols = (DUAL ? 2 : 1) * nct * BN, tmem_cols = 32;
+  while (tmem_cols < cols) tmem_cols *= 2;
+  dim3 grid((unsigned)((p.total_rows + BM - 1) / BM), 1);
+  ellconv_tc2_kernel<BN, DUAL><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, nct, tmem_cols);
+  CAPE_CHECK_CUDA(cudaGetLastError());
+  count_launches(1);
+  return 1;
+}
+
 }  // namespace
 
 static bool g_tc_enabled = true;
@@ -451,6 +747,12 @@ int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cu
   if (p.nslots > 0) {
     const long long max_samples = (BM - 1) / p.rows_out + 2;
     if (max_samples * p.nslots * p.ncols > QS_FLOATS / 2) return 0;
+  }
+  // narrow outputs: accumulator <= 256 TMEM columns -> the two-CTAs-per-SM variant
+  if ((dual ? 2 : 1) * p.ncols <= 256 && (!p.nslots || (long long)((BM - 1) / p.rows_out + 2) * p.nslots * p.ncols <= QS2_FLOATS)) {
+    if (dual) return launch_two<32, true>(p, st);      // 32-wide sub-tiles: two weight sets per stage must stay small
+    if (p.ncols >= 64) return launch_two<64, false>(p, st);
+    return launch_two<32, false>(p, st);
   }
   if (dual) {
     if (p.ncols >= 128) return launch_one<128, true>(t, p, st);
