@@ -748,8 +748,8 @@ int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cu
     const long long max_samples = (BM - 1) / p.rows_out + 2;
     if (max_samples * p.nslots * p.ncols > QS_FLOATS / 2) return 0;
   }
-  // narrow outputs: accumulator <= 256 TMEM columns -> the two-CTAs-per-SM variant
-  if ((dual ? 2 : 1) * p.ncols <= 256 && (!p.nslots || (long long)((BM - 1) / p.rows_out + 2) * p.nslots * p.ncols <= QS2_FLOATS)) {
+  // narrow outputs: accumulator <= 128 TMEM columns -> the two-CTAs-per-SM variant (wider ones measured slower)
+  if ((dual ? 2 : 1) * p.ncols <= 128 && (!p.nslots || (long long)((BM - 1) / p.rows_out + 2) * p.nslots * p.ncols <= QS2_FLOATS)) {
     if (dual) return launch_two<32, true>(p, st);      // 32-wide sub-tiles: two weight sets per stage must stay small
     if (p.ncols >= 64) return launch_two<64, false>(p, st);
     return launch_two<32, false>(p, st);
