@@ -105,6 +105,13 @@ class ChebLayer:
         self.Wt = torch.empty(Fout, K, F, device=dev)
         if self.affine:
             self.Wat = torch.empty(Fout, F, device=dev)
+        # Weight gradient "on the narrow side": dW_k = (op_k x)^T G = x^T (op_k^T G).  When the output is narrower than
+        # the input and the site does not pool, apply the (transposed) operators to G with the cheap resample kernel
+        # and contract ONCE over the input rows with plain (un-gathered) operands: all K terms in one pass over x.
+        self.dw_gside = (not site.ref_pool) and F >= Fout and K * Fout <= 512 and K > 1 and F % 4 == 0 and Fout % 32 == 0
+        if self.dw_gside:
+            self.Hg = torch.empty(maxN, site.rows_in, K * Fout, device=dev)
+            self.Ha = torch.empty(maxN, site.rows_in, Fout, device=dev) if (self.affine and site.opsT[0] != -1) else None
         # colsum targets: [bias?] + K condition sums (+1 for the affine branch)
         self.cs_ops = []
         if bias is not None and not bias_per_row:
@@ -168,7 +175,21 @@ class ChebLayer:
         tp, s, F, C, K, Fout = self.tp, self.site, self.F, self.C, self.K, self.Fout
         N = g.shape[0]
         sx = x.shape[2]
-        if want_dw:
+        if want_dw and self.dw_gside:
+            nl = 1 + (1 if self.affine else 0)
+            tg = (self.name + ":dW", self.alg_bytes(N, "dW") / nl)
+            H = self.Hg[:N]
+            for k in range(K):
+                E.resample(tp, s.opsT[k], g, H[:, :, k * Fout:], N, s.rows_in, s.rows_out, Fout, x_stride=Fout,
+                           y_stride=K * Fout)
+            cheb_dw(tp, N, s.rows_in, K * Fout, x, -1, F, s.rows_in, sx, H, self.gW3, K * Fout, tag=tg)
+            if self.affine:
+                Ha = g_aff
+                if self.Ha is not None:
+                    Ha = self.Ha[:N]
+                    E.resample(tp, s.opsT[0], g_aff, Ha, N, s.rows_in, s.rows_out, Fout)
+                cheb_dw(tp, N, s.rows_in, Fout, x, -1, F, s.rows_in, sx, Ha, self.gWa2, Fout, tag=tg)
+        elif want_dw:
             nl = K + (1 if self.affine else 0)
             tg = (self.name + ":dW", self.alg_bytes(N, "dW") / nl)
             for k in range(K):
