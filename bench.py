@@ -63,8 +63,9 @@ def cpu_port_rate(n_sample, steps, warmup):
     from cape_b200.params import init_params, param_specs
     from cape_b200.synthetic import make_batch
     cfg, h = config_and_hierarchy()
-    # all host cores up to 32: beyond that the oracle's small sparse/dense ops get SLOWER (measured on the 128-core
-    # GPU box: 128 threads 67 s/step vs 8 threads 5 s/step for 4 meshes), and the baseline should be the CPU's best
+    # all host cores up to 32: beyond that the oracle's small sparse/dense ops get SLOWER (measured on the GPU box:
+    # 67 s/step for 4 meshes with one thread per core vs. ~0.6 s/step capped at 32), and the baseline should be the
+    # CPU's best
     torch.set_num_threads(min(os.cpu_count() or 1, 32))
     specs = param_specs(cfg, [l.shape[0] for l in h["L"]], [l.shape[0] for l in h["L_d"]])
     params = init_params(specs, cfg["seed"])
