@@ -648,7 +648,7 @@ extern "C" int cape_cheb_fwd(cape_topology* t, const cape_conv_args* a, void* st
   ConvParams p{};
   p.N = a->N; p.rows_out = a->rows_out; p.ncols = a->ncols; p.nterms = a->nterms;
   p.total_rows = (long long)a->N * a->rows_out;
-  bool dual = false;
+  bool dual = false, any_stash = false;
   bool wvec = (a->ncols % 4 == 0);
   p.nslots = 0;
   for (int i = 0; i < a->nterms; ++i) {
@@ -661,6 +661,12 @@ extern "C" int cape_cheb_fwd(cape_topology* t, const cape_conv_args* a, void* st
     d.w = s.w; d.w2 = s.w2;
     d.wT = s.wT; d.w2T = s.w2T; d.wT_stride = s.wT_stride; d.w2T_stride = s.w2T_stride;
     d.vec = (s.F % 4 == 0) && (s.src_stride % 4 == 0) && aligned16(s.src);
+    d.stash = s.stash; d.stash_stride = s.stash_stride;
+    if (s.stash) {
+      CAPE_REQUIRE(s.F % 4 == 0 && s.stash_stride >= s.F && s.stash_stride % 4 == 0 && aligned16(s.stash),
+                   "stash needs F % 4 == 0, stash_stride % 4 == 0 and 16-byte alignment");
+      any_stash = true;
+    }
     wvec = wvec && (s.w_stride % 4 == 0) && aligned16(s.w) && (!s.w2 || aligned16(s.w2));
     if (s.w2) {
       dual = true;
@@ -694,8 +700,20 @@ extern "C" int cape_cheb_fwd(cape_topology* t, const cape_conv_args* a, void* st
   {
     int rc = launch_thin_fwd(t, p, dual, st);             // <= 4 input channels: streaming kernel
     if (rc != 0) return rc < 0 ? rc : 0;
-    rc = launch_ellconv_tc(t, p, dual, st);               // tcgen05 path when eligible
+    rc = launch_ellconv_tc(t, p, dual, st);               // tcgen05 path when eligible (writes the stashes itself)
     if (rc != 0) return rc < 0 ? rc : 0;
+  }
+  if (any_stash) {                                        // fp32-pipe path: the basis copies come from the resample kernel
+    for (int i = 0; i < a->nterms; ++i) {
+      const TermDev& d = p.terms[i];
+      if (!d.stash) continue;
+      const long long blocks = (p.total_rows * 32 + 255) / 256;
+      const int vec = d.vec && (d.stash_stride % 4 == 0);
+      resample_kernel<<<(unsigned)blocks, 256, 0, st>>>(d.op, d.src, d.src_stride, d.stash, d.stash_stride, p.total_rows,
+                                                        a->rows_out, d.src_rows, d.F, vec, nullptr, 0);
+      CAPE_CHECK_CUDA(cudaGetLastError());
+      cape::count_launches(1);
+    }
   }
   dim3 grid((unsigned)((p.total_rows + BM - 1) / BM), (unsigned)((a->ncols + BNsel - 1) / BNsel));
   if (dual) {
@@ -723,7 +741,9 @@ extern "C" int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* strea
     int rc = launch_thin_dw(t, a, p.op, &ns, (cudaStream_t)stream);               // <= 4 input channels
     if (rc < 0) return rc;
     if (rc == 1) always_reduce = true;                                            // partials always in the workspace
-    else rc = launch_ellconv_dw_tc(t, a, p.op, &ns, (cudaStream_t)stream);        // tcgen05 path when eligible
+    else rc = launch_dw_dense_tma(t, a, p.op, &ns, (cudaStream_t)stream);         // dense operands: TMA + tcgen05
+    if (rc < 0) return rc;
+    if (rc == 0) rc = launch_ellconv_dw_tc(t, a, p.op, &ns, (cudaStream_t)stream);   // gathered basis: tcgen05
     if (rc < 0) return rc;
     if (rc == 1) {
       if (ns > 1 || always_reduce) {

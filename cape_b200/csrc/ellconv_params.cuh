@@ -20,6 +20,8 @@ struct TermDev {
   const float* w2T;
   int wT_stride, w2T_stride;
   int vec;
+  float* stash;       // optional copy of the gathered basis rows [total_rows, stash_stride] (cape_term.stash)
+  int stash_stride;
 };
 
 struct ConvParams {
@@ -53,5 +55,12 @@ int launch_thin_dw(const cape_topology* t, const cape_dw_args* a, const OpView& 
 // tcgen05 weight-gradient path (ellconv_dw_tc.cu): 1 = launched (partials in the workspace if *nsplit_out > 1)
 int launch_ellconv_dw_tc(const cape_topology* t, const cape_dw_args* a, const OpView& op, int* nsplit_out,
                          cudaStream_t st);
+
+// dense-operand weight gradient on TMA + tcgen05 (dw_dense_tma.cu): same contract
+int launch_dw_dense_tma(const cape_topology* t, const cape_dw_args* a, const OpView& op, int* nsplit_out,
+                        cudaStream_t st);
+// experiment knobs (cape_set_tuning): [1] = 1 disables the TMA dense-dW kernel, [2] = its lo-part mode (1 = rna, wrong
+// on purpose: shows the tensor core truncates), [3] = 2: 128- instead of 256-wide G sub-tiles for wide outputs
+extern int g_tuning[8];
 
 }  // namespace cape

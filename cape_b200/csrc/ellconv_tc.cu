@@ -212,6 +212,10 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
                 }
                 if (rn[i] < 0) va = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (rn[i + 1] < 0) vb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tm.stash != nullptr) {     // keep the basis rows for the weight gradient (cape_term.stash)
+                  if (rn[i] >= 0) *reinterpret_cast<float4*>(tm.stash + (size_t)(row0 + row_a) * tm.stash_stride + f) = va;
+                  if (rn[i + 1] >= 0) *reinterpret_cast<float4*>(tm.stash + (size_t)(row0 + row_b) * tm.stash_stride + f) = vb;
+                }
               }
               split_store(va, a_hi, a_lo, (uint32_t)(row_a * 128 + ((l8 ^ (row_a & 7)) << 4)));
               split_store(vb, a_hi, a_lo, (uint32_t)(row_b * 128 + ((l8 ^ (row_b & 7)) << 4)));
@@ -521,6 +525,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) ellconv_tc2_kernel(const __grid
               }
               if (n_a < 0) va = make_float4(0.f, 0.f, 0.f, 0.f);
               if (n_b < 0) vb = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (tm.stash != nullptr) {       // keep the basis rows for the weight gradient (cape_term.stash)
+                if (n_a >= 0) *reinterpret_cast<float4*>(tm.stash + (size_t)(row0 + row_a) * tm.stash_stride + f) = va;
+                if (n_b >= 0) *reinterpret_cast<float4*>(tm.stash + (size_t)(row0 + row_b) * tm.stash_stride + f) = vb;
+              }
             }
             split_store(va, a_hi, a_lo, (uint32_t)(row_a * 128 + ((l8 ^ (row_a & 7)) << 4)));
             split_store(vb, a_hi, a_lo, (uint32_t)(row_b * 128 + ((l8 ^ (row_b & 7)) << 4)));
@@ -728,7 +736,7 @@ int launch_two(const ConvParams& p, cudaStream_t st) {
 }  // namespace
 
 static bool g_tc_enabled = true;
-int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // experiment knobs (cape_set_tuning); none is read by the shipped kernels
+int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // experiment knobs (cape_set_tuning), see ellconv_params.cuh
 bool tensor_cores_enabled() { return g_tc_enabled; }
 
 int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaStream_t st) {

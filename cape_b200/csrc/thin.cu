@@ -199,7 +199,7 @@ int launch_thin_fwd(const cape_topology* t, const ConvParams& p, bool dual, cuda
   if (p.ncols > TH_MAXCOLS || p.ncols < 16) return 0;
   int KF = 0;
   for (int i = 0; i < p.nterms; ++i) {
-    if (p.terms[i].F > 4) return 0;
+    if (p.terms[i].F > 4 || p.terms[i].stash != nullptr) return 0;
     KF += p.terms[i].F;
   }
   if (KF > TH_MAXKF) return 0;

@@ -98,8 +98,11 @@ class ConvSite:
     just after (:168,:807).
     """
 
-    def __init__(self, tp, L, K, U=None, D=None):
+    def __init__(self, tp, L, K, U=None, D=None, order_in=None, order_out=None):
+        """order_in / order_out: internal vertex order (order[new] = reference index) of the level the site reads
+        from / writes to; None = the reference's own numbering (topology.patch_order)."""
         self.K = K
+        self.order_in, self.order_out = order_in, order_out
         self.ref_unpool, self.ref_pool = U is not None, D is not None   # poolwT calls in the reference graph
         self.M = L.shape[0]
         self.ref_rows_in = U.shape[1] if U is not None else L.shape[0]
@@ -115,6 +118,8 @@ class ConvSite:
         self.ops, self.opsT, self.mats = [], [], []
         for k in range(K):
             m = topo.compose(D, T[k], U)
+            if order_in is not None or order_out is not None:
+                m = topo.permute(m, order_out, order_in)
             self.mats.append(m)
             if m.shape[0] == m.shape[1] and topo.is_identity(m, tol=0):
                 self.ops.append(-1)
@@ -162,11 +167,12 @@ def cheb_call(tp, N, rows_out, ncols, terms, out, out2=None, cond=None, epilogue
         d.w_stride = t["w_stride"]
         d.w2_stride = t.get("w2_stride", 0)
         d.w = t["w"].data_ptr()
-        for k in ("w2", "wc", "wc2", "wT", "w2T"):
+        for k in ("w2", "wc", "wc2", "wT", "w2T", "stash"):
             v = t.get(k)
             setattr(d, k, v.data_ptr() if v is not None else None)
         d.wT_stride = t.get("wT_stride", 0)
         d.w2T_stride = t.get("w2T_stride", 0)
+        d.stash_stride = t.get("stash_stride", 0)
     if cond is not None:
         a.cond = cond.data_ptr()
         a.C = cond.shape[1]

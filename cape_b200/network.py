@@ -7,6 +7,7 @@ encoder :514-561, decoder_cond_vert :564-617, res_block_affine :776-793, res_blo
 discriminator :648-678, loss :354-416, training :419-474.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -105,13 +106,36 @@ class ChebLayer:
         self.Wt = torch.empty(Fout, K, F, device=dev)
         if self.affine:
             self.Wat = torch.empty(Fout, F, device=dev)
-        # Weight gradient "on the narrow side": dW_k = (op_k x)^T G = x^T (op_k^T G).  When the output is narrower than
-        # the input and the site does not pool, apply the (transposed) operators to G with the cheap resample kernel
-        # and contract ONCE over the input rows with plain (un-gathered) operands: all K terms in one pass over x.
-        self.dw_gside = (not site.ref_pool) and F >= Fout and K * Fout <= 512 and K > 1 and F % 4 == 0 and Fout % 32 == 0
-        if self.dw_gside:
-            self.Hg = torch.empty(maxN, site.rows_in, K * Fout, device=dev)
-            self.Ha = torch.empty(maxN, site.rows_in, Fout, device=dev) if (self.affine and site.opsT[0] != -1) else None
+        # Where the weight gradient gets its operands (all three end in the same contraction  dW = A^T G over rows):
+        #   "aside":  the forward kernel also writes the gathered basis B_k = op_k x (cape_term.stash), dW_k = B_k^T G;
+        #   "gside":  the data-gradient kernel also writes H_k = op_k^T G, dW_k = x^T H_k -- all K terms in ONE pass
+        #             over x when K*Fout <= 512 (the TMEM width), over the smaller row set when the site un-pools;
+        #   "gather": cape_cheb_dw gathers the basis again (thin layers, odd shapes).
+        # The first two make both operands plain tensors, which is what the TMA-fed tcgen05 kernel wants.
+        dense_ok = F % 4 == 0 and F >= 32 and Fout % 32 == 0 and Fout <= 512
+        pooled, unpooled = site.rows_out < site.rows_in, site.rows_in < site.rows_out
+        self.dw_mode = "gather"
+        if dense_ok and os.environ.get("CAPE_DW_STASH", "1") != "0":
+            if pooled:
+                self.dw_mode = "aside"
+            elif need_dx and (unpooled or (K * Fout <= 512 and F >= Fout)):
+                self.dw_mode = "gside"
+            else:
+                self.dw_mode = "aside"
+        self.stash_a, self.stash_g, self.stash_ga = [None] * K, [None] * K, None
+        if self.dw_mode == "aside":
+            self.stash_a = [None if site.ops[k] == -1 else torch.empty(maxN, site.rows_out, F, device=dev)
+                            for k in range(K)]
+        elif self.dw_mode == "gside":
+            self.g_merged = K > 1 and K * Fout <= 512
+            if self.g_merged:
+                self.Hg = torch.empty(maxN, site.rows_in, K * Fout, device=dev)
+                self.stash_g = [self.Hg[:, :, k * Fout:(k + 1) * Fout] for k in range(K)]
+            else:
+                self.stash_g = [None if site.opsT[k] == -1 else torch.empty(maxN, site.rows_in, Fout, device=dev)
+                                for k in range(K)]
+            if self.affine and site.opsT[0] != -1:
+                self.stash_ga = torch.empty(maxN, site.rows_in, Fout, device=dev)
         # colsum targets: [bias?] + K condition sums (+1 for the affine branch)
         self.cs_ops = []
         if bias is not None and not bias_per_row:
@@ -158,6 +182,8 @@ class ChebLayer:
                      w_stride=K * Fout, wT=self.Wt[:, k, :], wT_stride=K * F)
             if C:
                 t["wc"] = self.W3[F:, k, :]
+            if self.stash_a[k] is not None:
+                t["stash"], t["stash_stride"] = self.stash_a[k][:N], F
             if self.affine and k == 0:
                 t["w2"], t["w2_stride"] = self.Wa2, Fout
                 t["w2T"], t["w2T_stride"] = self.Wat, F
@@ -175,21 +201,23 @@ class ChebLayer:
         tp, s, F, C, K, Fout = self.tp, self.site, self.F, self.C, self.K, self.Fout
         N = g.shape[0]
         sx = x.shape[2]
-        if want_dw and self.dw_gside:
-            nl = 1 + (1 if self.affine else 0)
+        mode = self.dw_mode if (want_dw and (self.dw_mode != "gside" or dx is not None)) else "gather"
+        if want_dw and mode == "aside":
+            nl = K + (1 if self.affine else 0)
             tg = (self.name + ":dW", self.alg_bytes(N, "dW") / nl)
-            H = self.Hg[:N]
             for k in range(K):
-                E.resample(tp, s.opsT[k], g, H[:, :, k * Fout:], N, s.rows_in, s.rows_out, Fout, x_stride=Fout,
-                           y_stride=K * Fout)
-            cheb_dw(tp, N, s.rows_in, K * Fout, x, -1, F, s.rows_in, sx, H, self.gW3, K * Fout, tag=tg)
+                B = self.stash_a[k]
+                if B is None:                                   # identity term: the basis is x itself
+                    cheb_dw(tp, N, s.rows_out, Fout, x, -1, F, s.rows_in, sx, g, self.gW3[:, k, :], K * Fout, tag=tg)
+                else:
+                    cheb_dw(tp, N, s.rows_out, Fout, B[:N], -1, F, s.rows_out, F, g, self.gW3[:, k, :], K * Fout, tag=tg)
             if self.affine:
-                Ha = g_aff
-                if self.Ha is not None:
-                    Ha = self.Ha[:N]
-                    E.resample(tp, s.opsT[0], g_aff, Ha, N, s.rows_in, s.rows_out, Fout)
-                cheb_dw(tp, N, s.rows_in, Fout, x, -1, F, s.rows_in, sx, Ha, self.gWa2, Fout, tag=tg)
-        elif want_dw:
+                B = self.stash_a[0]
+                if B is None:
+                    cheb_dw(tp, N, s.rows_out, Fout, x, -1, F, s.rows_in, sx, g_aff, self.gWa2, Fout, tag=tg)
+                else:
+                    cheb_dw(tp, N, s.rows_out, Fout, B[:N], -1, F, s.rows_out, F, g_aff, self.gWa2, Fout, tag=tg)
+        elif want_dw and mode == "gather":
             nl = K + (1 if self.affine else 0)
             tg = (self.name + ":dW", self.alg_bytes(N, "dW") / nl)
             for k in range(K):
@@ -225,15 +253,35 @@ class ChebLayer:
             gemm(tp, self.net.ones[:, :N], g.view(N, s.rows_out * Fout), self.gbias.view(1, s.rows_out * Fout))
         if dx is not None:
             assert self.need_dx
+            gs = want_dw and mode == "gside"
             terms = []
             if self.affine:
-                terms.append(dict(src=g_aff, op=s.opsT[0], F=Fout, src_rows=s.rows_out, src_stride=Fout, w=self.Wat,
-                                  w_stride=F, wT=self.Wa2, wT_stride=Fout))
+                t = dict(src=g_aff, op=s.opsT[0], F=Fout, src_rows=s.rows_out, src_stride=Fout, w=self.Wat,
+                         w_stride=F, wT=self.Wa2, wT_stride=Fout)
+                if gs and self.stash_ga is not None:
+                    t["stash"], t["stash_stride"] = self.stash_ga[:N], Fout
+                terms.append(t)
             for k in range(K):
-                terms.append(dict(src=g, op=s.opsT[k], F=Fout, src_rows=s.rows_out, src_stride=Fout,
-                                  w=self.Wt[:, k, :], w_stride=K * F, wT=self.W3[:, k, :], wT_stride=K * Fout))
+                t = dict(src=g, op=s.opsT[k], F=Fout, src_rows=s.rows_out, src_stride=Fout,
+                         w=self.Wt[:, k, :], w_stride=K * F, wT=self.W3[:, k, :], wT_stride=K * Fout)
+                if gs and self.stash_g[k] is not None:
+                    t["stash"], t["stash_stride"] = self.stash_g[k][:N], self.stash_g[k].stride(1)
+                terms.append(t)
             cheb_call(tp, N, s.rows_in, F, terms, dx, out2=dx2, epilogue=dx_epi, aux=dx_aux, alpha=dx_alpha,
                       tag=(self.name + ":dx", self.alg_bytes(N, "dx")))
+            if gs:
+                # dW_k = x^T (op_k^T G): the data-gradient kernel above left op_k^T G in the stash buffers
+                nl = (1 if self.g_merged else K) + (1 if self.affine else 0)
+                tg = (self.name + ":dW", self.alg_bytes(N, "dW") / nl)
+                if self.g_merged:
+                    cheb_dw(tp, N, s.rows_in, K * Fout, x, -1, F, s.rows_in, sx, self.Hg[:N], self.gW3, K * Fout, tag=tg)
+                else:
+                    for k in range(K):
+                        H = g if self.stash_g[k] is None else self.stash_g[k][:N]
+                        cheb_dw(tp, N, s.rows_in, Fout, x, -1, F, s.rows_in, sx, H, self.gW3[:, k, :], K * Fout, tag=tg)
+                if self.affine:
+                    Ha = g_aff if self.stash_ga is None else self.stash_ga[:N]
+                    cheb_dw(tp, N, s.rows_in, Fout, x, -1, F, s.rows_in, sx, Ha, self.gWa2, Fout, tag=tg)
 
     def _colsum_chunk(self, g, N, cs, o):
         # more than 4 operators (K > 3 with conditions): contiguous scratch per chunk, then copy back
@@ -275,18 +323,22 @@ class GNBlock:
     The concat+unpool is one gather kernel (condition channels = rowsum(U) * y, never read from HBM), every
     GN+ReLU is one fused pass each way, lin2 + lin_in is a single two-term contraction."""
 
-    def __init__(self, net, idx, L, U, Fin, Cc, Fo, K, scope, maxN):
+    def __init__(self, net, idx, L, U, Fin, Cc, Fo, K, scope, maxN, order_in=None, order_out=None):
         import scipy.sparse as sp
         self.net, self.tp = net, net.tp
         tp, dev = net.tp, net.device
         w, g = net._w, net._g
         self.Fin, self.Cc, self.Ft, self.mid, self.Fo = Fin, Cc, Fin + Cc, Fo // 2, Fo
         self.rows, self.rows_in = L.shape[0], U.shape[1]
-        if topo.is_identity(U, tol=1e-6):
+        if topo.is_identity(U, tol=1e-6) and order_in is order_out:
             self.op_u = self.op_uT = -1
         else:
-            self.op_u, self.op_uT = tp.add_operator(sp.csr_matrix(U)), tp.add_operator(sp.csr_matrix(U.T))
-        lin, conv = ConvSite(tp, L, 1), ConvSite(tp, L, K)
+            Up = topo.permute(sp.identity(U.shape[0], format="csr") if topo.is_identity(U, tol=1e-6) else U,
+                              order_out, order_in)
+            self.op_u, self.op_uT = tp.add_operator(sp.csr_matrix(Up)), tp.add_operator(sp.csr_matrix(Up.T))
+        lin = ConvSite(tp, L, 1, order_in=order_out, order_out=order_out)
+        conv = ConvSite(tp, L, K, order_in=order_out, order_out=order_out)
+        self.order_out = order_out
         nm = "dec/res%d" % (idx + 1)
         mk = lambda site, F, Fout, sc, tag: ChebLayer(net, site, F, 0, Fout, w(scope + "/" + sc + "/weights"),
                                                       g(scope + "/" + sc + "/weights"), maxN=maxN, name=nm + "/" + tag)
@@ -349,8 +401,15 @@ class GNBlock:
 class CapeNetwork:
     """Encoder/decoder/discriminator + losses + optimiser on one GPU for a fixed batch size."""
 
-    def __init__(self, L, D, U, L_d, D_d, cfg, batch_size, device=0, params=None, ref_compat=False):
+    def __init__(self, L, D, U, L_d, D_d, cfg, batch_size, device=0, params=None, ref_compat=False, reorder=None):
+        """reorder: keep the hidden activations in patch order (topology.patch_order) instead of the reference's
+        vertex numbering.  Everything visible from outside (inputs, outputs, parameters, their gradients, the
+        FC-layer row layout) stays in the reference numbering: the permutations are folded into the operator
+        tables of the first/last conv of each stack.  Default: on (env CAPE_REORDER=0 turns it off)."""
         self.cfg = dict(cfg)
+        if reorder is None:
+            reorder = os.environ.get("CAPE_REORDER", "1") != "0"
+        self.reorder = bool(reorder)
         self.N = int(batch_size)
         self.ref_compat = bool(ref_compat)
         c = self.cfg
@@ -381,10 +440,16 @@ class CapeNetwork:
 
         # ---- sites -------------------------------------------------------------------------------------
         nl = len(F)
+        if self.reorder:
+            og = topo.level_orders(L[0], D[:nl])
+            od = topo.level_orders(L_d[0], D_d)
+        else:
+            og, od = [None] * (nl + 1), [None] * (len(D_d) + 1)
+        self.order_g, self.order_d = og, od
         self.enc = []
         fin = c["nn_input_channel"]
         for i in range(nl):
-            site = ConvSite(tp, L[i], K[i], D=D[i])
+            site = ConvSite(tp, L[i], K[i], D=D[i], order_in=og[i] if i > 0 else None, order_out=og[i + 1])
             sc = "generator/encoder/encoder_conv%d" % (i + 1)
             self.enc.append(ChebLayer(self, site, fin, 0, F[i], w(sc + "/weights"), g(sc + "/weights"),
                                       bias=w(sc + "/bias"), gbias=g(sc + "/bias"), act=ACT_LEAKY, need_dx=(i > 0),
@@ -392,7 +457,8 @@ class CapeNetwork:
             fin = F[i]
         red = specs["generator/encoder/1x1-conv/weights"][1]
         self.red = red
-        self.enc_1x1 = ChebLayer(self, ConvSite(tp, L[-1], 1), F[-1], 0, red, w("generator/encoder/1x1-conv/weights"),
+        self.enc_1x1 = ChebLayer(self, ConvSite(tp, L[-1], 1, order_in=og[nl]), F[-1], 0, red,
+                                 w("generator/encoder/1x1-conv/weights"),
                                  g("generator/encoder/1x1-conv/weights"), maxN=N, name="enc/1x1")
         flat = self.p[-1] * red
         self.flat = flat
@@ -401,7 +467,8 @@ class CapeNetwork:
                                            g(s + "/dense/bias"), act, name=s.split("/", 1)[-1])
         self.fc_mean, self.fc_var = dn("generator/encoder/fc_mean"), dn("generator/encoder/fc_var")
         self.dec_fc1 = dn("generator/decoder/fc1", ACT_LEAKY)
-        self.dec_1x1 = ChebLayer(self, ConvSite(tp, L[-1], 1), red, 0, F[-1], w("generator/decoder/1x1-conv/weights"),
+        self.dec_1x1 = ChebLayer(self, ConvSite(tp, L[-1], 1, order_out=og[nl]), red, 0, F[-1],
+                                 w("generator/decoder/1x1-conv/weights"),
                                  g("generator/decoder/1x1-conv/weights"), maxN=N, name="dec/1x1")
         self.dec = []
         self.affine = bool(c["affine"])
@@ -409,7 +476,7 @@ class CapeNetwork:
         for i in range(nl):
             if self.affine:
                 Fo = F[-i - 1] // 2
-                site = ConvSite(tp, L[-i - 2], K[-i - 1], U=U[-i - 1])
+                site = ConvSite(tp, L[-i - 2], K[-i - 1], U=U[-i - 1], order_in=og[nl - i], order_out=og[nl - i - 1])
                 sc = "generator/decoder/decoder_resblock_affine%d" % (i + 1)
                 self.dec.append(ChebLayer(self, site, fin, Cc, Fo, w(sc + "/graph_conv/weights"),
                                           g(sc + "/graph_conv/weights"), Wa=w(sc + "/affine/weights"),
@@ -417,22 +484,23 @@ class CapeNetwork:
             else:
                 Fo = F[-i - 1]
                 self.dec.append(GNBlock(self, i, L[-i - 2], U[-i - 1], fin, Cc, Fo, K[-i - 1],
-                                        "generator/decoder/decoder_resblock_cmr%d" % (i + 1), N))
+                                        "generator/decoder/decoder_resblock_cmr%d" % (i + 1), N,
+                                        order_in=og[nl - i], order_out=og[nl - i - 1]))
             fin = Fo
-        self.dec_out = ChebLayer(self, ConvSite(tp, L[0], K[0]), fin, Cc, c["nn_input_channel"],
+        self.dec_out = ChebLayer(self, ConvSite(tp, L[0], K[0], order_in=og[0]), fin, Cc, c["nn_input_channel"],
                                  w("generator/decoder/outputs/weights"), g("generator/decoder/outputs/weights"),
                                  bias=w("generator/decoder/outputs/bias"), gbias=g("generator/decoder/outputs/bias"),
                                  bias_per_row=True, maxN=N, name="dec/outputs")
         self.disc = []
         fin = c["nn_input_channel"]
         for i in range(len(D_d)):
-            site = ConvSite(tp, L_d[i], Kd, D=D_d[i])
+            site = ConvSite(tp, L_d[i], Kd, D=D_d[i], order_in=od[i] if i > 0 else None, order_out=od[i + 1])
             sc = "discriminator/shared/conv%d" % (i + 1)
             self.disc.append(ChebLayer(self, site, fin, Cc if i == 0 else 0, F[i], w(sc + "/weights"),
                                        g(sc + "/weights"), bias=w(sc + "/bias"), gbias=g(sc + "/bias"), act=ACT_LEAKY,
                                        maxN=2 * N, n_cs_slots=2, name="disc/conv%d" % (i + 1)))
             fin = F[i]
-        self.disc_pred = ChebLayer(self, ConvSite(tp, L_d[-1], K[-1]), fin, 0, 1,
+        self.disc_pred = ChebLayer(self, ConvSite(tp, L_d[-1], K[-1], order_in=od[-1], order_out=od[-1]), fin, 0, 1,
                                    w("discriminator/prediction_map/weights"), g("discriminator/prediction_map/weights"),
                                    maxN=2 * N, n_cs_slots=2, name="disc/pred_map")
         # condition nets (models.py:479-511)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CAPE_ABI_VERSION 1
+#define CAPE_ABI_VERSION 2
 #define CAPE_MAX_TERMS 8
 
 typedef struct cape_topology cape_topology;
@@ -76,6 +76,13 @@ typedef struct {
   const float* w2T;
   int wT_stride;
   int w2T_stride;
+  /* optional: also write this term's gathered basis rows  B[n, r, 0:F] = sum_j op[r, j] * src[n, idx[r, j], 0:F]  to
+   * stash[(n * rows_out + r) * stash_stride + f]  (16-byte aligned, stash_stride % 4 == 0, F % 4 == 0).  The weight
+   * gradient of the layer can then contract plain tensors (cape_cheb_dw with op = -1: the TMA-fed kernel) instead of
+   * gathering again: in a forward call the stash is the basis itself, in a data-gradient call it is op^T . G, the
+   * "narrow side" operand (dW_k = x^T (op_k^T G)). */
+  float* stash;
+  int stash_stride;
 } cape_term;
 
 enum {

@@ -195,22 +195,27 @@ def train_step(h, cfg, N=2, ref_compat=False, step=100, seed=123, dtype=torch.fl
         def sel(D):
             return None if T2.is_identity(D, tol=0) else torch.from_numpy(sp.csr_matrix(D).indices.astype(np.int64))
 
+        def pos(a, order):
+            """sign mask of a hidden activation, back in the reference's vertex numbering"""
+            m = (a > 0).cpu()
+            return m if order is None else m[:, torch.from_numpy(T2.inverse_order(order))]
+
         for i, a in enumerate(net.enc_act):
-            masks["enc%d" % (i + 1)] = (a > 0).cpu()
+            masks["enc%d" % (i + 1)] = pos(a, net.enc[i].site.order_out)
             r = sel(h["D"][i])
             if r is not None:
                 rows["enc%d" % (i + 1)] = r
         for i, a in enumerate(net.dec_rg):
-            masks["dec%d" % (i + 1)] = (a > 0).cpu()
+            masks["dec%d" % (i + 1)] = pos(a, net.dec[i].site.order_out)
         if not net.affine:                                # GroupNorm blocks: three ReLUs each (lib/models.py:752-760)
             for i, b in enumerate(net.dec):
                 for j, a in enumerate((b.A1, b.A2, b.A3)):
-                    masks["gn%d_%d" % (i + 1, j)] = (a > 0).cpu()
+                    masks["gn%d_%d" % (i + 1, j)] = pos(a, b.order_out)
         masks["dec_fc1"] = (net.dec_fc > 0).cpu()
         for i, a in enumerate(net.disc_act):
             r = sel(h["D_d"][i])
             for tag, sl in (("_real", slice(0, N)), ("_fake", slice(N, 2 * N))):
-                masks["disc%d%s" % (i + 1, tag)] = (a[sl] > 0).cpu()
+                masks["disc%d%s" % (i + 1, tag)] = pos(a[sl], net.disc[i].site.order_out)
                 if r is not None:
                     rows["disc%d%s" % (i + 1, tag)] = r
         masks["cond_pose_d"], masks["cond_pose_g"] = (net.cp_h[:N] > 0).cpu(), (net.cp_h[N:] > 0).cpu()

@@ -24,7 +24,7 @@ def test_header_symbols_exported(lib_built):
 
 
 def test_abi_version_and_error_string(lib_built):
-    assert lib_built.cape_abi_version() == 1
+    assert lib_built.cape_abi_version() == 2
     assert isinstance(lib_built.cape_last_error(), bytes)
 
 

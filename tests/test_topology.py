@@ -87,3 +87,34 @@ def test_composed_operator_equals_sequential(hierarchy):
 def test_adjacency_ell_counts_edges(hierarchy):
     idx, _ = T.adjacency_ell(hierarchy["L"][0])
     assert (idx >= 0).sum() == 2 * 20664
+
+
+def _distinct_per_row(m, tile=128):
+    m = sp.csr_matrix(m)
+    r = [len(np.unique(m[r0:r0 + tile].indices)) / m[r0:r0 + tile].shape[0] for r0 in range(0, m.shape[0], tile)]
+    return float(np.mean(r))
+
+
+def test_patch_order_is_a_layout_change_only(hierarchy):
+    """The internal vertex order: a permutation per level, coarse levels induced from the fine one, operators
+    between re-ordered levels give the re-ordered result, and 128-row tiles touch fewer distinct rows."""
+    h = hierarchy
+    orders = T.level_orders(h["L"][0], h["D"])
+    assert [len(o) for o in orders] == [l.shape[0] for l in h["L"]]
+    for o in orders:
+        assert np.array_equal(np.sort(o), np.arange(len(o)))
+    assert T.patch_order(h["L"][0]) is orders[0]                 # cached, reproducible
+    rng = np.random.RandomState(1)
+    for lvl in (1, 3):                                           # a 2:1 pooled site and its unpool mirror
+        m = T.compose(h["D"][lvl], T.cheb_polynomials(h["L"][lvl], 2)[1], None)
+        oi, oo = orders[lvl], orders[lvl + 1]
+        x = rng.normal(size=(m.shape[1], 3))
+        assert np.abs(T.permute(m, oo, oi) @ x[oi] - (m @ x)[oo]).max() < 1e-12
+        inv = T.inverse_order(oo)
+        assert np.array_equal(oo[inv], np.arange(len(oo)))
+        # induced order keeps the pooling a monotone selection
+        sel = T.permute(h["D"][lvl], oo, oi).indices
+        assert (np.diff(sel) > 0).all()
+    Lt = T.rescale_L(h["L"][0])
+    before, after = _distinct_per_row(Lt), _distinct_per_row(T.permute(Lt, orders[0], orders[0]))
+    assert after < 0.75 * before and after < 1.7
