@@ -20,6 +20,8 @@ struct TermDev {
   const float* w2T;
   int wT_stride, w2T_stride;
   int vec;
+  const float* wT_lo;   // optional: wT - trunc_tf32(wT), same layout (weight tiles then come by TMA)
+  const float* w2T_lo;
   float* stash;       // optional copy of the gathered basis rows [total_rows, stash_stride] (cape_term.stash)
   int stash_stride;
 };
@@ -60,7 +62,8 @@ int launch_ellconv_dw_tc(const cape_topology* t, const cape_dw_args* a, const Op
 int launch_dw_dense_tma(const cape_topology* t, const cape_dw_args* a, const OpView& op, int* nsplit_out,
                         cudaStream_t st);
 // experiment knobs (cape_set_tuning): [1] = 1 disables the TMA dense-dW kernel, [2] = its lo-part mode (1 = rna, wrong
-// on purpose: shows the tensor core truncates), [3] = 2: 128- instead of 256-wide G sub-tiles for wide outputs
+// on purpose: shows the tensor core truncates), [3] = 2: 128- instead of 256-wide G sub-tiles for wide outputs, [4] = 1: weight tiles of the wide conv kernel by the
+// producer warps instead of TMA
 extern int g_tuning[8];
 
 }  // namespace cape

@@ -16,6 +16,7 @@
 // writes -- overlapping the next tile's main loop.
 #include "common.cuh"
 #include "ellconv_params.cuh"
+#include "tc_common.cuh"
 
 namespace cape {
 
@@ -111,7 +112,15 @@ struct TcCfg {
 
 constexpr int TC_EPI_WARPS = 4;
 constexpr int TC_EPI_WARP0 = TC_PROD_WARPS + 1;                        // warps 9..12: TMEM lane quadrants 1,2,3,0
-constexpr int TC_THREADS3 = (TC_PROD_WARPS + 1 + TC_EPI_WARPS) * 32;   // 416
+constexpr int TC_TMA_WARP = TC_EPI_WARP0 + TC_EPI_WARPS;               // warp 13: TMA issuer for the weight tiles
+constexpr int TC_THREADS3 = (TC_PROD_WARPS + 2 + TC_EPI_WARPS) * 32;   // 448
+constexpr int TC_TMA_TERMS = 4;
+
+// Tensor maps of the pre-split K-major weight copies, per term: [0] wT (raw fp32 = "hi": the tensor core reads the top
+// 19 bits), [1] wT_lo, [2] w2T, [3] w2T_lo.  Boxes of 32 k x BN columns, SWIZZLE_128B: a box lands as one operand tile.
+struct BMaps {
+  CUtensorMap m[TC_TMA_TERMS][4];
+};
 
 // Persistent kernel.  A CTA loops over 128-row output tiles (all output columns each).  Three roles run
 // concurrently on different tiles: 8 producer warps (gather/split/store the basis chunk A once per chunk, stream the
@@ -119,8 +128,9 @@ constexpr int TC_THREADS3 = (TC_PROD_WARPS + 1 + TC_EPI_WARPS) * 32;   // 416
 // accumulator buffers when 2 x accumulator columns <= 512), 4 epilogue warps (tcgen05.ld, condition/bias/
 // activation, stores) -- so the epilogue and start-up of one tile overlap the main loop of the next.
 template <int BN, bool DUAL>
-__global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid_constant__ ConvParams p, int nct,
-                                                                    int tmem_cols, int nbuf, int ntiles) {
+__global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid_constant__ ConvParams p,
+                                                                    const __grid_constant__ BMaps maps, int nct,
+                                                                    int tmem_cols, int nbuf, int ntiles, int tma_b) {
   using Cfg = TcCfg<BN, DUAL>;
   constexpr int SA = Cfg::A_STAGES, SB = Cfg::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -141,7 +151,10 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
   if (warp == TC_PROD_WARPS) {
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, TC_PROD_WARPS); mbar_init(bar_aempty + 8 * s, 1); }
-      for (int s = 0; s < SB; ++s) { mbar_init(bar_bfull + 8 * s, TC_PROD_WARPS); mbar_init(bar_bempty + 8 * s, 1); }
+      for (int s = 0; s < SB; ++s) {
+        mbar_init(bar_bfull + 8 * s, tma_b ? 1 : TC_PROD_WARPS);      // TMA: one arrive.expect_tx + the bytes
+        mbar_init(bar_bempty + 8 * s, 1);
+      }
       for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, TC_EPI_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
               }
             }
           };
-          load_b(0);
+          if (!tma_b) load_b(0);
           // ---- A chunk: gather 4 rows per thread, split, store swizzled
           mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
           {
@@ -225,8 +238,8 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
             if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
             if (++sa == SA) { sa = 0; pha ^= 1; }
           }
-          // ---- B chunks: one [BN x 32] K-major weight tile (hi/lo) per column sub-tile
-          for (int cs = 0; cs < nct; ++cs) {
+          // ---- B chunks: one [BN x 32] K-major weight tile (hi/lo) per column sub-tile (unless the TMA warp does it)
+          for (int cs = 0; cs < (tma_b ? 0 : nct); ++cs) {
             if (cs > 0) load_b(cs);
             mbar_wait(bar_bempty + 8 * sb, phb ^ 1);
             char* b_hi = b_ring + (size_t)sb * Cfg::B_STAGE_BYTES;
@@ -298,6 +311,36 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
           }
         }
         umma_commit(bar_tfull + 8 * buf);                  // this tile's accumulators are complete
+      }
+    }
+    __syncwarp();
+  } else if (warp == TC_TMA_WARP) {
+    // =========================== TMA issuer: weight tiles (hi = raw fp32, lo = pre-split copy) ===========================
+    if (tma_b && lane == 0) {
+      for (int t = 0; t < p.nterms; ++t) {
+        tc::tma_prefetch_desc(&maps.m[t][0]);
+        tc::tma_prefetch_desc(&maps.m[t][1]);
+      }
+      int sb = 0;
+      uint32_t phb = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int t = 0; t < p.nterms; ++t) {
+          const bool has2 = DUAL && p.terms[t].w2T != nullptr;
+          for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+            for (int cs = 0; cs < nct; ++cs) {
+              mbar_wait(bar_bempty + 8 * sb, phb ^ 1);
+              tc::mbar_arrive_expect_tx(bar_bfull + 8 * sb, (uint32_t)((has2 ? 4 : 2) * Cfg::B_TILE_BYTES));
+              const uint32_t dst = smem_u32(b_ring + (size_t)sb * Cfg::B_STAGE_BYTES);
+              tc::tma_load_2d(dst, &maps.m[t][0], f0, cs * BN, bar_bfull + 8 * sb);
+              tc::tma_load_2d(dst + Cfg::B_TILE_BYTES, &maps.m[t][1], f0, cs * BN, bar_bfull + 8 * sb);
+              if (has2) {
+                tc::tma_load_2d(dst + 2 * Cfg::B_TILE_BYTES, &maps.m[t][2], f0, cs * BN, bar_bfull + 8 * sb);
+                tc::tma_load_2d(dst + 3 * Cfg::B_TILE_BYTES, &maps.m[t][3], f0, cs * BN, bar_bfull + 8 * sb);
+              }
+              if (++sb == SB) { sb = 0; phb ^= 1; }
+            }
+          }
+        }
       }
     }
     __syncwarp();
@@ -411,6 +454,38 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
   }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// K-major weight copy: element (f, c) at base[c * stride + f]; boxes of 32 f x bn columns, 128-byte swizzle
+bool make_wmap(CUtensorMap* m, const float* base, int F, int ncols, int stride, int bn) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || base == nullptr || !aligned16(base) || stride % 4 != 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)F, (cuuint64_t)ncols};
+  const cuuint64_t strides[1] = {(cuuint64_t)stride * sizeof(float)};
+  const cuuint32_t box[2] = {32, (cuuint32_t)bn};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN, bool DUAL>
 int launch_one(const cape_topology* t, const ConvParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, DUAL>;
@@ -427,7 +502,20 @@ int launch_one(const cape_topology* t, const ConvParams& p, cudaStream_t st) {
   while (tmem_cols < acc_cols * nbuf) tmem_cols *= 2;
   const int ntiles = (int)((p.total_rows + BM - 1) / BM);
   const int grid = ntiles < t->sm_count ? ntiles : t->sm_count;
-  ellconv_tc_kernel<BN, DUAL><<<grid, TC_THREADS3, Cfg::SMEM_BYTES, st>>>(p, nct, tmem_cols, nbuf, ntiles);
+  // weight tiles by TMA when every term comes with pre-split copies (cape_term.wT_lo)
+  static BMaps maps;                      // host-side scratch, copied into the launch
+  int tma_b = (p.nterms <= TC_TMA_TERMS && g_tuning[4] != 1) ? 1 : 0;
+  for (int i = 0; i < p.nterms && tma_b; ++i) {
+    const TermDev& tm = p.terms[i];
+    if (tm.wT_lo == nullptr || (tm.w2T != nullptr && tm.w2T_lo == nullptr)) { tma_b = 0; break; }
+    if (!make_wmap(&maps.m[i][0], tm.wT, tm.F, p.ncols, tm.wT_stride, BN) ||
+        !make_wmap(&maps.m[i][1], tm.wT_lo, tm.F, p.ncols, tm.wT_stride, BN)) { tma_b = 0; break; }
+    if (DUAL && tm.w2T != nullptr) {
+      if (!make_wmap(&maps.m[i][2], tm.w2T, tm.F, p.ncols, tm.w2T_stride, BN) ||
+          !make_wmap(&maps.m[i][3], tm.w2T_lo, tm.F, p.ncols, tm.w2T_stride, BN)) { tma_b = 0; break; }
+    }
+  }
+  ellconv_tc_kernel<BN, DUAL><<<grid, TC_THREADS3, Cfg::SMEM_BYTES, st>>>(p, maps, nct, tmem_cols, nbuf, ntiles, tma_b);
   CAPE_CHECK_CUDA(cudaGetLastError());
   count_launches(1);
   return 1;

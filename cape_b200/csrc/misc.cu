@@ -171,7 +171,8 @@ __global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, f
   }
 }
 
-__global__ void wtrans_kernel(const float* __restrict__ w, int Fin, int K, int Fout, float* __restrict__ wt) {
+__global__ void wtrans_kernel(const float* __restrict__ w, int Fin, int K, int Fout, float* __restrict__ wt,
+                              float* __restrict__ wt_lo) {
   // tile transpose through shared memory: for each k, [Fin x Fout] -> [Fout x Fin]
   __shared__ float tile[32][33];
   const int k = blockIdx.z;
@@ -183,7 +184,18 @@ __global__ void wtrans_kernel(const float* __restrict__ w, int Fin, int K, int F
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i, f = f0 + threadIdx.x;
-    if (c < Fout && f < Fin) wt[((size_t)c * K + k) * Fin + f] = tile[threadIdx.x][i];
+    if (c < Fout && f < Fin) {
+      const float v = tile[threadIdx.x][i];
+      wt[((size_t)c * K + k) * Fin + f] = v;
+      if (wt_lo) wt_lo[((size_t)c * K + k) * Fin + f] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    }
+  }
+}
+
+__global__ void tf32_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    lo[i] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
   }
 }
 
@@ -290,10 +302,19 @@ extern "C" int cape_sgd_clip_update(float* w, const float* g, float* mom, int64_
   return 0;
 }
 
-extern "C" int cape_cheb_weight_transpose(const float* w, int Fin, int K, int Fout, float* wt, void* stream) {
+extern "C" int cape_cheb_weight_transpose(const float* w, int Fin, int K, int Fout, float* wt, float* wt_lo,
+                                          void* stream) {
   CAPE_REQUIRE(w && wt && Fin > 0 && K > 0 && Fout > 0, "bad arguments");
   dim3 grid((Fin + 31) / 32, (Fout + 31) / 32, K), block(32, 8);
-  wtrans_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, Fin, K, Fout, wt);
+  wtrans_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, Fin, K, Fout, wt, wt_lo);
+  CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
+  return 0;
+}
+
+extern "C" int cape_tf32_lo(const float* x, float* lo, long long n, void* stream) {
+  CAPE_REQUIRE(x && lo && n > 0, "bad arguments");
+  tf32_lo_kernel<<<blocks_for(n, 256, 4096), 256, 0, (cudaStream_t)stream>>>(x, lo, n);
   CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
   return 0;

@@ -167,7 +167,7 @@ def cheb_call(tp, N, rows_out, ncols, terms, out, out2=None, cond=None, epilogue
         d.w_stride = t["w_stride"]
         d.w2_stride = t.get("w2_stride", 0)
         d.w = t["w"].data_ptr()
-        for k in ("w2", "wc", "wc2", "wT", "w2T", "stash"):
+        for k in ("w2", "wc", "wc2", "wT", "w2T", "stash", "wT_lo", "w2T_lo"):
             v = t.get(k)
             setattr(d, k, v.data_ptr() if v is not None else None)
         d.wT_stride = t.get("wT_stride", 0)
@@ -202,8 +202,13 @@ def colsum(tp, g, N, rows, ncols, ops, out, g_stride=None):
                              _ptr(out), _stream()))
 
 
-def weight_transpose(tp, w, Fin, K, Fout, wt):
-    check(tp.lib.cape_cheb_weight_transpose(_ptr(w), Fin, K, Fout, _ptr(wt), _stream()))
+def weight_transpose(tp, w, Fin, K, Fout, wt, wt_lo=None):
+    check(tp.lib.cape_cheb_weight_transpose(_ptr(w), Fin, K, Fout, _ptr(wt), _ptr(wt_lo), _stream()))
+
+
+def tf32_lo(tp, x, lo):
+    """lo = x - tf32_trunc(x) (the pre-split low part of an operand the tensor cores read raw)."""
+    check(tp.lib.cape_tf32_lo(_ptr(_f32(x)), _ptr(_f32(lo)), x.numel(), _stream()))
 
 
 def act_bwd(tp, dy, y, g, alpha=LEAKY_ALPHA):

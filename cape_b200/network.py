@@ -39,6 +39,14 @@ class ParamStore:
         self.flat = torch.zeros(self.size, device=device)
         self.grad = torch.zeros(self.size, device=device)
         self.mom = torch.zeros(self.size, device=device)
+        self.lo = torch.zeros(self.size, device=device)     # flat - tf32_trunc(flat): weight tiles by TMA (3xTF32)
+
+    def lo_of(self, t):
+        """The view of `lo` that corresponds to `t`, a contiguous view of `flat`; None if t is not one."""
+        off = (t.data_ptr() - self.flat.data_ptr()) // 4
+        if t.data_ptr() < self.flat.data_ptr() or off + t.numel() > self.size or not t.is_contiguous():
+            return None
+        return self.lo[off: off + t.numel()].view(t.shape)
 
     def _view(self, buf, n):
         k = int(np.prod(self.shapes[n]))
@@ -103,9 +111,11 @@ class ChebLayer:
         self.need_dx = need_dx
         dev = W.device
         # K-major copies of the weights: B operand of the tcgen05 forward, and N-major operand of the data gradient
-        self.Wt = torch.empty(Fout, K, F, device=dev)
+        self.Wt, self.Wt_lo = torch.empty(Fout, K, F, device=dev), torch.empty(Fout, K, F, device=dev)
+        self.W3_lo = net.lo_of(W).view(F + C, K, Fout)
         if self.affine:
-            self.Wat = torch.empty(Fout, F, device=dev)
+            self.Wat, self.Wat_lo = torch.empty(Fout, F, device=dev), torch.empty(Fout, F, device=dev)
+            self.Wa2_lo = net.lo_of(Wa).view(F + C, Fout)
         # Where the weight gradient gets its operands (all three end in the same contraction  dW = A^T G over rows):
         #   "aside":  the forward kernel also writes the gathered basis B_k = op_k x (cape_term.stash), dW_k = B_k^T G;
         #   "gside":  the data-gradient kernel also writes H_k = op_k^T G, dW_k = x^T H_k -- all K terms in ONE pass
@@ -168,9 +178,9 @@ class ChebLayer:
         return 4 * N * s.M * Fin * (2 if self.affine else 1) + wbytes      # all dW launches of the layer together
 
     def prep(self):
-        weight_transpose(self.tp, self.W, self.F, self.K, self.Fout, self.Wt)
+        weight_transpose(self.tp, self.W, self.F, self.K, self.Fout, self.Wt, self.Wt_lo)
         if self.affine:
-            weight_transpose(self.tp, self.Wa, self.F, 1, self.Fout, self.Wat)
+            weight_transpose(self.tp, self.Wa, self.F, 1, self.Fout, self.Wat, self.Wat_lo)
 
     def fwd(self, x, ycat, out, out2=None):
         N = x.shape[0]
@@ -179,14 +189,14 @@ class ChebLayer:
         terms = []
         for k in range(K):
             t = dict(src=x, op=s.ops[k], F=F, src_rows=s.rows_in, src_stride=x.shape[2], w=self.W3[:, k, :],
-                     w_stride=K * Fout, wT=self.Wt[:, k, :], wT_stride=K * F)
+                     w_stride=K * Fout, wT=self.Wt[:, k, :], wT_stride=K * F, wT_lo=self.Wt_lo[:, k, :])
             if C:
                 t["wc"] = self.W3[F:, k, :]
             if self.stash_a[k] is not None:
                 t["stash"], t["stash_stride"] = self.stash_a[k][:N], F
             if self.affine and k == 0:
                 t["w2"], t["w2_stride"] = self.Wa2, Fout
-                t["w2T"], t["w2T_stride"] = self.Wat, F
+                t["w2T"], t["w2T_stride"], t["w2T_lo"] = self.Wat, F, self.Wat_lo
                 if C:
                     t["wc2"] = self.Wa2[F:]
             terms.append(t)
@@ -257,13 +267,14 @@ class ChebLayer:
             terms = []
             if self.affine:
                 t = dict(src=g_aff, op=s.opsT[0], F=Fout, src_rows=s.rows_out, src_stride=Fout, w=self.Wat,
-                         w_stride=F, wT=self.Wa2, wT_stride=Fout)
+                         w_stride=F, wT=self.Wa2, wT_stride=Fout, wT_lo=self.Wa2_lo)
                 if gs and self.stash_ga is not None:
                     t["stash"], t["stash_stride"] = self.stash_ga[:N], Fout
                 terms.append(t)
             for k in range(K):
                 t = dict(src=g, op=s.opsT[k], F=Fout, src_rows=s.rows_out, src_stride=Fout,
-                         w=self.Wt[:, k, :], w_stride=K * F, wT=self.W3[:, k, :], wT_stride=K * Fout)
+                         w=self.Wt[:, k, :], w_stride=K * F, wT=self.W3[:, k, :], wT_stride=K * Fout,
+                         wT_lo=self.W3_lo[:, k, :])
                 if gs and self.stash_g[k] is not None:
                     t["stash"], t["stash_stride"] = self.stash_g[k][:N], self.stash_g[k].stride(1)
                 terms.append(t)
@@ -405,10 +416,11 @@ class CapeNetwork:
         """reorder: keep the hidden activations in patch order (topology.patch_order) instead of the reference's
         vertex numbering.  Everything visible from outside (inputs, outputs, parameters, their gradients, the
         FC-layer row layout) stays in the reference numbering: the permutations are folded into the operator
-        tables of the first/last conv of each stack.  Default: on (env CAPE_REORDER=0 turns it off)."""
+        tables of the first/last conv of each stack.  Default: off (env CAPE_REORDER=1 turns it on): measured
+        neutral on B200 -- a gather batch waits for its slowest load, so a better L1 hit rate does not shorten it."""
         self.cfg = dict(cfg)
         if reorder is None:
-            reorder = os.environ.get("CAPE_REORDER", "1") != "0"
+            reorder = os.environ.get("CAPE_REORDER", "0") == "1"
         self.reorder = bool(reorder)
         self.N = int(batch_size)
         self.ref_compat = bool(ref_compat)
@@ -600,8 +612,14 @@ class CapeNetwork:
         dec = self.dec if self.affine else [l for b in self.dec for l in b.layers()]
         return self.enc + [self.enc_1x1, self.dec_1x1] + dec + [self.dec_out] + self.disc + [self.disc_pred]
 
+    def lo_of(self, t):
+        r = self.PG.lo_of(t)
+        return r if r is not None else self.PD.lo_of(t)
+
     def prep_weights(self):
-        """Re-layouts derived from the weights (transposes for the data-gradient pass); run after every update."""
+        """Copies derived from the weights (K-major transposes, tf32 low parts); run after every update."""
+        E.tf32_lo(self.tp, self.PG.flat, self.PG.lo)
+        E.tf32_lo(self.tp, self.PD.flat, self.PD.lo)
         for l in self.all_layers():
             l.prep()
 

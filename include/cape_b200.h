@@ -83,6 +83,10 @@ typedef struct {
    * "narrow side" operand (dW_k = x^T (op_k^T G)). */
   float* stash;
   int stash_stride;
+  /* optional: low parts of wT / w2T (x - tf32_trunc(x), same layout; cape_tf32_lo or cape_cheb_weight_transpose
+   * make them).  With them the wide-output kernel fetches its weight tiles by TMA (raw fp32 tile = "hi" operand). */
+  const float* wT_lo;
+  const float* w2T_lo;
 } cape_term;
 
 enum {
@@ -154,8 +158,12 @@ int cape_resample(cape_topology* t, int op, const float* x, int x_stride, float*
                   int rows_in, int F, const float* cond, int C, void* stream);
 
 /* Weight re-layout for the data-gradient pass of chebyshev5: wt[(c*K + k)*Fin + f] = w[(f*K + k)*Fout + c]
- * for f < Fin (rows of w beyond Fin*K -- the condition channels -- are not touched). */
-int cape_cheb_weight_transpose(const float* w, int Fin, int K, int Fout, float* wt, void* stream);
+ * for f < Fin (rows of w beyond Fin*K -- the condition channels -- are not touched); wt_lo (optional, same layout)
+ * receives wt - tf32_trunc(wt). */
+int cape_cheb_weight_transpose(const float* w, int Fin, int K, int Fout, float* wt, float* wt_lo, void* stream);
+
+/* lo[i] = x[i] - tf32_trunc(x[i]): the second operand of the 3xTF32 scheme for a tensor the tensor cores read raw */
+int cape_tf32_lo(const float* x, float* lo, long long n, void* stream);
 
 /* ---- elementwise helpers ------------------------------------------------------------------------ */
 /* g = dy * (y > 0 ? 1 : alpha)   (backward of leaky_relu given its output) */

@@ -159,7 +159,7 @@ def calibrated_params(specs, seed=123, fc_scale=0.05):
 
 
 def train_step(h, cfg, N=2, ref_compat=False, step=100, seed=123, dtype=torch.float32, fc_scale=0.05,
-               impose_masks=True):
+               impose_masks=True, reorder=None):
     """Full VAE+GAN update (BASELINE configs[2] at a small batch): x_hat, losses, every gradient and every
     post-update parameter vs the oracle's autograd.  impose_masks: the oracle's (leaky-)ReLUs take their branch
     decisions from the CUDA forward (about 1e-6 of all units sit within fp32 rounding of zero and would otherwise
@@ -174,7 +174,8 @@ def train_step(h, cfg, N=2, ref_compat=False, step=100, seed=123, dtype=torch.fl
     specs = param_specs(cfg, p, p_d)
     params = calibrated_params(specs, seed, fc_scale)
     batch = make_batch(N, cfg["nz"], seed=seed)
-    net = CapeNetwork(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], cfg, N, params=params, ref_compat=ref_compat)
+    net = CapeNetwork(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], cfg, N, params=params, ref_compat=ref_compat,
+                      reorder=reorder)
     tb = {k: torch.from_numpy(v) for k, v in batch.items()}
     net.set_inputs(tb["x_g"], tb["cond_g"], tb["cond2_g"], tb["eps"], tb["x_d"], tb["cond_d"], tb["cond2_d"])
     net.train_step(step=step)

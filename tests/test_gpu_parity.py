@@ -67,6 +67,17 @@ def test_train_step_simt_only(hierarchy, cfg):
         parity.set_tensor_cores(prev)
 
 
+def test_train_step_patch_vertex_order(hierarchy, cfg):
+    """Hidden activations kept in patch order (topology.patch_order): a layout change only."""
+    _assert_all(parity.train_step(hierarchy, cfg, N=2, reorder=True))
+
+
+def test_train_step_regathered_weight_gradient(hierarchy, cfg, monkeypatch):
+    """CAPE_DW_STASH=0: cape_cheb_dw gathers the basis again instead of contracting the stashed copies."""
+    monkeypatch.setenv("CAPE_DW_STASH", "0")
+    _assert_all(parity.train_step(hierarchy, cfg, N=2))
+
+
 def test_train_step_odd_batch(hierarchy, cfg):
     """Batch that does not divide the 128-row tiles; other seed."""
     _assert_all(parity.train_step(hierarchy, cfg, N=5, seed=7))
