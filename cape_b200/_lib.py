@@ -31,7 +31,8 @@ class ConvArgs(C.Structure):
 class DwArgs(C.Structure):
     _fields_ = [("N", C.c_int), ("rows_out", C.c_int), ("ncols", C.c_int), ("src", C.c_void_p), ("op", C.c_int),
                 ("F", C.c_int), ("src_rows", C.c_int), ("src_stride", C.c_int), ("g", C.c_void_p),
-                ("dw", C.c_void_p), ("dw_stride", C.c_int), ("accumulate", C.c_int)]
+                ("dw", C.c_void_p), ("dw_stride", C.c_int), ("accumulate", C.c_int), ("nops", C.c_int),
+                ("ops", C.c_int * MAX_TERMS), ("dw_term_stride", C.c_int), ("dw_col_stride", C.c_int)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/cape_b200.h

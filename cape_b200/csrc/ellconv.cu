@@ -479,9 +479,11 @@ __global__ void __launch_bounds__(NT, 2) ellconv_dw_kernel(const __grid_constant
   }
 }
 
+// rows q of the partial blocks go to  dw + (q % Fper) * dw_stride + (q / Fper) * term_stride  (several terms at once)
 __global__ void __launch_bounds__(1024) reduce_splits_kernel(const float* __restrict__ ws, int nsplit, int F, int ncols,
                                                              float* __restrict__ dw, long long dw_stride,
-                                                             int accumulate) {
+                                                             int accumulate, int Fper, long long term_stride,
+                                                             long long col_stride) {
   // 64 consecutive elements x 16 split lanes per CTA; fixed summation order (deterministic)
   __shared__ float red[16][64];
   const long long total = (long long)F * ncols;
@@ -497,8 +499,8 @@ __global__ void __launch_bounds__(1024) reduce_splits_kernel(const float* __rest
       s = 0.f;
 #pragma unroll
       for (int k = 0; k < 16; ++k) s += red[k][el];
-      const int f = (int)(e / ncols), c = (int)(e % ncols);
-      float* o = dw + (size_t)f * dw_stride + c;
+      const int q = (int)(e / ncols), c = (int)(e % ncols);
+      float* o = dw + (size_t)(q % Fper) * dw_stride + (size_t)(q / Fper) * term_stride + (size_t)c * col_stride;
       *o = accumulate ? (*o + s) : s;
     }
     __syncthreads();
@@ -701,6 +703,8 @@ extern "C" int cape_cheb_fwd(cape_topology* t, const cape_conv_args* a, void* st
   {
     int rc = launch_thin_fwd(t, p, dual, st);             // <= 4 input channels: streaming kernel
     if (rc != 0) return rc < 0 ? rc : 0;
+    rc = launch_thinout_fwd(t, p, dual, st);              // <= 4 output columns: contract first, then gather
+    if (rc != 0) return rc < 0 ? rc : 0;
     rc = launch_ellconv_tc(t, p, dual, st);               // tcgen05 path when eligible (writes the stashes itself)
     if (rc != 0) return rc < 0 ? rc : 0;
   }
@@ -729,17 +733,53 @@ extern "C" int cape_cheb_fwd(cape_topology* t, const cape_conv_args* a, void* st
   return 0;
 }
 
+static int dw_single(cape_topology* t, const cape_dw_args* a, void* stream);
+
 extern "C" int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* stream) {
   CAPE_REQUIRE(t && a, "null handle/args");
   CAPE_REQUIRE(a->N > 0 && a->rows_out > 0 && a->ncols > 0 && a->F > 0, "empty problem");
   CAPE_REQUIRE(a->src && a->g && a->dw, "null pointer");
-  CAPE_REQUIRE(a->src_stride >= a->F && a->dw_stride >= a->ncols, "bad strides");
+  CAPE_REQUIRE(a->src_stride >= a->F && (a->dw_stride >= a->ncols || a->dw_col_stride > 1), "bad strides");
+  if (a->nops <= 0) {
+    CAPE_REQUIRE(a->dw_col_stride <= 1, "dw_col_stride needs the multi-term form (nops > 0)");
+    return dw_single(t, a, stream);
+  }
+  CAPE_REQUIRE(a->nops <= CAPE_MAX_TERMS, "nops out of range");
+  // several terms of one layer: one pass over g when the input is thin, else term by term
+  OpView ops[CAPE_MAX_TERMS];
+  for (int j = 0; j < a->nops; ++j)
+    if (get_op(t, a->ops[j], a->rows_out, a->src_rows, &ops[j]) != 0) return -1;
+  int ns = 1;
+  int rc = launch_thin_dw(t, a, ops, a->nops, &ns, (cudaStream_t)stream);
+  if (rc < 0) return rc;
+  if (rc == 1) {
+    const long long total = (long long)a->nops * a->F * a->ncols;
+    long long blocks = (total + 63) / 64;
+    if (blocks > 8LL * t->sm_count) blocks = 8LL * t->sm_count;
+    reduce_splits_kernel<<<(unsigned)blocks, 1024, 0, (cudaStream_t)stream>>>(
+        (const float*)t->workspace, ns, a->nops * a->F, a->ncols, a->dw, a->dw_stride, a->accumulate, a->F,
+        a->dw_term_stride, a->dw_col_stride > 0 ? a->dw_col_stride : 1);
+    CAPE_CHECK_CUDA(cudaGetLastError());
+    cape::count_launches(1);
+    return 0;
+  }
+  CAPE_REQUIRE(a->dw_col_stride <= 1, "dw_col_stride is only implemented for thin inputs (F <= 4, ncols 32..256)");
+  for (int j = 0; j < a->nops; ++j) {
+    cape_dw_args b = *a;
+    b.nops = 0; b.op = a->ops[j]; b.dw = a->dw + (size_t)j * a->dw_term_stride;
+    rc = dw_single(t, &b, stream);
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+static int dw_single(cape_topology* t, const cape_dw_args* a, void* stream) {
   DwParams p{};
   if (get_op(t, a->op, a->rows_out, a->src_rows, &p.op) != 0) return -1;
   {
     int ns = 1;
     bool always_reduce = false;
-    int rc = launch_thin_dw(t, a, p.op, &ns, (cudaStream_t)stream);               // <= 4 input channels
+    int rc = launch_thin_dw(t, a, &p.op, 1, &ns, (cudaStream_t)stream);           // <= 4 input channels
     if (rc < 0) return rc;
     if (rc == 1) always_reduce = true;                                            // partials always in the workspace
     else rc = launch_dw_dense_tma(t, a, p.op, &ns, (cudaStream_t)stream);         // dense operands: TMA + tcgen05
@@ -753,7 +793,7 @@ extern "C" int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* strea
         if (blocks > 8LL * t->sm_count) blocks = 8LL * t->sm_count;
         reduce_splits_kernel<<<(unsigned)blocks, 1024, 0, (cudaStream_t)stream>>>((const float*)t->workspace, ns, a->F,
                                                                                  a->ncols, a->dw, a->dw_stride,
-                                                                                 a->accumulate);
+                                                                                 a->accumulate, a->F, 0, 1);
         CAPE_CHECK_CUDA(cudaGetLastError());
         cape::count_launches(1);
       }
@@ -790,7 +830,7 @@ extern "C" int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* strea
     long long blocks = (total + 63) / 64;
     if (blocks > 8LL * t->sm_count) blocks = 8LL * t->sm_count;
     reduce_splits_kernel<<<(unsigned)blocks, 1024, 0, st>>>((const float*)t->workspace, (int)nsplit, a->F, a->ncols, a->dw,
-                                                  a->dw_stride, a->accumulate);
+                                                  a->dw_stride, a->accumulate, a->F, 0, 1);
     CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
   }

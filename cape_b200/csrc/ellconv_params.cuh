@@ -53,7 +53,10 @@ int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cu
 bool tensor_cores_enabled();
 // thin-input layers (thin.cu): sources with <= 4 channels.  1 = launched, 0 = not eligible, <0 = error
 int launch_thin_fwd(const cape_topology* t, const ConvParams& p, bool dual, cudaStream_t st);
-int launch_thin_dw(const cape_topology* t, const cape_dw_args* a, const OpView& op, int* nsplit_out, cudaStream_t st);
+// thin-output layers (<= 4 columns): project, then combine
+int launch_thinout_fwd(const cape_topology* t, const ConvParams& p, bool dual, cudaStream_t st);
+int launch_thin_dw(const cape_topology* t, const cape_dw_args* a, const OpView* ops, int nops, int* nsplit_out,
+                   cudaStream_t st);
 // tcgen05 weight-gradient path (ellconv_dw_tc.cu): 1 = launched (partials in the workspace if *nsplit_out > 1)
 int launch_ellconv_dw_tc(const cape_topology* t, const cape_dw_args* a, const OpView& op, int* nsplit_out,
                          cudaStream_t st);
@@ -63,7 +66,8 @@ int launch_dw_dense_tma(const cape_topology* t, const cape_dw_args* a, const OpV
                         cudaStream_t st);
 // experiment knobs (cape_set_tuning): [1] = 1 disables the TMA dense-dW kernel, [2] = its lo-part mode (1 = rna, wrong
 // on purpose: shows the tensor core truncates), [3] = 2: 128- instead of 256-wide G sub-tiles for wide outputs, [4] = 1: weight tiles of the wide conv kernel by the
-// producer warps instead of TMA
+// producer warps instead of TMA, [6] = 1: identity-term basis
+// tiles by the producer warps instead of TMA, [7] = 1: thin-output layers on the generic kernels
 extern int g_tuning[8];
 
 }  // namespace cape

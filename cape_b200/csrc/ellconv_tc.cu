@@ -120,6 +120,7 @@ constexpr int TC_TMA_TERMS = 4;
 // 19 bits), [1] wT_lo, [2] w2T, [3] w2T_lo.  Boxes of 32 k x BN columns, SWIZZLE_128B: a box lands as one operand tile.
 struct BMaps {
   CUtensorMap m[TC_TMA_TERMS][4];
+  CUtensorMap a[TC_TMA_TERMS];     // identity-operator terms: the source rows themselves, boxes of 32 f x 128 rows
 };
 
 // Persistent kernel.  A CTA loops over 128-row output tiles (all output columns each).  Three roles run
@@ -130,7 +131,7 @@ struct BMaps {
 template <int BN, bool DUAL>
 __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid_constant__ ConvParams p,
                                                                     const __grid_constant__ BMaps maps, int nct,
-                                                                    int tmem_cols, int nbuf, int ntiles, int tma_b) {
+                                                                    int tmem_cols, int nbuf, int ntiles, int tma_b, int tma_a) {
   using Cfg = TcCfg<BN, DUAL>;
   constexpr int SA = Cfg::A_STAGES, SB = Cfg::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -141,12 +142,13 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
   float* qs_all = reinterpret_cast<float*>(b_ring + SB * Cfg::B_STAGE_BYTES);
   // a_full[4] a_empty[4] b_full[4] b_empty[4] t_full[2] t_empty[2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(qs_all + QS_FLOATS);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * MAX_STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 * MAX_STAGES + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + MAX_STAGES);
   const uint32_t bar_bfull = smem_u32(bars + 2 * MAX_STAGES), bar_bempty = smem_u32(bars + 3 * MAX_STAGES);
   const uint32_t bar_tfull = smem_u32(bars + 4 * MAX_STAGES), bar_tempty = smem_u32(bars + 4 * MAX_STAGES + 2);
+  const uint32_t bar_atma = smem_u32(bars + 4 * MAX_STAGES + 4);      // hi tile of an identity-term chunk landed (TMA)
 
   if (warp == TC_PROD_WARPS) {
     if (lane == 0) {
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
         mbar_init(bar_bempty + 8 * s, 1);
       }
       for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, TC_EPI_WARPS); }
+      for (int s = 0; s < SA; ++s) mbar_init(bar_atma + 8 * s, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -205,6 +208,30 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
           };
           if (!tma_b) load_b(0);
           // ---- A chunk: gather 4 rows per thread, split, store swizzled
+          if ((tma_a >> t) & 1) {
+            // identity term: the TMA warp put the raw rows (= hi operand) in place; derive the lo tile from them
+            mbar_wait(bar_atma + 8 * sa, pha);
+            char* a_hi = a_ring + (size_t)sa * Cfg::A_STAGE_BYTES;
+            char* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = rs + 32 * i;
+              const uint32_t off = (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4));
+              const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
+              float4 l;
+              l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+              l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+              l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+              l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+              *reinterpret_cast<float4*>(a_lo + off) = l;
+              if (tm.stash != nullptr && rn[i] >= 0 && f < tm.F)
+                *reinterpret_cast<float4*>(tm.stash + (size_t)(row0 + row) * tm.stash_stride + f) = v;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
+            if (++sa == SA) { sa = 0; pha ^= 1; }
+          } else {
           mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
           {
             char* a_hi = a_ring + (size_t)sa * Cfg::A_STAGE_BYTES;
@@ -237,6 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
             if (++sa == SA) { sa = 0; pha ^= 1; }
+          }
           }
           // ---- B chunks: one [BN x 32] K-major weight tile (hi/lo) per column sub-tile (unless the TMA warp does it)
           for (int cs = 0; cs < (tma_b ? 0 : nct); ++cs) {
@@ -278,6 +306,7 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
         for (int t = 0; t < p.nterms; ++t) {
           const bool has2 = DUAL && p.terms[t].w2T != nullptr;
           for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+            if ((tma_a >> t) & 1) mbar_wait(bar_atma + 8 * sa, pha);      // hi tile written by TMA
             mbar_wait(bar_afull + 8 * sa, pha);
             const uint32_t aaddr = smem_u32(a_ring + (size_t)sa * Cfg::A_STAGE_BYTES);
             const uint64_t a_hi = make_desc(aaddr), a_lo = make_desc(aaddr + A_TILE_BYTES);
@@ -316,18 +345,22 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
     __syncwarp();
   } else if (warp == TC_TMA_WARP) {
     // =========================== TMA issuer: weight tiles (hi = raw fp32, lo = pre-split copy) ===========================
-    if (tma_b && lane == 0) {
-      for (int t = 0; t < p.nterms; ++t) {
-        tc::tma_prefetch_desc(&maps.m[t][0]);
-        tc::tma_prefetch_desc(&maps.m[t][1]);
-      }
-      int sb = 0;
-      uint32_t phb = 0;
+    if ((tma_b || tma_a) && lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row0 = tile * BM;
         for (int t = 0; t < p.nterms; ++t) {
           const bool has2 = DUAL && p.terms[t].w2T != nullptr;
+          const bool a_here = (tma_a >> t) & 1;
           for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
-            for (int cs = 0; cs < nct; ++cs) {
+            if (a_here) {
+              mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
+              tc::mbar_arrive_expect_tx(bar_atma + 8 * sa, (uint32_t)A_TILE_BYTES);
+              tc::tma_load_2d(smem_u32(a_ring + (size_t)sa * Cfg::A_STAGE_BYTES), &maps.a[t], f0, row0, bar_atma + 8 * sa);
+            }
+            if (++sa == SA) { sa = 0; pha ^= 1; }
+            for (int cs = 0; cs < (tma_b ? nct : 0); ++cs) {
               mbar_wait(bar_bempty + 8 * sb, phb ^ 1);
               tc::mbar_arrive_expect_tx(bar_bfull + 8 * sb, (uint32_t)((has2 ? 4 : 2) * Cfg::B_TILE_BYTES));
               const uint32_t dst = smem_u32(b_ring + (size_t)sb * Cfg::B_STAGE_BYTES);
@@ -515,7 +548,25 @@ int launch_one(const cape_topology* t, const ConvParams& p, cudaStream_t st) {
           !make_wmap(&maps.m[i][3], tm.w2T_lo, tm.F, p.ncols, tm.w2T_stride, BN)) { tma_b = 0; break; }
     }
   }
-  ellconv_tc_kernel<BN, DUAL><<<grid, TC_THREADS3, Cfg::SMEM_BYTES, st>>>(p, maps, nct, tmem_cols, nbuf, ntiles, tma_b);
+  // basis tiles of identity-operator terms (plain source rows) by TMA as well
+  int tma_a = 0;
+  if (encode_fn() != nullptr && g_tuning[6] != 1 && p.total_rows < (1LL << 31)) {
+    for (int i = 0; i < p.nterms && i < TC_TMA_TERMS; ++i) {
+      const TermDev& tm = p.terms[i];
+      if (tm.op.idx != nullptr || tm.src_rows != p.rows_out || !tm.vec) continue;
+      EncodeTiledFn fn = encode_fn();
+      const cuuint64_t dims[2] = {(cuuint64_t)tm.F, (cuuint64_t)p.total_rows};
+      const cuuint64_t strides[1] = {(cuuint64_t)tm.src_stride * sizeof(float)};
+      const cuuint32_t box[2] = {32, (cuuint32_t)BM};
+      const cuuint32_t estr[2] = {1, 1};
+      if (fn(&maps.a[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(tm.src), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+        tma_a |= 1 << i;
+    }
+  }
+  ellconv_tc_kernel<BN, DUAL><<<grid, TC_THREADS3, Cfg::SMEM_BYTES, st>>>(p, maps, nct, tmem_cols, nbuf, ntiles, tma_b,
+                                                                        tma_a);
   CAPE_CHECK_CUDA(cudaGetLastError());
   count_launches(1);
   return 1;

@@ -187,9 +187,16 @@ def cheb_call(tp, N, rows_out, ncols, terms, out, out2=None, cond=None, epilogue
         check(tp.lib.cape_cheb_fwd(tp.h, C.byref(a), _stream()))
 
 
-def cheb_dw(tp, N, rows_out, ncols, src, op, F, src_rows, src_stride, g, dw, dw_stride, accumulate=False, tag=None):
+def cheb_dw(tp, N, rows_out, ncols, src, op, F, src_rows, src_stride, g, dw, dw_stride, accumulate=False, tag=None,
+            dw_term_stride=0, dw_col_stride=0):
+    """op: one operator id, or a list of them (all terms of a layer, term j written to dw + j * dw_term_stride)."""
     a = DwArgs()
     a.N, a.rows_out, a.ncols = N, rows_out, ncols
+    if isinstance(op, (list, tuple)):
+        a.nops, a.dw_term_stride, a.dw_col_stride = len(op), dw_term_stride, dw_col_stride
+        for j, o in enumerate(op):
+            a.ops[j] = o
+        op = op[0]
     a.src, a.op, a.F, a.src_rows, a.src_stride = src.data_ptr(), op, F, src_rows, src_stride
     a.g, a.dw, a.dw_stride, a.accumulate = g.data_ptr(), dw.data_ptr(), dw_stride, 1 if accumulate else 0
     with _Prof("ellconv_dw", tag):

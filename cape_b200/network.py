@@ -227,10 +227,19 @@ class ChebLayer:
                     cheb_dw(tp, N, s.rows_out, Fout, x, -1, F, s.rows_in, sx, g_aff, self.gWa2, Fout, tag=tg)
                 else:
                     cheb_dw(tp, N, s.rows_out, Fout, B[:N], -1, F, s.rows_out, F, g_aff, self.gWa2, Fout, tag=tg)
+        elif (want_dw and mode == "gather" and Fout <= 4 and not self.affine and F in (32, 64, 128, 256) and sx == F
+              and K <= 4):
+            # thin OUTPUT: swap the roles -- operators on the narrow gradient (H_k = op_k^T g), one pass over x;
+            # dW_k[f, c] = sum_r x[r, f] H_k[r, c] lands in the [F, K, Fout] layout through the three strides
+            cheb_dw(tp, N, s.rows_in, F, g, list(s.opsT), Fout, s.rows_out, Fout, x, self.gW3, 1,
+                    tag=(self.name + ":dW", self.alg_bytes(N, "dW")), dw_term_stride=Fout, dw_col_stride=K * Fout)
         elif want_dw and mode == "gather":
-            nl = K + (1 if self.affine else 0)
+            nl = (1 if F <= 4 else K) + (1 if self.affine else 0)
             tg = (self.name + ":dW", self.alg_bytes(N, "dW") / nl)
-            for k in range(K):
+            if F <= 4:          # thin input: all K terms in one pass over g
+                cheb_dw(tp, N, s.rows_out, Fout, x, list(s.ops), F, s.rows_in, sx, g, self.gW3, K * Fout, tag=tg,
+                        dw_term_stride=Fout)
+            for k in range(K if F > 4 else 0):
                 cheb_dw(tp, N, s.rows_out, Fout, x, s.ops[k], F, s.rows_in, sx, g, self.gW3[:, k, :], K * Fout, tag=tg)
             if self.affine:
                 cheb_dw(tp, N, s.rows_out, Fout, x, s.ops[0], F, s.rows_in, sx, g_aff, self.gWa2, Fout, tag=tg)

@@ -132,6 +132,16 @@ typedef struct {
   const float* g;      /* [N, rows_out, ncols] */
   float* dw; int dw_stride;
   int accumulate;      /* 0: overwrite, 1: add */
+  /* optional: all the terms of one layer in one call (one pass over g when the input is thin): operators ops[0..nops)
+   * instead of `op`, term j written to dw + j * dw_term_stride.  nops = 0: the single term `op`. */
+  int nops;
+  int ops[CAPE_MAX_TERMS];
+  int dw_term_stride;
+  /* with nops > 0 and a thin input (F <= 4): element (f, c) of term j goes to
+   * dw[j * dw_term_stride + f * dw_stride + c * dw_col_stride]  (0 = 1).  Lets the caller swap the operand roles for
+   * thin-OUTPUT layers -- dW_j^T = (op_j^T g)^T x, the operators applied to the 3-channel gradient -- and still get
+   * dW in the [Fin, K, Fout] layout. */
+  int dw_col_stride;
 } cape_dw_args;
 int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* stream);
 
