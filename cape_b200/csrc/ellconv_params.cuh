@@ -66,7 +66,7 @@ int launch_dw_dense_tma(const cape_topology* t, const cape_dw_args* a, const OpV
                         cudaStream_t st);
 // experiment knobs (cape_set_tuning): [1] = 1 disables the TMA dense-dW kernel, [2] = its lo-part mode (1 = rna, wrong
 // on purpose: shows the tensor core truncates), [3] = 2: 128- instead of 256-wide G sub-tiles for wide outputs, [4] = 1: weight tiles of the wide conv kernel by the
-// producer warps instead of TMA, [6] = 1: identity-term basis
+// producer warps instead of TMA, [5] = 1: one narrow-kernel CTA per SM (bigger L1), [6] = 1: identity-term basis
 // tiles by the producer warps instead of TMA, [7] = 1: thin-output layers on the generic kernels
 extern int g_tuning[8];
 

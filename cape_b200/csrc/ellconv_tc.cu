@@ -519,6 +519,25 @@ bool make_wmap(CUtensorMap* m, const float* base, int F, int ncols, int stride, 
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// tensor maps of the pre-split weight copies of every term (cape_term.wT_lo); false: the producers load the weights
+template <bool DUAL>
+bool build_wmaps(const ConvParams& p, int bn, BMaps* maps) {
+  if (p.nterms > TC_TMA_TERMS) return false;
+  for (int i = 0; i < p.nterms; ++i) {
+    const TermDev& tm = p.terms[i];
+    if (tm.wT_lo == nullptr || (tm.w2T != nullptr && tm.w2T_lo == nullptr)) return false;
+    if (!make_wmap(&maps->m[i][0], tm.wT, tm.F, p.ncols, tm.wT_stride, bn) ||
+        !make_wmap(&maps->m[i][1], tm.wT_lo, tm.F, p.ncols, tm.wT_stride, bn))
+      return false;
+    if (DUAL && tm.w2T != nullptr) {
+      if (!make_wmap(&maps->m[i][2], tm.w2T, tm.F, p.ncols, tm.w2T_stride, bn) ||
+          !make_wmap(&maps->m[i][3], tm.w2T_lo, tm.F, p.ncols, tm.w2T_stride, bn))
+        return false;
+    }
+  }
+  return true;
+}
+
 template <int BN, bool DUAL>
 int launch_one(const cape_topology* t, const ConvParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, DUAL>;
@@ -537,17 +556,7 @@ int launch_one(const cape_topology* t, const ConvParams& p, cudaStream_t st) {
   const int grid = ntiles < t->sm_count ? ntiles : t->sm_count;
   // weight tiles by TMA when every term comes with pre-split copies (cape_term.wT_lo)
   static BMaps maps;                      // host-side scratch, copied into the launch
-  int tma_b = (p.nterms <= TC_TMA_TERMS && g_tuning[4] != 1) ? 1 : 0;
-  for (int i = 0; i < p.nterms && tma_b; ++i) {
-    const TermDev& tm = p.terms[i];
-    if (tm.wT_lo == nullptr || (tm.w2T != nullptr && tm.w2T_lo == nullptr)) { tma_b = 0; break; }
-    if (!make_wmap(&maps.m[i][0], tm.wT, tm.F, p.ncols, tm.wT_stride, BN) ||
-        !make_wmap(&maps.m[i][1], tm.wT_lo, tm.F, p.ncols, tm.wT_stride, BN)) { tma_b = 0; break; }
-    if (DUAL && tm.w2T != nullptr) {
-      if (!make_wmap(&maps.m[i][2], tm.w2T, tm.F, p.ncols, tm.w2T_stride, BN) ||
-          !make_wmap(&maps.m[i][3], tm.w2T_lo, tm.F, p.ncols, tm.w2T_stride, BN)) { tma_b = 0; break; }
-    }
-  }
+  const int tma_b = g_tuning[4] != 1 && build_wmaps<DUAL>(p, BN, &maps);
   // basis tiles of identity-operator terms (plain source rows) by TMA as well
   int tma_a = 0;
   if (encode_fn() != nullptr && g_tuning[6] != 1 && p.total_rows < (1LL << 31)) {
@@ -589,7 +598,8 @@ struct Tc2Cfg {
 // warps double as the epilogue), <= 112 registers and ~106 KB of shared memory, so that TWO CTAs share an SM: twice
 // the warps hide the latency of the neighbour gather, and one CTA's epilogue overlaps the other's main loop.
 template <int BN, bool DUAL>
-__global__ void __launch_bounds__(TC_THREADS, 2) ellconv_tc2_kernel(const __grid_constant__ ConvParams p, int nct,
+__global__ void __launch_bounds__(TC_THREADS + 32, 2) ellconv_tc2_kernel(const __grid_constant__ ConvParams p,
+                                                                        const __grid_constant__ BMaps maps, int tma_b, int nct,
                                                                    int tmem_cols) {
   using Cfg = Tc2Cfg<BN, DUAL>;
   constexpr int SA = Cfg::A_STAGES, SB = Cfg::B_STAGES;
@@ -618,7 +628,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) ellconv_tc2_kernel(const __grid
   if (warp == TC_PROD_WARPS) {
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, TC_PROD_WARPS); mbar_init(bar_aempty + 8 * s, 1); }
-      for (int s = 0; s < SB; ++s) { mbar_init(bar_bfull + 8 * s, TC_PROD_WARPS); mbar_init(bar_bempty + 8 * s, 1); }
+      for (int s = 0; s < SB; ++s) { mbar_init(bar_bfull + 8 * s, tma_b ? 1 : TC_PROD_WARPS); mbar_init(bar_bempty + 8 * s, 1); }
       mbar_init(bar_accum, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -677,8 +687,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) ellconv_tc2_kernel(const __grid
           if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
           if (++sa == SA) { sa = 0; pha ^= 1; }
         }
-        // ---- B chunks: one [BN x 32] K-major weight tile (hi/lo) per column sub-tile
-        for (int cs = 0; cs < nct; ++cs) {
+        // ---- B chunks: one [BN x 32] K-major weight tile (hi/lo) per column sub-tile (unless the TMA warp does it)
+        for (int cs = 0; cs < (tma_b ? 0 : nct); ++cs) {
           mbar_wait(bar_bempty + 8 * sb, phb ^ 1);
           char* b_hi = b_ring + (size_t)sb * Cfg::B_STAGE_BYTES;
           char* b_lo = b_hi + Cfg::B_TILE_BYTES;
@@ -799,6 +809,30 @@ __global__ void __launch_bounds__(TC_THREADS, 2) ellconv_tc2_kernel(const __grid
       }
     }
     tc_fence_before();
+  } else if (warp == TC_PROD_WARPS + 1) {
+    // =========================== TMA issuer: weight tiles (hi = raw fp32, lo = pre-split copy) ===========================
+    if (tma_b && lane == 0) {
+      int sb = 0;
+      uint32_t phb = 0;
+      for (int t = 0; t < p.nterms; ++t) {
+        const bool has2 = DUAL && p.terms[t].w2T != nullptr;
+        for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+          for (int cs = 0; cs < nct; ++cs) {
+            mbar_wait(bar_bempty + 8 * sb, phb ^ 1);
+            tc::mbar_arrive_expect_tx(bar_bfull + 8 * sb, (uint32_t)((has2 ? 4 : 2) * Cfg::B_TILE_BYTES));
+            const uint32_t dst = smem_u32(b_ring + (size_t)sb * Cfg::B_STAGE_BYTES);
+            tc::tma_load_2d(dst, &maps.m[t][0], f0, cs * BN, bar_bfull + 8 * sb);
+            tc::tma_load_2d(dst + Cfg::B_TILE_BYTES, &maps.m[t][1], f0, cs * BN, bar_bfull + 8 * sb);
+            if (has2) {
+              tc::tma_load_2d(dst + 2 * Cfg::B_TILE_BYTES, &maps.m[t][2], f0, cs * BN, bar_bfull + 8 * sb);
+              tc::tma_load_2d(dst + 3 * Cfg::B_TILE_BYTES, &maps.m[t][3], f0, cs * BN, bar_bfull + 8 * sb);
+            }
+            if (++sb == SB) { sb = 0; phb ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // =========================== MMA issuer (one elected lane) ===========================
     if (lane == 0) {
@@ -859,14 +893,18 @@ int launch_two(const ConvParams& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     CAPE_CHECK_CUDA(cudaFuncSetAttribute(ellconv_tc2_kernel<BN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES));
+                                         Cfg::SMEM_BYTES + 24 * 1024));
     configured = true;
   }
   const int nct = (p.ncols + BN - 1) / BN;
   int cols = (DUAL ? 2 : 1) * nct * BN, tmem_cols = 32;
   while (tmem_cols < cols) tmem_cols *= 2;
   dim3 grid((unsigned)((p.total_rows + BM - 1) / BM), 1);
-  ellconv_tc2_kernel<BN, DUAL><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, nct, tmem_cols);
+  // experiment [5] = 1: pad the request so that only one CTA fits per SM and the L1 gets the rest
+  const int smem = Cfg::SMEM_BYTES + (g_tuning[5] == 1 ? 24 * 1024 : 0);
+  static BMaps maps;
+  const int tma_b = g_tuning[4] != 1 && build_wmaps<DUAL>(p, BN, &maps);
+  ellconv_tc2_kernel<BN, DUAL><<<grid, TC_THREADS + 32, smem, st>>>(p, maps, tma_b, nct, tmem_cols);
   CAPE_CHECK_CUDA(cudaGetLastError());
   count_launches(1);
   return 1;

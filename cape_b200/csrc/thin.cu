@@ -277,31 +277,42 @@ __global__ void __launch_bounds__(256) thinout_project_kernel(const float* __res
     Ws[e] = (t < nterms && c < ncols) ? __ldg(wt.w[t] + (size_t)f * wt.ws[t] + c) : 0.f;
   }
   __syncthreads();
+  // lpr lanes share a source row (F / 4 of them are busy; narrow sources put 2 or 4 rows on a warp)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lpr = F >= 128 ? 32 : (F >= 64 ? 16 : 8), rpw = 32 / lpr;
+  const int sub = lane / lpr, l = lane % lpr;
   const int nq = nterms * 4;
-  for (long long R = (long long)blockIdx.x * 8 + warp; R < nrows; R += (long long)gridDim.x * 8) {
+  for (long long R0 = ((long long)blockIdx.x * 8 + warp) * rpw; R0 < nrows; R0 += (long long)gridDim.x * 8 * rpw) {
+    const long long R = R0 + sub;
     float acc[TO_ZW];
 #pragma unroll
     for (int q = 0; q < TO_ZW; ++q) acc[q] = 0.f;
-    const float* row = src + (size_t)R * src_stride;
-    for (int f = lane * 4; f < F; f += 128) {
-      const float4 v = ldg4(row + f);
+    if (R < nrows) {
+      const float* row = src + (size_t)R * src_stride;
+      for (int f = l * 4; f < F; f += lpr * 4) {
+        const float4 v = ldg4(row + f);
 #pragma unroll
-      for (int q = 0; q < TO_ZW; ++q) {
-        if (q < nq) {
-          const float4 w = *reinterpret_cast<const float4*>(&Ws[q * F + f]);
-          acc[q] += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+        for (int q = 0; q < TO_ZW; ++q) {
+          if (q < nq) {
+            const float4 w = *reinterpret_cast<const float4*>(&Ws[q * F + f]);
+            acc[q] += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+          }
         }
       }
     }
 #pragma unroll
     for (int q = 0; q < TO_ZW; ++q) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+      for (int o = 16; o > 0; o >>= 1)
+        if (o < lpr) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
     }
-    if (lane < 4)
-      *reinterpret_cast<float4*>(z + (size_t)R * TO_ZW + lane * 4) =
-          make_float4(acc[lane * 4], acc[lane * 4 + 1], acc[lane * 4 + 2], acc[lane * 4 + 3]);
+    if (R < nrows) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (l == g)
+          *reinterpret_cast<float4*>(z + (size_t)R * TO_ZW + g * 4) =
+              make_float4(acc[g * 4], acc[g * 4 + 1], acc[g * 4 + 2], acc[g * 4 + 3]);
+    }
   }
 }
 
@@ -322,8 +333,28 @@ struct ThinOutParams {
   float* out;
 };
 
+constexpr int TO_MAXS = 8;        // samples a 256-row block may touch
+
 __global__ void __launch_bounds__(256) thinout_combine_kernel(const __grid_constant__ ThinOutParams p) {
-  const long long R = (long long)blockIdx.x * 256 + threadIdx.x;
+  __shared__ float qs[TO_MAXS][TO_MAXT][4];
+  const long long R0 = (long long)blockIdx.x * 256;
+  const int n_first = (int)(R0 / p.rows_out);
+  if (p.nslots > 0) {
+    // condition vectors of the samples in this block: q[s][slot][c] = cond[n_first+s,:] @ Wc_slot[:, c]
+    const long long rlast = min(p.total_rows, R0 + 256) - 1;
+    const int S = (int)(rlast / p.rows_out) - n_first + 1;
+    for (int o = threadIdx.x; o < S * p.nslots * 4; o += 256) {
+      const int c = o & 3, slot = (o >> 2) % p.nslots, s = (o >> 2) / p.nslots;
+      float q = 0.f;
+      if (c < p.ncols) {
+        const float* y = p.cond + (size_t)(n_first + s) * p.C;
+        for (int j = 0; j < p.C; ++j) q = fmaf(__ldg(y + j), __ldg(p.slot_w[slot] + (size_t)j * p.slot_ws[slot] + c), q);
+      }
+      qs[s][slot][c] = q;
+    }
+    __syncthreads();
+  }
+  const long long R = R0 + threadIdx.x;
   if (R >= p.total_rows) return;
   const int n = (int)(R / p.rows_out), r = (int)(R % p.rows_out);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -353,12 +384,8 @@ __global__ void __launch_bounds__(256) thinout_combine_kernel(const __grid_const
   for (int s = 0; s < p.nslots; ++s) {
     const OpView& op = p.op[p.slot_term[s]];
     const float coef = op.rowsum ? __ldg(op.rowsum + r) : 1.f;
-    const float* y = p.cond + (size_t)n * p.C;
-    for (int c = 0; c < p.ncols; ++c) {
-      float q = 0.f;
-      for (int j = 0; j < p.C; ++j) q = fmaf(__ldg(y + j), __ldg(p.slot_w[s] + (size_t)j * p.slot_ws[s] + c), q);
-      acc[c] = fmaf(coef, q, acc[c]);
-    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = fmaf(coef, qs[n - n_first][s][c], acc[c]);
   }
   for (int c = 0; c < p.ncols; ++c) {
     float v = acc[c];
@@ -439,7 +466,7 @@ int launch_thinout_fwd(const cape_topology* t, const ConvParams& p, bool dual, c
         tm.stash != nullptr)
       return 0;
   }
-  if (p.nslots > TO_MAXT) return 0;
+  if (p.nslots > TO_MAXT || (p.nslots > 0 && 255 / p.rows_out + 2 > TO_MAXS)) return 0;
   for (int s = 0; s < p.nslots; ++s)
     if (p.slot_acc[s] != 0) return 0;
   const long long nsrc = (long long)p.N * t0.src_rows;
@@ -455,7 +482,7 @@ int launch_thinout_fwd(const cape_topology* t, const ConvParams& p, bool dual, c
     configured = true;
   }
   long long blocks = (nsrc + 7) / 8;
-  if (blocks > 16LL * t->sm_count) blocks = 16LL * t->sm_count;
+  if (blocks > 8LL * t->sm_count) blocks = 8LL * t->sm_count;
   thinout_project_kernel<<<(unsigned)blocks, 256, smem, st>>>(
       t0.src, t0.F, t0.src_stride, nsrc, p.nterms, p.ncols, h, z);
   CAPE_CHECK_CUDA(cudaGetLastError());

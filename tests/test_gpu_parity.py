@@ -68,7 +68,7 @@ def test_train_step_simt_only(hierarchy, cfg):
 
 
 def test_train_step_patch_vertex_order(hierarchy, cfg):
-    """Hidden activations kept in patch order (topology.patch_order): a layout change only."""
+    """reorder=True: hidden activations kept in patch order (topology.patch_order) -- a layout change only."""
     _assert_all(parity.train_step(hierarchy, cfg, N=2, reorder=True))
 
 

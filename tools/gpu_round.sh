@@ -13,9 +13,12 @@ echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 450 -c 900 --csv --log-file gpurun_out/launches.csv \
    python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline --no-profile > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log | cut -c1-200; wc -l gpurun_out/launches.csv
-echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:ellconv_tc_kernel -s 30 -c 4 -o gpurun_out/prof_ellconv_tc \
-   python bench.py --steps 1 --warmup 0 --no-graph --no-cpu-baseline --no-profile > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_full.log
+echo "== ncu full (wide conv, narrow conv, dense dW)"
+for spec in "conv_wide:ellconv_tc_kernel:12" "conv_narrow:ellconv_tc2_kernel:20" "dw_dense:dw_dense_kernel:16"; do
+  name="${spec%%:*}"; rest="${spec#*:}"; kern="${rest%%:*}"; skip="${rest#*:}"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kern -s $skip -c 4 -f -o gpurun_out/prof_$name \
+     python bench.py --steps 1 --warmup 0 --no-graph --no-cpu-baseline --no-profile > gpurun_out/ncu_$name.log 2>&1
+  tail -1 gpurun_out/ncu_$name.log | cut -c1-150
+done
 fi
 ls -la gpurun_out | head -30

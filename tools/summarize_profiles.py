@@ -78,6 +78,7 @@ WANT = ["Kernel Name", "launch__grid_size", "launch__registers_per_thread", "gpu
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+traffic = {}
 for rep in sorted(f for f in os.listdir(G) if f.endswith(".ncu-rep")):
     out = subprocess.run(["ncu", "-i", os.path.join(G, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -92,6 +93,20 @@ for rep in sorted(f for f in os.listdir(G) if f.endswith(".ncu-rep")):
         w.writerow([units[i] for i in idx])
         for r in rows[2:]:
             w.writerow([r[i] for i in idx])
+            try:      # DRAM bytes per launch of the conv kernels -> bench.py's roofline.traffic
+                if "ellconv_tc" in r[hdr.index("Kernel Name")]:
+                    b = 0.0
+                    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                        k = hdr.index(key)
+                        b += float(r[k].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[k]]
+                    traffic.setdefault("ellconv", []).append(b)
+            except (ValueError, KeyError):
+                pass
             md.append("| " + " | ".join(re.sub(r"\(.*", "", r[i])[-48:] + (" " + units[i] if units[i] else "") for i in idx) + " |\n")
+if traffic:
+    json.dump({"ellconv": sum(traffic["ellconv"]) / len(traffic["ellconv"]),
+               "note": "mean dram__bytes_read.sum + dram__bytes_write.sum per launch over the %d fused-conv launches captured "
+                       "with ncu --set full (%s_prof_conv_*.csv); bench.py reports it as roofline.traffic" % (len(traffic["ellconv"]), tag)},
+              open(os.path.join(P, "roofline_traffic.json"), "w"), indent=1)
 open(os.path.join(P, "%s_summary.md" % tag), "w").write("".join(md))
 print("".join(md)[:3000])
