@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
     // =========================== producers ===========================
     const int l8 = tid & 7, rs = tid >> 3;       // 8 lanes per 128-byte row, 32 row slots
     int sa = 0, sb = 0;
-    uint32_t pha = 0, phb = 0;
+    uint32_t pha = 0, phb = 0, tph = 0;       // tph bit s: parity of the TMA fills stage s has seen (bar_atma)
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long row0 = (long long)tile * BM;
       int rn[4], rr[4];
@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
           // ---- A chunk: gather 4 rows per thread, split, store swizzled
           if ((tma_a >> t) & 1) {
             // identity term: the TMA warp put the raw rows (= hi operand) in place; derive the lo tile from them
-            mbar_wait(bar_atma + 8 * sa, pha);
+            mbar_wait(bar_atma + 8 * sa, (tph >> sa) & 1u);
+            tph ^= 1u << sa;
             char* a_hi = a_ring + (size_t)sa * Cfg::A_STAGE_BYTES;
             char* a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N=BN, M=128
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int sa = 0, sb = 0, it = 0;
-      uint32_t pha = 0, phb = 0;
+      uint32_t pha = 0, phb = 0, tph = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int buf = it % nbuf;
         const uint32_t use = (uint32_t)(it / nbuf);
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
         for (int t = 0; t < p.nterms; ++t) {
           const bool has2 = DUAL && p.terms[t].w2T != nullptr;
           for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
-            if ((tma_a >> t) & 1) mbar_wait(bar_atma + 8 * sa, pha);      // hi tile written by TMA
+            if ((tma_a >> t) & 1) { mbar_wait(bar_atma + 8 * sa, (tph >> sa) & 1u); tph ^= 1u << sa; }   // hi tile by TMA
             mbar_wait(bar_afull + 8 * sa, pha);
             const uint32_t aaddr = smem_u32(a_ring + (size_t)sa * Cfg::A_STAGE_BYTES);
             const uint64_t a_hi = make_desc(aaddr), a_lo = make_desc(aaddr + A_TILE_BYTES);
@@ -354,8 +355,10 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
           const bool has2 = DUAL && p.terms[t].w2T != nullptr;
           const bool a_here = (tma_a >> t) & 1;
           for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+            // Follow the A ring chunk by chunk even when the producers fill it: a parity wait cannot tell "two uses
+            // ago" from "this use", so this thread must never get more than one use of a stage ahead of the MMAs.
+            if (tma_a) mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
             if (a_here) {
-              mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
               tc::mbar_arrive_expect_tx(bar_atma + 8 * sa, (uint32_t)A_TILE_BYTES);
               tc::tma_load_2d(smem_u32(a_ring + (size_t)sa * Cfg::A_STAGE_BYTES), &maps.a[t], f0, row0, bar_atma + 8 * sa);
             }

@@ -18,6 +18,7 @@ LEAKY_ALPHA = 0.2  # tf.nn.leaky_relu default (lib/models.py:109,506,582)
 # Optional per-launch timing (bench.py's roofline pass): when PROFILE is a list, every helper below brackets its
 # launch with CUDA events on the launching stream and appends (family, tag, algorithmic_bytes, ev0, ev1).
 PROFILE = None
+TRACE = bool(int(__import__("os").environ.get("CAPE_TRACE", "0")))   # debug: print and sync every conv launch
 
 
 class _Prof:
@@ -183,8 +184,12 @@ def cheb_call(tp, N, rows_out, ncols, terms, out, out2=None, cond=None, epilogue
     a.aux = aux.data_ptr() if aux is not None else None
     a.out = out.data_ptr()
     a.out2 = out2.data_ptr() if out2 is not None else None
+    if TRACE:
+        print("cheb_fwd", tag[0] if tag else None, N, rows_out, ncols, [(t["op"], t["F"]) for t in terms], flush=True)
     with _Prof("ellconv", tag):
         check(tp.lib.cape_cheb_fwd(tp.h, C.byref(a), _stream()))
+    if TRACE:
+        torch.cuda.synchronize()
 
 
 def cheb_dw(tp, N, rows_out, ncols, src, op, F, src_rows, src_stride, g, dw, dw_stride, accumulate=False, tag=None,

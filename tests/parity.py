@@ -87,6 +87,9 @@ def cheb_grad_cases(h):
     out.update(cheb_grads("thin L0 K=2 32->3", h["L"][0], 2, 32, 3, 2, act=None))
     out.update(cheb_grads("first L0 K=2 3->64", h["L"][0], 2, 3, 64, 2))
     out.update(cheb_grads("odd Ld4 K=2 13->1 relu", h["L_d"][4], 2, 13, 1, 5, act="b1relu"))
+    # wide same-level layer through the plain op API (no pre-split weight copies), more 128-row tiles than SMs:
+    # persistent kernel, identity term by TMA, weights by the producer warps
+    out.update(cheb_grads("wide L6 K=2 128->256 multi-tile", h["L"][6], 2, 128, 256, 24, act=None))
     return out
 
 
