@@ -417,9 +417,26 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quad * 32) << 16);
       const size_t orow = (size_t)R * p.ncols;
+      // backward epilogues read the saved activation (aux): fetch it one column group ahead, the loads are row-strided
+      // (one row per lane) and their latency would otherwise sit in front of every group
+      const bool use_aux = valid && (p.epilogue == CAPE_EPI_SLOPE || p.epilogue == CAPE_EPI_DUALMASK);
+      float4 axn[4];
+      if (use_aux) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) axn[j] = ldg4(p.aux + orow + 4 * j);
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < p.ncols; c0 += 16) {
         float v0[16], v1[16];
+        float4 axc[4];
+        if (use_aux) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) axc[j] = axn[j];
+          if (c0 + 16 < p.ncols) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) axn[j] = ldg4(p.aux + orow + c0 + 16 + 4 * j);
+          }
+        }
         tmem_ld16(taddr_row + (uint32_t)c0, v0);           // warp-collective: executed by every lane
         if (DUAL) tmem_ld16(taddr_row + acc1_col + (uint32_t)c0, v1);
         if (!valid) continue;
@@ -458,7 +475,7 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
           float ax[16];
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            const float4 a4 = ldg4(p.aux + orow + c0 + j);
+            const float4 a4 = axc[j >> 2];
             ax[j] = a4.x; ax[j + 1] = a4.y; ax[j + 2] = a4.z; ax[j + 3] = a4.w;
           }
           if (p.epilogue == CAPE_EPI_SLOPE) {
@@ -742,18 +759,35 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 2) ellconv_tc2_kernel(const _
     }
 
     // =========================== epilogue ===========================
-    mbar_wait(bar_accum, 0);
-    tc_fence_after();
     const int quad = warp & 3, half = warp >> 2;          // TMEM lane quadrant of this warp; column half
     const int row = quad * 32 + lane;
     const int n = s_n[row], r = s_r[row];
     const int cpw = p.ncols >> 1;                         // columns per warp (ncols is a multiple of 32)
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16);
     const size_t orow = (size_t)(row0 + row) * p.ncols;
+    // backward epilogues read the saved activation (aux): first column group before waiting for the MMAs, then one
+    // group ahead (row-strided loads, one row per lane: their latency would sit in front of every group)
+    const bool use_aux = n >= 0 && (p.epilogue == CAPE_EPI_SLOPE || p.epilogue == CAPE_EPI_DUALMASK);
+    float4 axn[4];
+    if (use_aux) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) axn[j] = ldg4(p.aux + orow + half * cpw + 4 * j);
+    }
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
 #pragma unroll 1
     for (int g = 0; g < cpw / 16; ++g) {
       const int c0 = half * cpw + g * 16;                 // first of 16 output columns
       float v0[16], v1[16];
+      float4 axc[4];
+      if (use_aux) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) axc[j] = axn[j];
+        if (g + 1 < cpw / 16) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) axn[j] = ldg4(p.aux + orow + c0 + 16 + 4 * j);
+        }
+      }
       tmem_ld16(taddr_row + (uint32_t)c0, v0);             // warp-collective: executed by every lane
       if (DUAL) tmem_ld16(taddr_row + acc1_col + (uint32_t)c0, v1);
       if (n < 0) continue;
@@ -792,7 +826,7 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 2) ellconv_tc2_kernel(const _
         float ax[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const float4 a4 = ldg4(p.aux + orow + c0 + j);
+          const float4 a4 = axc[j >> 2];
           ax[j] = a4.x; ax[j + 1] = a4.y; ax[j + 2] = a4.z; ax[j + 3] = a4.w;
         }
         if (p.epilogue == CAPE_EPI_SLOPE) {
