@@ -646,6 +646,35 @@ class CapeNetwork:
             self.in_cond[:N].copy_(cond_d, non_blocking=non_blocking)
             self.in_cond2[:N].copy_(cond2_d, non_blocking=non_blocking)
 
+    def prefetch_inputs(self, x_g, cond_g, cond2_g, eps, x_d, cond_d, cond2_d):
+        """Start the host->device copy of the NEXT step's batch (pinned host tensors) on a side stream, into one of two
+        staging sets; `commit_inputs()` makes it the current batch.  The copy overlaps the step that is running."""
+        if not hasattr(self, "_stage"):
+            bufs = (self.in_x, self.in_cond[self.N:], self.in_cond2[self.N:], self.in_eps, self.xcat[:self.N],
+                    self.in_cond[:self.N], self.in_cond2[:self.N])
+            self._stage = [[torch.empty_like(b) for b in bufs] for _ in range(2)]
+            self._stage_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage_slot = 0
+            for e in self._stage_free:
+                e.record()
+        slot = self._stage_slot
+        self._copy_stream.wait_event(self._stage_free[slot])        # its previous contents have been consumed
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(self._stage[slot], (x_g, cond_g, cond2_g, eps, x_d, cond_d, cond2_d)):
+                dst.copy_(src, non_blocking=True)
+            self._stage_ev[slot].record(self._copy_stream)
+
+    def commit_inputs(self):
+        """Make the batch started by the last `prefetch_inputs` the current one (device-to-device, compute stream)."""
+        slot = self._stage_slot
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._stage_ev[slot])
+        self.set_inputs(*self._stage[slot])
+        self._stage_free[slot].record(cur)
+        self._stage_slot = 1 - slot
+
     # ---- forward pieces ---------------------------------------------------------------------------------------
     def cond_fwd(self, lo, hi):
         """condition nets on rows [lo,hi) of the stacked condition inputs -> ycat rows."""

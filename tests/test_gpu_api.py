@@ -85,3 +85,36 @@ def test_checkpoint_roundtrip(hierarchy, tmp_path):
     assert all(np.array_equal(before[k], after[k]) for k in before)
     assert set(np.load(fn).files) >= set(before)          # keyed by the reference's TF variable names
     assert m.get_var("generator/decoder/outputs/bias").shape == (1, 6890, 3)
+
+
+def test_prefetched_inputs_equal_direct_inputs(hierarchy):
+    """prefetch_inputs/commit_inputs (copy stream + staging buffers, what bench.py's end-to-end loop uses) feed the
+    step the same batch as set_inputs: two alternating batches, same losses (up to the last bits: the loss and
+    column-sum kernels accumulate with atomics)."""
+    from cape_b200.network import CapeNetwork
+    from cape_b200.params import NZ64_AFFINE, param_specs
+    from cape_b200.synthetic import make_batch
+    h, cfg, N = hierarchy, dict(NZ64_AFFINE), 2
+    specs = param_specs(cfg, [l.shape[0] for l in h["L"]], [l.shape[0] for l in h["L_d"]])
+    params = parity.calibrated_params(specs, 3)
+    order = ("x_g", "cond_g", "cond2_g", "eps", "x_d", "cond_d", "cond2_d")
+    batches = [[torch.from_numpy(make_batch(N, cfg["nz"], seed=s)[k]).pin_memory() for k in order] for s in (1, 2)]
+
+    def run(prefetch):
+        net = CapeNetwork(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], cfg, N, params=params)
+        out = []
+        if prefetch:
+            net.prefetch_inputs(*batches[0])
+        for i in range(4):
+            if prefetch:
+                net.commit_inputs()
+                net.prefetch_inputs(*batches[(i + 1) % 2])
+            else:
+                net.set_inputs(*batches[i % 2])
+            net.train_step(step=10 + 2 * i)
+            out.append(net.losses.cpu().numpy().copy())
+        return np.stack(out)
+
+    a, b = run(False), run(True)
+    assert np.isfinite(a).all() and np.allclose(a, b, rtol=1e-4, atol=1e-6)
+    assert not np.array_equal(a[0], a[1])                     # the two batches differ
