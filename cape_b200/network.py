@@ -215,18 +215,22 @@ class ChebLayer:
         if want_dw and mode == "aside":
             nl = K + (1 if self.affine else 0)
             tg = (self.name + ":dW", self.alg_bytes(N, "dW") / nl)
-            for k in range(K):
-                B = self.stash_a[k]
-                if B is None:                                   # identity term: the basis is x itself
-                    cheb_dw(tp, N, s.rows_out, Fout, x, -1, F, s.rows_in, sx, g, self.gW3[:, k, :], K * Fout, tag=tg)
-                else:
-                    cheb_dw(tp, N, s.rows_out, Fout, B[:N], -1, F, s.rows_out, F, g, self.gW3[:, k, :], K * Fout, tag=tg)
-            if self.affine:
-                B = self.stash_a[0]
-                if B is None:
-                    cheb_dw(tp, N, s.rows_out, Fout, x, -1, F, s.rows_in, sx, g_aff, self.gWa2, Fout, tag=tg)
-                else:
-                    cheb_dw(tp, N, s.rows_out, Fout, B[:N], -1, F, s.rows_out, F, g_aff, self.gWa2, Fout, tag=tg)
+
+            def dw_aside(tp):
+                for k in range(K):
+                    B = self.stash_a[k]
+                    if B is None:                               # identity term: the basis is x itself
+                        cheb_dw(tp, N, s.rows_out, Fout, x, -1, F, s.rows_in, sx, g, self.gW3[:, k, :], K * Fout, tag=tg)
+                    else:
+                        cheb_dw(tp, N, s.rows_out, Fout, B[:N], -1, F, s.rows_out, F, g, self.gW3[:, k, :], K * Fout,
+                                tag=tg)
+                if self.affine:
+                    B = self.stash_a[0]
+                    if B is None:
+                        cheb_dw(tp, N, s.rows_out, Fout, x, -1, F, s.rows_in, sx, g_aff, self.gWa2, Fout, tag=tg)
+                    else:
+                        cheb_dw(tp, N, s.rows_out, Fout, B[:N], -1, F, s.rows_out, F, g_aff, self.gWa2, Fout, tag=tg)
+            self.net.run_dw(dw_aside)
         elif (want_dw and mode == "gather" and Fout <= 4 and not self.affine and F in (32, 64, 128, 256) and sx == F
               and K <= 4):
             # thin OUTPUT: swap the roles -- operators on the narrow gradient (H_k = op_k^T g), one pass over x;
@@ -293,15 +297,19 @@ class ChebLayer:
                 # dW_k = x^T (op_k^T G): the data-gradient kernel above left op_k^T G in the stash buffers
                 nl = (1 if self.g_merged else K) + (1 if self.affine else 0)
                 tg = (self.name + ":dW", self.alg_bytes(N, "dW") / nl)
-                if self.g_merged:
-                    cheb_dw(tp, N, s.rows_in, K * Fout, x, -1, F, s.rows_in, sx, self.Hg[:N], self.gW3, K * Fout, tag=tg)
-                else:
-                    for k in range(K):
-                        H = g if self.stash_g[k] is None else self.stash_g[k][:N]
-                        cheb_dw(tp, N, s.rows_in, Fout, x, -1, F, s.rows_in, sx, H, self.gW3[:, k, :], K * Fout, tag=tg)
-                if self.affine:
-                    Ha = g_aff if self.stash_ga is None else self.stash_ga[:N]
-                    cheb_dw(tp, N, s.rows_in, Fout, x, -1, F, s.rows_in, sx, Ha, self.gWa2, Fout, tag=tg)
+
+                def dw_gside(tp):
+                    if self.g_merged:
+                        cheb_dw(tp, N, s.rows_in, K * Fout, x, -1, F, s.rows_in, sx, self.Hg[:N], self.gW3, K * Fout, tag=tg)
+                    else:
+                        for k in range(K):
+                            H = g if self.stash_g[k] is None else self.stash_g[k][:N]
+                            cheb_dw(tp, N, s.rows_in, Fout, x, -1, F, s.rows_in, sx, H, self.gW3[:, k, :], K * Fout,
+                                    tag=tg)
+                    if self.affine:
+                        Ha = g_aff if self.stash_ga is None else self.stash_ga[:N]
+                        cheb_dw(tp, N, s.rows_in, Fout, x, -1, F, s.rows_in, sx, Ha, self.gWa2, Fout, tag=tg)
+                self.net.run_dw(dw_gside)
 
     def _colsum_chunk(self, g, N, cs, o):
         # more than 4 operators (K > 3 with conditions): contiguous scratch per chunk, then copy back
@@ -443,6 +451,13 @@ class CapeNetwork:
         self.tp = tp = Topology(device)
         self.device = dev = tp.device
         torch.cuda.set_device(dev)
+        # Weight gradients on plain tensors (stashes) depend on nothing but their layer's operands, so they run on a
+        # second stream next to the data-gradient chain and fill the ramp-up / tail bubbles of its kernels.  They get
+        # a handle of their own (no operators, its own split-K workspace).
+        self.async_dw = os.environ.get("CAPE_ASYNC_DW", "1") != "0"
+        self.tp_dw = Topology(device) if self.async_dw else tp
+        self.dw_stream = torch.cuda.Stream(device=dev) if self.async_dw else None
+        self._dw_pending = False
         self.p = [int(l.shape[0]) for l in L]
         self.p_d = [int(l.shape[0]) for l in L_d]
         F, K, Kd = c["F"], c["K"], c["Kd"]
@@ -591,6 +606,8 @@ class CapeNetwork:
         self.step_count = 0
         # workspace: split-K partials (dW of the widest layer, FC split-K)
         tp.reserve_workspace(64 << 20)
+        if self.async_dw:
+            self.tp_dw.reserve_workspace(64 << 20)
         self.prep_weights()
 
     # ---- parameter access --------------------------------------------------------------------------------
@@ -621,6 +638,24 @@ class CapeNetwork:
     def all_layers(self):
         dec = self.dec if self.affine else [l for b in self.dec for l in b.layers()]
         return self.enc + [self.enc_1x1, self.dec_1x1] + dec + [self.dec_out] + self.disc + [self.disc_pred]
+
+    def run_dw(self, fn):
+        """Issue the weight-gradient launches `fn(topology)` of one layer: on the side stream (after everything
+        enqueued so far on the main one) or, when profiling per launch / CAPE_ASYNC_DW=0, in line."""
+        if not self.async_dw or E.PROFILE is not None:
+            fn(self.tp)
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.dw_stream.wait_event(ev)
+        with torch.cuda.stream(self.dw_stream):
+            fn(self.tp_dw)
+        self._dw_pending = True
+
+    def join_dw(self):
+        if self._dw_pending:
+            torch.cuda.current_stream().wait_stream(self.dw_stream)
+            self._dw_pending = False
 
     def lo_of(self, t):
         r = self.PG.lo_of(t)
@@ -856,7 +891,9 @@ class CapeNetwork:
         # discriminator-loss path: weight gradients from both halves
         if not self.ref_compat:
             self.disc_bwd(0, 2 * N, self.d_logits, want_dw=True)
-        # generator-loss path through D(fake): gradient w.r.t. x_hat and the condition embedding
+        # generator-loss path through D(fake): gradient w.r.t. x_hat and the condition embedding (it rewrites the
+        # gradient buffers the discriminator's weight gradients are still reading on the side stream: join first)
+        self.join_dw()
         self.disc_bwd(N, 2 * N, self.d_logits_g, want_dw=False, dx=self.d_xhat, dycat=self.d_ycat, cs_slot=1)
         _lib.check(lib.cape_recon_losses(tp.h, self.nbr_op, E._ptr(self.x_hat), E._ptr(self.in_x), N, self.p[0],
                                          float(c["lambda_recon"]), float(c["lambda_edge"]), self.n_edges,
@@ -865,6 +902,7 @@ class CapeNetwork:
         self.decoder_bwd()
         self.encoder_bwd()
         self.cond_bwd()
+        self.join_dw()
         # fc L2 regularisation: regularization * sum(l2_regularizer(regularization)(W)) -> grad reg^2 * W (models.py:378)
         r2 = float(c["regularization"]) ** 2
         if r2 > 0:
