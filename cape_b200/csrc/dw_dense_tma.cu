@@ -99,6 +99,9 @@ dw_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const long long rbeg = (long long)blockIdx.y * p.rows_per_split;
   const long long rend = min(p.total_rows, rbeg + p.rows_per_split);
   const long long nchunks = (rend - rbeg + DD_KCH - 1) / DD_KCH;
+  // MN blocks of the A tile that hold real channels: the others are neither loaded nor converted -- whatever shared
+  // memory holds there only reaches accumulator rows f >= F, which the epilogue never stores
+  const int a_blocks = min(4, (p.F - ftile + 31) / 32);
   // per ring: "full" (TMA bytes landed / converters done) and "empty" (the MMAs that read the stage have retired)
   const uint32_t bar_ahf = smem_u32(bars), bar_ahe = smem_u32(bars + DD_MAX_STAGES);
   const uint32_t bar_alf = smem_u32(bars + 2 * DD_MAX_STAGES), bar_ale = smem_u32(bars + 3 * DD_MAX_STAGES);
@@ -138,6 +141,7 @@ dw_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         char* lo = alo_ring + (size_t)al * DD_A_TILE;
 #pragma unroll
         for (int i = 0; i < DD_A_TILE / 16 / DD_CONV_THREADS; ++i) {
+          if (i >= a_blocks) break;                    // one MN block = 4096 B = one pass of the 256 converter threads
           const int off = (i * DD_CONV_THREADS + tid) * 16;
           const float4 v = *reinterpret_cast<const float4*>(hi + off);
           *reinterpret_cast<float4*>(lo + off) =
@@ -265,11 +269,12 @@ dw_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           } else {
             mbar_wait(bar_ahe + 8 * ah, pah ^ 1);
           }
-          mbar_arrive_expect_tx(bar_ahf + 8 * ah, DD_A_TILE);
+          mbar_arrive_expect_tx(bar_ahf + 8 * ah, (uint32_t)(a_blocks * 4096));
           const uint32_t adst = smem_u32(ahi_ring + (size_t)ah * DD_A_TILE);
           const int row0 = (int)(rbeg + ka * DD_KCH);
 #pragma unroll
-          for (int mb = 0; mb < 4; ++mb) tma_load_2d(adst + mb * 4096, &tmA, ftile + mb * 32, row0, bar_ahf + 8 * ah);
+          for (int mb = 0; mb < 4; ++mb)
+            if (mb < a_blocks) tma_load_2d(adst + mb * 4096, &tmA, ftile + mb * 32, row0, bar_ahf + 8 * ah);
           if (++ah == SAH) { ah = 0; pah ^= 1; }
           ++ka;
           block = false;
@@ -300,29 +305,10 @@ dw_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    else
-      (void)cudaGetLastError();
-  }
-  return fn;
-}
 
 // [rows, inner] fp32 row-major with `row_stride` floats between rows; boxes of 32 floats x 32 rows, MN-swizzled
 bool make_map(CUtensorMap* m, const float* base, long long inner, long long rows, long long row_stride) {
-  EncodeTiledFn fn = encode_fn();
+  tc::EncodeTiledFn fn = tc::encode_fn();
   if (!fn) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)row_stride * sizeof(float)};

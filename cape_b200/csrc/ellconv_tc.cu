@@ -28,46 +28,7 @@ constexpr int TC_THREADS = TC_PROD_THREADS + 32;
 constexpr int A_TILE_BYTES = BM * 128;            // 128 rows x 32 fp32 (one 128-byte swizzle row each)
 constexpr int QS_FLOATS = 4096;
 constexpr int MAX_STAGES = 4;
-constexpr uint32_t SPIN_LIMIT = 1u << 27;         // trap instead of hanging the GPU if a barrier never flips
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++spins > SPIN_LIMIT) __trap();
-  }
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
+using namespace tc;     // mbarriers, fences, UMMA issue, TMEM loads, TMA loads (tc_common.cuh)
 
 // K-major, SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor, sm100 "version 1"):
 // start address >> 4 | LBO(ignored for swizzled K-major)=1 | SBO = 1024 B (8 rows x 128 B) | layout_type = 2.
@@ -76,28 +37,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
          (2ull << 61);
 }
 
-// 16 accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void split_store(float4 v, char* hi_tile, char* lo_tile, uint32_t off) {
-  float4 h, l;
-  h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-  h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-  h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-  h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-  *reinterpret_cast<float4*>(hi_tile + off) = h;
-  *reinterpret_cast<float4*>(lo_tile + off) = l;
-}
 
 template <int BN, bool DUAL>
 struct TcCfg {
@@ -507,28 +446,10 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    else
-      (void)cudaGetLastError();
-  }
-  return fn;
-}
 
 // K-major weight copy: element (f, c) at base[c * stride + f]; boxes of 32 f x bn columns, 128-byte swizzle
 bool make_wmap(CUtensorMap* m, const float* base, int F, int ncols, int stride, int bn) {
-  EncodeTiledFn fn = encode_fn();
+  tc::EncodeTiledFn fn = tc::encode_fn();
   if (!fn || base == nullptr || !aligned16(base) || stride % 4 != 0) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)F, (cuuint64_t)ncols};
   const cuuint64_t strides[1] = {(cuuint64_t)stride * sizeof(float)};
@@ -579,11 +500,11 @@ int launch_one(const cape_topology* t, const ConvParams& p, cudaStream_t st) {
   const int tma_b = g_tuning[4] != 1 && build_wmaps<DUAL>(p, BN, &maps);
   // basis tiles of identity-operator terms (plain source rows) by TMA as well
   int tma_a = 0;
-  if (encode_fn() != nullptr && g_tuning[6] != 1 && p.total_rows < (1LL << 31)) {
+  if (tc::encode_fn() != nullptr && g_tuning[6] != 1 && p.total_rows < (1LL << 31)) {
     for (int i = 0; i < p.nterms && i < TC_TMA_TERMS; ++i) {
       const TermDev& tm = p.terms[i];
       if (tm.op.idx != nullptr || tm.src_rows != p.rows_out || !tm.vec) continue;
-      EncodeTiledFn fn = encode_fn();
+      tc::EncodeTiledFn fn = tc::encode_fn();
       const cuuint64_t dims[2] = {(cuuint64_t)tm.F, (cuuint64_t)p.total_rows};
       const cuuint64_t strides[1] = {(cuuint64_t)tm.src_stride * sizeof(float)};
       const cuuint32_t box[2] = {32, (cuuint32_t)BM};

@@ -70,6 +70,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 3xTF32 operand split of four values: hi = the top 19 bits (what the tensor core reads of a raw fp32 word), lo = x - hi;
+// both tiles get the value at the same byte offset
+__device__ __forceinline__ void split_store(float4 v, char* hi_tile, char* lo_tile, uint32_t off) {
+  float4 h, l;
+  h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+  h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+  h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+  h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+  *reinterpret_cast<float4*>(hi_tile + off) = h;
+  *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
 // MN-major SWIZZLE_128B_BASE32B operand descriptor (layout_type 1), the only MN-major layout tcgen05 accepts for
 // 32-bit operands: 32-element MN blocks of 4096 B (LBO), 4-row K groups of 512 B (SBO), 128-byte rows whose 32-byte
 // chunks are XOR-ed with (row & 3)  [cute Layout_MN_SW128_32B_Atom, Swizzle<2,5,2>].  A TMA box of 32 floats x 32 rows
@@ -88,6 +100,27 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (no link-time dependency on libcuda);
+// nullptr if the driver does not provide it -- callers then keep their non-TMA path
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
 }
 
 }  // namespace tc

@@ -113,8 +113,11 @@ typedef struct {
   float* out2;         /* [N, rows_out, ncols] or NULL */
 } cape_conv_args;
 
-/* Experiment knobs (process-wide, 8 integer slots read by experimental kernel variants; none is used by the shipped
- * kernels).  Returns the previous value, <0 for an unknown key. */
+/* Experiment knobs (process-wide, 8 integer slots, all 0 by default = the shipped configuration).  They switch single
+ * optimisations off for A/B measurements and fallback-path tests: [1]=1 no TMA dense weight-gradient kernel, [3]=2
+ * 128- instead of 256-wide column sub-tiles in it, [4]=1 conv weight tiles by the producer warps instead of TMA,
+ * [5]=1 one narrow-conv CTA per SM, [6]=1 identity-term basis tiles by the producer warps, [7]=1 thin-output layers
+ * on the generic kernels ([2] is a diagnostic of the dense kernel).  Returns the previous value, <0 for an unknown key. */
 int cape_set_tuning(int key, int value);
 
 /* Process-wide switch for the tcgen05 path of cape_cheb_fwd (default on); returns the previous setting. */
