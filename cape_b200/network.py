@@ -93,6 +93,21 @@ class Arena:
         self.buf.zero_()
 
 
+def choose_dw_mode(F, Fout, K, rows_in, rows_out, need_dx, stash=True):
+    """Where a layer's weight gradient takes its operands from (see ChebLayer): "aside" = basis stashed by the forward
+    kernel, "gside" = op^T G stashed by the data-gradient kernel, "gather" = gathered again by cape_cheb_dw.
+    The dense TMA kernel needs F % 4 == 0, F >= 32 and 32 | Fout <= 512; pooled sites contract over the (fewer)
+    output rows, un-pooling ones over the (fewer) input rows, same-level ones take the narrower side."""
+    dense_ok = F % 4 == 0 and F >= 32 and Fout % 32 == 0 and Fout <= 512
+    if not (dense_ok and stash):
+        return "gather"
+    if rows_out < rows_in:
+        return "aside"
+    if need_dx and (rows_in < rows_out or (K * Fout <= 512 and F >= Fout)):
+        return "gside"
+    return "aside"
+
+
 class ChebLayer:
     """chebyshev5 (+bias/act, +pool/unpool folded into the site, +condition channels, + optional affine
     branch) with its backward."""
@@ -122,16 +137,8 @@ class ChebLayer:
         #             over x when K*Fout <= 512 (the TMEM width), over the smaller row set when the site un-pools;
         #   "gather": cape_cheb_dw gathers the basis again (thin layers, odd shapes).
         # The first two make both operands plain tensors, which is what the TMA-fed tcgen05 kernel wants.
-        dense_ok = F % 4 == 0 and F >= 32 and Fout % 32 == 0 and Fout <= 512
-        pooled, unpooled = site.rows_out < site.rows_in, site.rows_in < site.rows_out
-        self.dw_mode = "gather"
-        if dense_ok and os.environ.get("CAPE_DW_STASH", "1") != "0":
-            if pooled:
-                self.dw_mode = "aside"
-            elif need_dx and (unpooled or (K * Fout <= 512 and F >= Fout)):
-                self.dw_mode = "gside"
-            else:
-                self.dw_mode = "aside"
+        self.dw_mode = choose_dw_mode(F, Fout, K, site.rows_in, site.rows_out, need_dx,
+                                      os.environ.get("CAPE_DW_STASH", "1") != "0")
         self.stash_a, self.stash_g, self.stash_ga = [None] * K, [None] * K, None
         if self.dw_mode == "aside":
             self.stash_a = [None if site.ops[k] == -1 else torch.empty(maxN, site.rows_out, F, device=dev)

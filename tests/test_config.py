@@ -80,3 +80,18 @@ def test_param_store_low_part_views():
     v = ps.w("a/weights").view(6, 8)
     assert torch.equal(ps.lo_of(v), -v)
     assert ps.lo_of(torch.zeros(4)) is None                     # not a view of this store
+
+
+def test_weight_gradient_operand_choice():
+    """choose_dw_mode on the layer shapes of the shipped config (levels 6890/3445/1723/862)."""
+    from cape_b200.network import choose_dw_mode as m
+    assert m(3, 64, 2, 6890, 6890, False) == "gather"            # enc conv1: thin input
+    assert m(64, 64, 2, 6890, 3445, True) == "aside"             # enc conv2: pooled -> contract over the coarse rows
+    assert m(64, 128, 2, 3445, 3445, True) == "aside"            # enc conv3: widening, same level -> narrower side is x
+    assert m(512, 512, 2, 862, 862, True) == "aside"             # enc conv8: K*Fout > 512
+    assert m(512, 256, 2, 862, 862, True) == "gside"             # dec aff1: narrowing, all terms in one pass
+    assert m(256, 256, 2, 862, 1723, True) == "gside"            # dec aff2: un-pooling -> contract over the coarse rows
+    assert m(32, 3, 2, 6890, 6890, True) == "gather"             # dec outputs: thin output (role-swapped thin kernel)
+    assert m(64, 64, 3, 3445, 1723, True) == "aside"             # disc conv2
+    assert m(128, 128, 2, 862, 862, False) == "aside"            # no data gradient requested -> no G-side stash
+    assert m(64, 64, 2, 6890, 3445, True, stash=False) == "gather"
