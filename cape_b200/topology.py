@@ -250,3 +250,23 @@ def adjacency_ell(L):
     A.eliminate_zeros()
     A.data[:] = 1.0
     return to_ell(A)
+
+
+def window_split(m, tile=128, halo=32):
+    """Classify the taps of a same-level operator for window staging: for the rows of each
+    `tile`-row tile, the taps whose source row lies in [tile_start - halo, tile_start + tile + halo) can be served
+    from one contiguous window of the source staged in shared memory (a single TMA box), the rest are "far" taps.
+    Returns (idx, w, n_in): ELL tables like `to_ell` but with the window taps packed first in every row (by source
+    row), far taps after them, and n_in[r] = number of window taps of row r."""
+    m = sp.csr_matrix(m)
+    assert m.shape[0] == m.shape[1], "window staging is for same-level operators"
+    idx, w = to_ell(m)
+    rows, width = idx.shape
+    start = (np.arange(rows) // tile) * tile - halo
+    local = idx - start[:, None]
+    inside = (idx >= 0) & (local >= 0) & (local < tile + 2 * halo)
+    # stable sort key: window taps (0) < far taps (1) < padding (2); ties keep the source-row order of to_ell
+    key = np.where(idx < 0, 2, np.where(inside, 0, 1))
+    order = np.argsort(key, axis=1, kind="stable")
+    take = lambda a: np.take_along_axis(a, order, axis=1)
+    return take(idx), take(w), inside.sum(1).astype(np.int32)

@@ -118,3 +118,23 @@ def test_patch_order_is_a_layout_change_only(hierarchy):
     Lt = T.rescale_L(h["L"][0])
     before, after = _distinct_per_row(Lt), _distinct_per_row(T.permute(Lt, orders[0], orders[0]))
     assert after < 0.75 * before and after < 1.7
+
+
+def test_window_split_keeps_the_operator_and_packs_window_taps_first(hierarchy):
+    h = hierarchy
+    orders = T.level_orders(h["L"][0], h["D"])
+    for lvl in (0, 6):
+        Lt = T.cheb_polynomials(h["L"][lvl], 2)[1]
+        for m in (Lt, T.permute(Lt, orders[lvl], orders[lvl])):
+            idx, w, n_in = T.window_split(m, tile=128, halo=32)
+            x = np.random.RandomState(0).normal(size=(m.shape[1], 2))
+            assert np.abs(_apply_ell(idx, w, x) - m @ x).max() < 1e-5
+            rows = np.arange(idx.shape[0])
+            start = (rows // 128) * 128 - 32
+            for j in range(idx.shape[1]):
+                valid = idx[:, j] >= 0
+                inwin = valid & (idx[:, j] - start >= 0) & (idx[:, j] - start < 192)
+                assert np.array_equal(inwin, valid & (j < n_in))
+        # patch order: almost every one-ring tap of a tile sits in its 192-row window
+        idx, w, n_in = T.window_split(T.permute(Lt, orders[lvl], orders[lvl]))
+        assert n_in.sum() / (idx >= 0).sum() > 0.85
