@@ -1,5 +1,5 @@
 """Parity checks of the CUDA path (through the C ABI) against the CPU oracle.  Each function returns a dict
-{name: relative error}; tests assert on them, tools/gpu_check.py prints them all."""
+{name: relative error}; tests assert on them, tests/gpu_check.py prints them all."""
 import os
 
 import numpy as np
@@ -152,7 +152,7 @@ def calibrated_params(specs, seed=123, fc_scale=0.05):
     """Reference initialisers, with the encoder's fc_mean / fc_var kernels scaled down so that the KL term is O(1)
     as in a trained model.  With raw glorot init on N(0,1) inputs logvar reaches +-10, exp(logvar) ~ 1e4, the KL
     term is ~1e4 and single leaky-ReLU sign flips (fp32 rounding) move conv gradients by 1e-3: ill-conditioned for
-    ANY fp32 implementation, so not a meaningful parity regime (both regimes are reported by tools/gpu_check.py)."""
+    ANY fp32 implementation, so not a meaningful parity regime (both regimes are reported by tests/gpu_check.py)."""
     from cape_b200.params import init_params
     params = init_params(specs, seed)
     for k in params:

@@ -2,7 +2,7 @@
 # One GPU-box visit: parity checks, tests, bench (+ optional ncu).  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi -L | head -1
-echo "== gpu_check"; timeout 900 python tools/gpu_check.py golden tc cheb step step_n5 step_gn 2>&1 | grep -v "Warn\|warn\|return torch\|out = {" > gpurun_out/gpu_check.log; grep -c FAIL gpurun_out/gpu_check.log; grep -v "param-update\|  grad " gpurun_out/gpu_check.log | tail -60; grep FAIL gpurun_out/gpu_check.log | head -30
+echo "== gpu_check"; timeout 900 python tests/gpu_check.py golden tc cheb step step_n5 step_gn 2>&1 | grep -v "Warn\|warn\|return torch\|out = {" > gpurun_out/gpu_check.log; grep -c FAIL gpurun_out/gpu_check.log; grep -v "param-update\|  grad " gpurun_out/gpu_check.log | tail -60; grep FAIL gpurun_out/gpu_check.log | head -30
 echo "== pytest -m gpu"; timeout 1200 python -m pytest tests -q -m gpu 2>&1 > gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log
 echo "== bench"; timeout 900 python bench.py --steps 10 --warmup 3 2> gpurun_out/bench.err | tee gpurun_out/bench.json | cut -c1-400; tail -3 gpurun_out/bench.err
 if [ -n "$AB_ENV$AB_ARGS" ]; then
