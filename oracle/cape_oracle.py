@@ -90,6 +90,19 @@ class Oracle:
         # (pooled sites): `mask_rows[name]` then lists the rows they refer to.
         self.masks = None
         self.mask_rows = {}
+        # Optional dict: when set, every (leaky-)ReLU site stores the branch decisions it took (all rows), so that a
+        # second oracle of another precision can be run with exactly these decisions (tests: fp32 vs fp64 truth).
+        self.record = None
+        # Optional dict: when set, named intermediate tensors of the forward are kept (with retain_grad) so that a test
+        # can compare hidden activations and their gradients, not only the leaves.
+        self.keep = None
+
+    def _keep(self, name, t):
+        if self.keep is not None:
+            if t.requires_grad:
+                t.retain_grad()
+            self.keep[name] = t
+        return t
 
     # ---- ops ---------------------------------------------------------------------------------------
     def chebyshev5(self, x, Lt, W, K):
@@ -119,6 +132,8 @@ class Oracle:
             else:
                 pos = pos.clone()
                 pos[:, rows] = m
+        if self.record is not None and site is not None:
+            self.record[site] = pos.clone()
         return torch.where(pos, v, slope * v)
 
     def b1leakyrelu(self, x, b, site=None):
@@ -177,9 +192,9 @@ class Oracle:
             sc = s + "encoder_conv%d" % (i + 1)
             x = self.chebyshev5(x, self.Lt[i], P[sc + "/weights"], self.K[i])     # cnp :164
             x = self.b1leakyrelu(x, P[sc + "/bias"], site="enc%d" % (i + 1))      # :166
-            x = self.poolwT(x, self.Dm[i])                                        # :168
+            x = self._keep("enc_act%d" % (i + 1), self.poolwT(x, self.Dm[i]))     # :168
         if self.reduce_dim > 0:
-            x = self.chebyshev5(x, self.Lt[-1], P[s + "1x1-conv/weights"], 1)      # :551
+            x = self._keep("enc_red", self.chebyshev5(x, self.Lt[-1], P[s + "1x1-conv/weights"], 1))   # :551
         x = x.reshape(x.shape[0], -1)                                             # :554
         z_mean = self.dense(x, P, s + "fc_mean")
         z_logvar = self.dense(x, P, s + "fc_var")

@@ -27,6 +27,10 @@ def main():
             ("step", lambda: parity.train_step(h, cfg, N=2)),
             ("step_ref", lambda: parity.train_step(h, cfg, N=2, ref_compat=True)),
             ("step_rawinit", lambda: parity.train_step(h, cfg, N=2, fc_scale=1.0)),
+            ("step_truth", lambda: {k: v[0] for k, v in parity.train_step(h, cfg, N=2, fc_scale=1.0, truth=True).items()}),
+            ("step3", lambda: parity.train_step(h, cfg, N=2, nsteps=3, fc_scale=1.0)),
+            ("step_n64", lambda: parity.train_step(h, cfg, N=64, use_graph=True, fc_scale=1.0)),
+            ("fwd_n32", lambda: parity.generator_forward(h, cfg, N=32)),
             ("step_nomask", lambda: parity.train_step(h, cfg, N=2, impose_masks=False)),
             ("step_n5", lambda: parity.train_step(h, cfg, N=5, seed=7)),
             ("step_gn", lambda: parity.train_step(h, dict(__import__("cape_b200.params", fromlist=["x"]).NZ18_PLAIN,

@@ -161,82 +161,136 @@ def calibrated_params(specs, seed=123, fc_scale=0.05):
     return params
 
 
-def train_step(h, cfg, N=2, ref_compat=False, step=100, seed=123, dtype=torch.float32, fc_scale=0.05,
-               impose_masks=True, reorder=None):
-    """Full VAE+GAN update (BASELINE configs[2] at a small batch): x_hat, losses, every gradient and every
-    post-update parameter vs the oracle's autograd.  impose_masks: the oracle's (leaky-)ReLUs take their branch
-    decisions from the CUDA forward (about 1e-6 of all units sit within fp32 rounding of zero and would otherwise
-    flip between any two fp32 implementations, which moves single-sample gradients such as the fc1 columns by
-    percents); forward outputs and losses are compared unmasked in either case."""
-    from cape_b200.network import CapeNetwork
-    from cape_b200.params import init_params, param_specs
-    from cape_b200.synthetic import make_batch
+def cuda_masks(net, h, N):
+    """Branch decisions (activation > 0) of every (leaky-)ReLU site taken from the CUDA forward, in the reference's
+    vertex numbering, keyed like Oracle.masks; pooled sites only know the selected rows (second dict)."""
+    import scipy.sparse as sp
+    from cape_b200 import topology as T2
+    masks, rows = {}, {}
+
+    def sel(D):
+        return None if T2.is_identity(D, tol=0) else torch.from_numpy(sp.csr_matrix(D).indices.astype(np.int64))
+
+    def pos(a, order):
+        m = (a > 0).cpu()
+        return m if order is None else m[:, torch.from_numpy(T2.inverse_order(order))]
+
+    for i, a in enumerate(net.enc_act):
+        masks["enc%d" % (i + 1)] = pos(a, net.enc[i].site.order_out)
+        r = sel(h["D"][i])
+        if r is not None:
+            rows["enc%d" % (i + 1)] = r
+    for i, a in enumerate(net.dec_rg):
+        masks["dec%d" % (i + 1)] = pos(a, net.dec[i].site.order_out)
+    if not net.affine:                                # GroupNorm blocks: three ReLUs each (lib/models.py:752-760)
+        for i, b in enumerate(net.dec):
+            for j, a in enumerate((b.A1, b.A2, b.A3)):
+                masks["gn%d_%d" % (i + 1, j)] = pos(a, b.order_out)
+    masks["dec_fc1"] = (net.dec_fc > 0).cpu()
+    for i, a in enumerate(net.disc_act):
+        r = sel(h["D_d"][i])
+        for tag, sl in (("_real", slice(0, N)), ("_fake", slice(N, 2 * N))):
+            masks["disc%d%s" % (i + 1, tag)] = pos(a[sl], net.disc[i].site.order_out)
+            if r is not None:
+                rows["disc%d%s" % (i + 1, tag)] = r
+    masks["cond_pose_d"], masks["cond_pose_g"] = (net.cp_h[:N] > 0).cpu(), (net.cp_h[N:] > 0).cpu()
+    return masks, rows
+
+
+def _oracle_update(h, cfg, params, mom, tb, step, dtype, ref_compat, masks=None, rows=None, record=None):
+    """One O.train_update from numpy params/momentum (not modified); returns (result dict, new params, new momentum)."""
     from cape_b200 import topology as T
+    o = O.Oracle(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], cfg, dtype=dtype)
+    if masks is not None:
+        o.masks, o.mask_rows = masks, rows or {}
+    o.record = record
+    P = {k: torch.from_numpy(np.asarray(v)).to(dtype) for k, v in params.items()}
+    M = {k: torch.from_numpy(np.asarray(v)).to(dtype) for k, v in mom.items()}
+    ob = {k: v.to(dtype) for k, v in tb.items()}
+    res = O.train_update(o, P, M, ob, step, T.smpl_edges(), ref_compat=ref_compat)
+    return res, {k: v.numpy() for k, v in P.items()}, {k: v.numpy() for k, v in M.items()}
+
+
+def train_step(h, cfg, N=2, ref_compat=False, step=100, seed=123, dtype=torch.float32, fc_scale=0.05,
+               impose_masks=True, reorder=None, nsteps=1, use_graph=False, truth=False, report_unmasked=False):
+    """Full VAE+GAN update(s) (BASELINE configs[2]): x_hat, losses, every gradient, the clipped momentum update and
+    every post-update parameter vs the oracle's autograd, for `nsteps` CONSECUTIVE updates (the oracle carries its own
+    parameters and momentum from update to update; fresh eps and batches every update as in CAPE.fit).
+
+    impose_masks: the oracle's (leaky-)ReLUs take their branch decisions from the CUDA forward (about 1e-6 of all
+    units sit within fp32 rounding of zero and would otherwise flip between any two fp32 implementations, which
+    moves single-sample gradients such as the fc1 columns by percents); forward outputs and losses are compared
+    unmasked in either case (keys "unmasked ...").
+    use_graph: the CUDA step replays the two captured CUDA graphs (what bench.py times) instead of eager launches.
+    truth: the comparison target is the FLOAT64 oracle, and every entry is returned as a pair
+    (err(CUDA, fp64), err(fp32 oracle, fp64)) -- the second one measured with the fp32 oracle's own branch decisions
+    imposed on a second fp64 run -- so that the caller can require the CUDA path to be as close to the truth as a
+    plain fp32 CPU implementation is (reference initialisers, fc_scale=1.0: logvar reaches +-10, the KL term 1e4).
+    report_unmasked: also return the gradient errors against an oracle WITHOUT imposed decisions ("unmasked grad ...",
+    informational: they contain the sign flips)."""
+    from cape_b200.network import CapeNetwork
+    from cape_b200.params import param_specs
+    from cape_b200.synthetic import make_batch
     p = [l.shape[0] for l in h["L"]]
     p_d = [l.shape[0] for l in h["L_d"]]
     specs = param_specs(cfg, p, p_d)
     params = calibrated_params(specs, seed, fc_scale)
-    batch = make_batch(N, cfg["nz"], seed=seed)
     net = CapeNetwork(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], cfg, N, params=params, ref_compat=ref_compat,
                       reorder=reorder)
-    tb = {k: torch.from_numpy(v) for k, v in batch.items()}
-    net.set_inputs(tb["x_g"], tb["cond_g"], tb["cond2_g"], tb["eps"], tb["x_d"], tb["cond_d"], tb["cond2_d"])
-    net.train_step(step=step)
-    torch.cuda.synchronize()
-    got_loss = net.loss_dict()
-    got_x = net.x_hat.cpu().numpy()
-    got_g = net.get_grads()
-    got_p = net.get_params()
-    got_m = net.PG.export(net.PG.mom)
-    got_m.update(net.PD.export(net.PD.mom))
-    # oracle, with the branch decisions (activation signs) of the CUDA forward imposed -- see Oracle.masks
-    o = O.Oracle(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], cfg, dtype=dtype)
-    if impose_masks:
-        import scipy.sparse as sp
-        from cape_b200 import topology as T2
-        masks, rows = {}, {}
-
-        def sel(D):
-            return None if T2.is_identity(D, tol=0) else torch.from_numpy(sp.csr_matrix(D).indices.astype(np.int64))
-
-        def pos(a, order):
-            """sign mask of a hidden activation, back in the reference's vertex numbering"""
-            m = (a > 0).cpu()
-            return m if order is None else m[:, torch.from_numpy(T2.inverse_order(order))]
-
-        for i, a in enumerate(net.enc_act):
-            masks["enc%d" % (i + 1)] = pos(a, net.enc[i].site.order_out)
-            r = sel(h["D"][i])
-            if r is not None:
-                rows["enc%d" % (i + 1)] = r
-        for i, a in enumerate(net.dec_rg):
-            masks["dec%d" % (i + 1)] = pos(a, net.dec[i].site.order_out)
-        if not net.affine:                                # GroupNorm blocks: three ReLUs each (lib/models.py:752-760)
-            for i, b in enumerate(net.dec):
-                for j, a in enumerate((b.A1, b.A2, b.A3)):
-                    masks["gn%d_%d" % (i + 1, j)] = pos(a, b.order_out)
-        masks["dec_fc1"] = (net.dec_fc > 0).cpu()
-        for i, a in enumerate(net.disc_act):
-            r = sel(h["D_d"][i])
-            for tag, sl in (("_real", slice(0, N)), ("_fake", slice(N, 2 * N))):
-                masks["disc%d%s" % (i + 1, tag)] = pos(a[sl], net.disc[i].site.order_out)
-                if r is not None:
-                    rows["disc%d%s" % (i + 1, tag)] = r
-        masks["cond_pose_d"], masks["cond_pose_g"] = (net.cp_h[:N] > 0).cpu(), (net.cp_h[N:] > 0).cpu()
-        o.masks, o.mask_rows = masks, rows
-    P = {k: torch.from_numpy(v).to(dtype) for k, v in params.items()}
-    mom = {k: torch.zeros_like(v) for k, v in P.items()}
-    ob = {k: v.to(dtype) for k, v in tb.items()}
-    res = O.train_update(o, P, mom, ob, step, T.smpl_edges(), ref_compat=ref_compat)
-    out = {"x_hat (vertex-L2)": vertex_l2(got_x, res["x_hat"].numpy()), "x_hat (max-rel)": rel(got_x, res["x_hat"].numpy())}
-    for k in ("recon", "edge", "latent", "gan_g", "gan_d"):
-        out["loss " + k] = abs(got_loss[k] - res[k]) / max(abs(res[k]), 1e-30)
-    for k, g in res["grads"].items():
-        out["grad " + k] = rel(got_g[k].reshape(-1), g.numpy().reshape(-1))
-    for k, m in res["mom"].items():                  # first step: momentum accumulator = clip coefficient * grad
-        out["clipped-update " + k] = rel(got_m[k].reshape(-1), m.numpy().reshape(-1))
-    for k, v in P.items():                           # post-update parameters (fp32 resolution of the weights)
-        out["param " + k] = rel(got_p[k].reshape(-1), v.numpy().reshape(-1))
+    odt = torch.float64 if truth else dtype
+    o_params = {k: np.asarray(v, np.float64 if truth else np.float32) for k, v in params.items()}
+    o_mom = {k: np.zeros_like(v) for k, v in o_params.items()}
+    out = {}
+    for it in range(nsteps):
+        batch = make_batch(N, cfg["nz"], seed=seed + 1000 * it)
+        tb = {k: torch.from_numpy(v) for k, v in batch.items()}
+        net.set_inputs(tb["x_g"], tb["cond_g"], tb["cond2_g"], tb["eps"], tb["x_d"], tb["cond_d"], tb["cond2_d"])
+        if use_graph and it == 0:
+            net.train_step(step=step, update=False)          # lazy initialisations before the capture
+            torch.cuda.synchronize()
+            net.capture_graphs()
+        net.train_step(step=step + it, use_graph=use_graph)
+        torch.cuda.synchronize()
+        got_loss = net.loss_dict()
+        got_x = net.x_hat.cpu().numpy()
+        got_g = net.get_grads()
+        got_p = net.get_params()
+        got_m = net.PG.export(net.PG.mom)
+        got_m.update(net.PD.export(net.PD.mom))
+        masks, rows = cuda_masks(net, h, N) if impose_masks else (None, None)
+        pre = "" if nsteps == 1 else "update %d: " % (it + 1)
+        bound = None
+        if truth:
+            # how far a plain fp32 CPU implementation is from the truth on the same update (its own decisions imposed)
+            rec = {}
+            r32, _, _ = _oracle_update(h, cfg, {k: v.astype(np.float32) for k, v in o_params.items()},
+                                       {k: v.astype(np.float32) for k, v in o_mom.items()}, tb, step + it,
+                                       torch.float32, ref_compat, record=rec)
+            r64b, _, _ = _oracle_update(h, cfg, o_params, o_mom, tb, step + it, torch.float64, ref_compat, masks=rec)
+            bound = {"x_hat (max-rel)": rel(r32["x_hat"].numpy(), r64b["x_hat"].numpy())}
+            for k in r64b["grads"]:
+                bound["grad " + k] = rel(r32["grads"][k].numpy(), r64b["grads"][k].numpy())
+        if report_unmasked and impose_masks:
+            ru, _, _ = _oracle_update(h, cfg, o_params, o_mom, tb, step + it, odt, ref_compat)
+            out[pre + "unmasked fwd x_hat (vertex-L2)"] = vertex_l2(got_x, ru["x_hat"].numpy())
+            out[pre + "unmasked fwd x_hat (max-rel)"] = rel(got_x, ru["x_hat"].numpy())
+            for k in ("recon", "edge", "latent", "gan_g", "gan_d"):
+                out[pre + "unmasked fwd loss " + k] = abs(got_loss[k] - ru[k]) / max(abs(ru[k]), 1e-30)
+            for k, g in ru["grads"].items():
+                out[pre + "unmasked grad " + k] = rel(got_g[k].reshape(-1), g.numpy().reshape(-1))
+        res, o_params, o_mom = _oracle_update(h, cfg, o_params, o_mom, tb, step + it, odt, ref_compat, masks, rows)
+        cur = {"x_hat (vertex-L2)": vertex_l2(got_x, res["x_hat"].numpy()),
+               "x_hat (max-rel)": rel(got_x, res["x_hat"].numpy())}
+        for k in ("recon", "edge", "latent", "gan_g", "gan_d"):
+            cur["loss " + k] = abs(got_loss[k] - res[k]) / max(abs(res[k]), 1e-30)
+        for k, g in res["grads"].items():
+            cur["grad " + k] = rel(got_g[k].reshape(-1), g.numpy().reshape(-1))
+        for k, m in res["mom"].items():                  # momentum accumulator (first update: clip coefficient * grad)
+            cur["clipped-update " + k] = rel(got_m[k].reshape(-1), m.numpy().reshape(-1))
+        for k, v in o_params.items():                    # post-update parameters (fp32 resolution of the weights)
+            cur["param " + k] = rel(got_p[k].reshape(-1), v.reshape(-1))
+        for k, v in cur.items():
+            out[pre + k] = (v, bound.get(k, 0.0)) if truth else v
     return out
 
 
@@ -278,3 +332,24 @@ def tc_vs_simt(h):
         for nm, a, bb in zip(("fwd", "dx", "dW"), res[True], res[False]):
             out["tc-vs-simt %s %s" % (tag, nm)] = rel(a, bb)
     return out
+
+
+def generator_forward(h, cfg, N=32, seed=123, fc_scale=1.0):
+    """BASELINE configs[1]: condition nets + encoder + sampling + decoder forward at batch N vs the oracle (no imposed
+    decisions: forward outputs only)."""
+    from cape_b200.network import CapeNetwork
+    from cape_b200.params import param_specs
+    from cape_b200.synthetic import make_batch
+    specs = param_specs(cfg, [l.shape[0] for l in h["L"]], [l.shape[0] for l in h["L_d"]])
+    params = calibrated_params(specs, seed, fc_scale)
+    net = CapeNetwork(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], cfg, N, params=params)
+    tb = {k: torch.from_numpy(v) for k, v in make_batch(N, cfg["nz"], seed=seed).items()}
+    net.set_inputs(tb["x_g"], tb["cond_g"], tb["cond2_g"], tb["eps"])
+    got = net.forward_generator().cpu().numpy()
+    o = O.Oracle(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], cfg)
+    P = {k: torch.from_numpy(v) for k, v in params.items()}
+    with torch.no_grad():
+        y, y2 = o.cond_embeddings(tb["cond_g"], tb["cond2_g"], P)
+        x_hat, zm, zl = o.generator(tb["x_g"], y, y2, tb["eps"], P)
+    return {"x_hat (vertex-L2)": vertex_l2(got, x_hat.numpy()), "x_hat (max-rel)": rel(got, x_hat.numpy()),
+            "z_mean": rel(net.z_mean.cpu().numpy(), zm.numpy()), "z_logvar": rel(net.z_logvar.cpu().numpy(), zl.numpy())}
