@@ -109,6 +109,9 @@ class ConvSite:
         self.ref_rows_in = U.shape[1] if U is not None else L.shape[0]
         self.ref_rows_out = D.shape[0] if D is not None else L.shape[0]
         self.nnz = int(topo.rescale_L(L).nnz)
+        # The reference computes pool(act(conv + b)) (lib/models.py:164-168); folding D into the operators computes
+        # act(pool(conv) + b), which is the same only if D selects rows.  Callers that fuse a bias / activation check this.
+        self.pool_is_selection = D is None or topo.is_selection(D)
         if U is not None and topo.is_identity(U, tol=1e-6):
             U = None     # factor-1 levels: identity up to 5e-11
         if D is not None and topo.is_identity(D, tol=0):

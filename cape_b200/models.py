@@ -59,6 +59,8 @@ class CAPE(object):
         self.net = None
         self.rng = np.random.RandomState(seed)
         self.global_step = 0
+        # where the current weights come from: "init" (random initialisers), "checkpoint", "fit", "set"
+        self._weights_source = "init"
 
     # ---- graph -------------------------------------------------------------------------------------------
     def build_graph(self, input_num_verts, nn_input_channel, phase="train"):
@@ -73,7 +75,26 @@ class CAPE(object):
         return self
 
     def _get_path(self, folder):
-        return os.path.join(folder, self.name)
+        """<folder>/<experiment name> (lib/models.py:204-207); config_parser's default name is None -> no sub-folder."""
+        name = self.name if self.name is not None else ""
+        if not isinstance(name, str):
+            raise ValueError("experiment name must be a string, got %r" % (name,))
+        return os.path.join(folder, name)
+
+    def _get_session(self, sess=None):
+        """The reference's inference entry points open a session and restore the newest checkpoint when none is
+        passed (lib/models.py:209-215, 941, 1040, 1140); with no TF session here, "restoring" happens once: weights
+        that are still the random initialisers are replaced by the newest checkpoint, and a missing checkpoint is an
+        error instead of a silent run on random weights.  A non-None `sess`, `fit`, `restore` or `load_weights`
+        count as "the caller has put weights in place"."""
+        if sess is None and self._weights_source == "init":
+            self.restore()
+        return self
+
+    def load_weights(self, values):
+        """Set all weights from {TF variable name: array} (e.g. cape_b200.tf_checkpoint.read_checkpoint)."""
+        self.net.set_params(values)
+        self._weights_source = "set"
 
     def save(self, step):
         path = self._get_path(self.checkpoint_dir)
@@ -101,6 +122,7 @@ class CAPE(object):
                 if "momentum/" + n in z.files:
                     P._view(P.mom, n).copy_(torch.as_tensor(z["momentum/" + n].reshape(-1)))
         self.global_step = int(z["global_step"])
+        self._weights_source = "checkpoint"
         return filename
 
     def get_var(self, name):
@@ -138,6 +160,7 @@ class CAPE(object):
             if not self.name:
                 raise ValueError("Please provide an expriment name by setting the --name flag.")   # models.py:858-859
             start_step, self.global_step = 1, 0
+        self._weights_source = "fit"
         losses = []
         indices_g, indices_d = collections.deque(), collections.deque()
         net = self.net
@@ -168,6 +191,7 @@ class CAPE(object):
 
     # ---- inference entry points (lib/models.py:931-1174) --------------------------------------------------------
     def encode(self, data=None, cond=None, cond2=None):
+        self._get_session(None)
         size, N, net = data.shape[0], self.batch_size, self.net
         zm, zl = np.zeros((size, self.nz), np.float32), np.zeros((size, self.nz), np.float32)
         zc = np.zeros((size, self.nz_cond), np.float32)
@@ -183,6 +207,7 @@ class CAPE(object):
         return zm, zl, zc, zc2
 
     def encode_only_condition(self, cond=None, cond2=None):
+        self._get_session(None)
         size, N, net = cond.shape[0], self.batch_size, self.net
         zc = np.zeros((size, self.nz_cond), np.float32)
         zc2 = np.zeros((size, self.nz_cond2), np.float32)
@@ -195,6 +220,7 @@ class CAPE(object):
         return zc, zc2
 
     def predict(self, data, cond=None, cond2=None, labels=None, sess=None, phase="train"):
+        self._get_session(sess)
         size, N, net = data.shape[0], self.batch_size, self.net
         preds = np.zeros((size,) + data.shape[1:], np.float32)
         lr_, ll_, le_ = [], [], []
@@ -234,6 +260,7 @@ class CAPE(object):
     def decode(self, data, cond=None, cond2=None):
         """data: z_total [size, nz+nz_cond+nz_cond2]; cond / cond2: condition EMBEDDINGS (lib/models.py:1128-1174);
         a single condition row is broadcast over the batch as in the demos (:1152-1153)."""
+        self._get_session(None)
         size, N, net = data.shape[0], self.batch_size, self.net
         x_rec = np.zeros((size, self.input_num_verts, self.nn_input_channel), np.float32)
         for b in range(0, size, N):

@@ -115,6 +115,10 @@ class ChebLayer:
     def __init__(self, net, site, F, C, Fout, W, gW, bias=None, gbias=None, act=ACT_NONE, Wa=None, gWa=None,
                  bias_per_row=False, need_dx=True, maxN=1, n_cs_slots=1, name=""):
         self.net, self.tp, self.site, self.name = net, net.tp, site, name
+        if (bias is not None or act != ACT_NONE) and not site.pool_is_selection:
+            raise NotImplementedError("%s: the down-sampling matrix is not a pure row selection, so pooling cannot be "
+                                      "folded in front of the bias/activation (lib/models.py:164-168 applies them "
+                                      "before the pool)" % name)
         self.F, self.C, self.Fout, self.K = F, C, Fout, site.K
         K = self.K
         self.W3, self.gW3 = W.view(F + C, K, Fout), gW.view(F + C, K, Fout)
@@ -380,7 +384,9 @@ class GNBlock:
         self.lin1 = mk(lin, self.Ft, self.mid, "graph_linear_1", "lin1")
         self.conv = mk(conv, self.mid, self.mid, "graph_conv", "graph_conv")
         self.lin2 = mk(lin, self.mid, Fo, "graph_linear_2", "lin2")
-        self.lin_in = mk(lin, self.Ft, Fo, "graph_linear_input", "lin_in")
+        # the skip connection is projected only when the channel counts differ (lib/models.py:764-768)
+        self.lin_in = (mk(lin, self.Ft, Fo, "graph_linear_input", "lin_in")
+                       if (scope + "/graph_linear_input/weights") in net.specs else None)
         self.gn = []
         for sc, C in (("group_norm", self.Ft), ("group_norm_1", self.mid), ("group_norm_2", self.mid)):
             self.gn.append(dict(C=C, G=min(32, C), gamma=w(scope + "/" + sc + "/gamma"), beta=w(scope + "/" + sc + "/beta"),
@@ -394,7 +400,7 @@ class GNBlock:
         self.dH1, self.dA2, self.dH2, self.dA3 = z(N, M, self.mid), z(N, M, self.mid), z(N, M, self.mid), z(N, M, self.mid)
 
     def layers(self):
-        return [self.lin1, self.conv, self.lin2, self.lin_in]
+        return [l for l in (self.lin1, self.conv, self.lin2, self.lin_in) if l is not None]
 
     def fwd(self, x, ycat, out):
         tp, N = self.tp, x.shape[0]
@@ -408,18 +414,24 @@ class GNBlock:
         E.gn_relu_fwd(tp, self.H2, g2["gamma"], g2["beta"], self.A3, g2["stats"], g2["G"])
         l2, li = self.lin2, self.lin_in
         terms = [dict(src=self.A3, op=-1, F=self.mid, src_rows=self.rows, src_stride=self.mid, w=l2.W3[:, 0, :],
-                      w_stride=self.Fo, wT=l2.Wt[:, 0, :], wT_stride=self.mid),
-                 dict(src=self.Z, op=-1, F=self.Ft, src_rows=self.rows, src_stride=self.Ft, w=li.W3[:, 0, :],
-                      w_stride=self.Fo, wT=li.Wt[:, 0, :], wT_stride=self.Ft)]
+                      w_stride=self.Fo, wT=l2.Wt[:, 0, :], wT_stride=self.mid)]
+        if li is not None:
+            terms.append(dict(src=self.Z, op=-1, F=self.Ft, src_rows=self.rows, src_stride=self.Ft, w=li.W3[:, 0, :],
+                              w_stride=self.Fo, wT=li.Wt[:, 0, :], wT_stride=self.Ft))
         cheb_call(tp, N, self.rows, self.Fo, terms, out,
-                  tag=("dec/res:out", l2.alg_bytes(N, "fwd") + li.alg_bytes(N, "fwd")))
+                  tag=("dec/res:out", l2.alg_bytes(N, "fwd") + (li.alg_bytes(N, "fwd") if li is not None else 0)))
+        if li is None:
+            axpy(tp, out, self.Z[:N], 1.0)               # identity skip connection
 
     def bwd(self, x, ycat, dout, dx, dycat):
         """dout: gradient w.r.t. the block output; dx: gradient w.r.t. the block input x (written); dycat +=."""
         tp, N = self.tp, dout.shape[0]
         g0, g1, g2 = self.gn
         self.lin2.bwd(self.A3, None, dout, dx=self.dA3)
-        self.lin_in.bwd(self.Z, None, dout, dx=self.dZ)
+        if self.lin_in is not None:
+            self.lin_in.bwd(self.Z, None, dout, dx=self.dZ)
+        else:
+            self.dZ[:N].copy_(dout)
         E.gn_relu_bwd(tp, self.H2, self.A3, self.dA3, g2["gamma"], g2["stats"], self.dH2, g2["dgamma"], g2["dbeta"], g2["G"])
         self.conv.bwd(self.A2, None, self.dH2, dx=self.dA2)
         E.gn_relu_bwd(tp, self.H1, self.A2, self.dA2, g1["gamma"], g1["stats"], self.dH1, g1["dgamma"], g1["dbeta"], g1["G"])

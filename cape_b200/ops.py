@@ -90,8 +90,15 @@ def chebyshev5(x, L, W, K, bias=None, activation=None, pool=None, unpool=None):
     index fin*K + k.  Optional fusions: `unpool` U applied to x first (models.py:750,782), `bias`+`activation`
     ('b1leakyrelu' | 'b1relu' | None, models.py:105-121) and `pool` D applied last (models.py:168)."""
     tp = topology_for(x.device)
-    site = _site(tp, L, K, unpool, pool)
     act = {None: ACT_NONE, "b1leakyrelu": ACT_LEAKY, "b1relu": ACT_RELU}[activation]
+    if pool is not None and (bias is not None or act != ACT_NONE):
+        from . import topology as topo
+        if not topo.is_selection(pool):
+            # pooling commutes with the pointwise bias/activation only for row selections (the reference's D): a
+            # general sampling matrix is applied after them, as the reference does (lib/models.py:164-168)
+            y = _ChebFn.apply(x, W, bias, _site(tp, L, K, unpool, None), tp, act)
+            return poolwT(y, pool)
+    site = _site(tp, L, K, unpool, pool)
     return _ChebFn.apply(x, W, bias, site, tp, act)
 
 

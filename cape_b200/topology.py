@@ -3,7 +3,8 @@
 Host-side counterpart of the reference's topology prep:
   - `laplacian`, `rescale_L`  : lib/mesh_sampling.py:10-38 (same names, same arithmetic in fp32)
   - `load_graph_mtx`          : lib/load_data.py:7-32 (same return convention) -- reads the pickle-free
-                                copy of data/transform_matrices/** made by tools/pack_topology.py
+                                copy of data/transform_matrices/** that cape_b200/pack_topology.py makes
+                                from the user's reference checkout (licensed data: not part of this repo)
 The reference turns every scipy matrix into a tf.SparseTensor and runs one SpMM per Chebyshev order and
 per pool/unpool (lib/models.py:74-96,141-149).  Here the operators are constants, so they are composed
 offline:  op_k = D . T_k(L~) . U  -- one sparse "row-gather" per polynomial order with pooling (row
@@ -43,7 +44,14 @@ def rescale_L(L, lmax=2):
 def _npz():
     if "npz" not in _cache:
         if not os.path.exists(_DATA):
-            raise FileNotFoundError("%s missing: run tools/pack_topology.py in the build container" % _DATA)
+            from . import pack_topology
+            ref = pack_topology.default_reference()
+            if ref is None:
+                raise FileNotFoundError(
+                    "%s missing and no reference checkout to build it from: the SMPL mesh hierarchy is licensed data of "
+                    "qianlim/CAPE and is not shipped here.  Run `python -m cape_b200.pack_topology --reference "
+                    "/path/to/CAPE` (or set CAPE_REFERENCE) once." % _DATA)
+            pack_topology.pack(ref, _DATA)
         _cache["npz"] = np.load(_DATA)
     return _cache["npz"]
 
@@ -95,6 +103,14 @@ def is_identity(S, tol=1e-9):
         return False
     d = S - sp.identity(S.shape[0], dtype=S.dtype, format="csr")
     return d.nnz == 0 or float(np.abs(d.data).max()) <= tol
+
+
+def is_selection(S):
+    """True if S has exactly one entry, equal to 1, in every row (a pure row selection, like the reference's
+    down-sampling matrices D).  Only then does pooling commute with a pointwise bias/activation."""
+    S = sp.csr_matrix(S, copy=True)
+    S.eliminate_zeros()
+    return bool(S.nnz == S.shape[0] and np.all(np.diff(S.indptr) == 1) and np.all(S.data == 1))
 
 
 def cheb_polynomials(L, K):

@@ -33,7 +33,7 @@ def test_encode_decode_predict_match_oracle(hierarchy):
     m = _model(h, batch_size=4)
     specs = m.net.specs
     params = parity.calibrated_params(specs, 11)
-    m.net.set_params(params)
+    m.load_weights(params)
     n = 6                                                     # 1.5 batches: exercises the zero padding
     b = make_batch(n, 64, seed=5)
     o = O.Oracle(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], m.cfg)
@@ -85,6 +85,29 @@ def test_checkpoint_roundtrip(hierarchy, tmp_path):
     assert all(np.array_equal(before[k], after[k]) for k in before)
     assert set(np.load(fn).files) >= set(before)          # keyed by the reference's TF variable names
     assert m.get_var("generator/decoder/outputs/bias").shape == (1, 6890, 3)
+
+
+def test_inference_entry_points_restore_the_checkpoint(hierarchy, tmp_path):
+    """encode/decode on a freshly built model restore the newest checkpoint like the reference's _get_session
+    (lib/models.py:209-215) -- save -> new CAPE -> decode reproduces the saved model's output -- and refuse to run on
+    random initialisers when there is none."""
+    m = _model(hierarchy, batch_size=2)
+    m.checkpoint_dir = str(tmp_path)
+    m.load_weights(parity.calibrated_params(m.net.specs, 5))
+    z = np.random.RandomState(1).normal(size=(2, 128)).astype(np.float32)
+    want = m.decode(z, z[:, 64:96], z[:, 96:])
+    m.save(3)
+    m2 = _model(hierarchy, batch_size=2)
+    m2.checkpoint_dir = str(tmp_path)
+    assert m2._weights_source == "init"
+    got = m2.decode(z, z[:, 64:96], z[:, 96:])
+    assert m2._weights_source == "checkpoint" and np.array_equal(got, want)
+    m3 = _model(hierarchy, batch_size=2)
+    m3.checkpoint_dir = str(tmp_path / "empty")
+    with pytest.raises(FileNotFoundError):
+        m3.decode(z, z[:, 64:96], z[:, 96:])
+    m3.name = None                                  # config_parser's default: checkpoints directly under the folder
+    assert m3._get_path("x") == "x/"
 
 
 def test_prefetched_inputs_equal_direct_inputs(hierarchy):
