@@ -25,7 +25,24 @@ class ConvArgs(C.Structure):
     _fields_ = [("N", C.c_int), ("rows_out", C.c_int), ("ncols", C.c_int), ("nterms", C.c_int),
                 ("terms", Term * MAX_TERMS), ("cond", C.c_void_p), ("C", C.c_int), ("epilogue", C.c_int),
                 ("act", C.c_int), ("alpha", C.c_float), ("bias", C.c_void_p), ("bias_per_row", C.c_int),
-                ("aux", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p)]
+                ("aux", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p), ("precise", C.c_int), ("plain_only", C.c_int)]
+
+
+class ApplyTerm(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("op", C.c_int), ("src_rows", C.c_int), ("src_stride", C.c_int), ("acc", C.c_int),
+                ("scale", C.c_float), ("wc", C.c_void_p), ("wc_stride", C.c_int)]
+
+
+class ApplyArgs(C.Structure):
+    _fields_ = [("N", C.c_int), ("rows_out", C.c_int), ("ncols", C.c_int), ("nterms", C.c_int),
+                ("terms", ApplyTerm * MAX_TERMS), ("cond", C.c_void_p), ("C", C.c_int), ("epilogue", C.c_int),
+                ("act", C.c_int), ("alpha", C.c_float), ("bias", C.c_void_p), ("bias_per_row", C.c_int),
+                ("aux", C.c_void_p), ("out", C.c_void_p), ("out_stride", C.c_int), ("out2", C.c_void_p)]
+
+
+class WPrep(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("Fin", C.c_int), ("K", C.c_int), ("Fout", C.c_int), ("wt", C.c_void_p),
+                ("wt_lo", C.c_void_p), ("wk", C.c_void_p), ("wk_lo", C.c_void_p)]
 
 
 class DwArgs(C.Structure):
@@ -45,8 +62,11 @@ SIGNATURES = {
     "cape_topology_add_operator": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cape_topology_reserve_workspace": (C.c_int, [C.c_void_p, C.c_int64]),
     "cape_set_tensor_cores": (C.c_int, [C.c_int]),
+    "cape_tensor_cores_enabled": (C.c_int, []),
+    "cape_weight_prep": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "cape_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "cape_cheb_fwd": (C.c_int, [C.c_void_p, C.POINTER(ConvArgs), C.c_void_p]),
+    "cape_apply": (C.c_int, [C.c_void_p, C.POINTER(ApplyArgs), C.c_void_p]),
     "cape_cheb_dw": (C.c_int, [C.c_void_p, C.POINTER(DwArgs), C.c_void_p]),
     "cape_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int,
                               C.c_void_p, C.c_void_p]),

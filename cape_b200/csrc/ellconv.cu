@@ -655,8 +655,8 @@ extern "C" int cape_cheb_fwd(cape_topology* t, const cape_conv_args* a, void* st
   p.nslots = 0;
   for (int i = 0; i < a->nterms; ++i) {
     const cape_term& s = a->terms[i];
-    CAPE_REQUIRE(s.src && s.w && s.F > 0, "term needs src, w and F > 0");
-    CAPE_REQUIRE(s.src_stride >= s.F && s.w_stride >= a->ncols, "bad strides");
+    CAPE_REQUIRE(s.src && (s.w || a->plain_only) && s.F > 0, "term needs src, w and F > 0");
+    CAPE_REQUIRE(s.src_stride >= s.F && (s.w_stride >= a->ncols || a->plain_only), "bad strides");
     TermDev& d = p.terms[i];
     if (get_op(t, s.op, a->rows_out, s.src_rows, &d.op) != 0) return -1;
     d.src = s.src; d.F = s.F; d.src_rows = s.src_rows; d.src_stride = s.src_stride; d.w_stride = s.w_stride; d.w2_stride = s.w2_stride;
@@ -693,6 +693,8 @@ extern "C" int cape_cheb_fwd(cape_topology* t, const cape_conv_args* a, void* st
   if (a->epilogue == CAPE_EPI_AFFINE) CAPE_REQUIRE(dual, "AFFINE epilogue needs a w2 term");
   if (a->epilogue == CAPE_EPI_SLOPE || a->epilogue == CAPE_EPI_DUALMASK) CAPE_REQUIRE(a->aux, "epilogue needs aux");
   p.wvec = wvec ? 1 : 0;
+  p.split_rn = g_tuning[0];
+  p.precise = a->precise;
   p.ovec = (a->ncols % 4 == 0) && aligned16(a->out) && (!a->out2 || aligned16(a->out2)) && (!a->aux || aligned16(a->aux));
   const int BNsel = a->ncols <= 32 ? 32 : 64;
   if (p.nslots > 0) {
@@ -700,10 +702,18 @@ extern "C" int cape_cheb_fwd(cape_topology* t, const cape_conv_args* a, void* st
     CAPE_REQUIRE(max_samples * p.nslots * BNsel <= BM * AS_STRIDE, "rows_out too small for the condition staging buffer");
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->plain_only) {
+    const int rc = launch_gemm_tc(t, p, dual, st);
+    if (rc != 0) return rc < 0 ? rc : 0;
+    CAPE_REQUIRE(false, "plain_only call not eligible for the TMA-fed kernel (needs the tensor-core path, all terms "
+                        "identity with wT and wT_lo, ncols % 16 == 0, 16-byte aligned operands)");
+  }
   {
     int rc = launch_thin_fwd(t, p, dual, st);             // <= 4 input channels: streaming kernel
     if (rc != 0) return rc < 0 ? rc : 0;
     rc = launch_thinout_fwd(t, p, dual, st);              // <= 4 output columns: contract first, then gather
+    if (rc != 0) return rc < 0 ? rc : 0;
+    rc = launch_gemm_tc(t, p, dual, st);                  // plain operands only: TMA-fed tcgen05 contraction
     if (rc != 0) return rc < 0 ? rc : 0;
     rc = launch_ellconv_tc(t, p, dual, st);               // tcgen05 path when eligible (writes the stashes itself)
     if (rc != 0) return rc < 0 ? rc : 0;

@@ -45,9 +45,13 @@ struct ConvParams {
   float* out;
   float* out2;
   int wvec, ovec;
+  int split_rn;   // experiment (cape_set_tuning key 0): 0 = truncating 3xTF32 split, 1 = round to nearest, 2 = + lo*lo term
+  int precise;    // cape_conv_args.precise: split accumulation chains (gemm_tc.cu)
 };
 
 
+// all-plain-operand calls (every term an identity operator) on the TMA-fed kernel (gemm_tc.cu): 1 = launched, 0 = not eligible
+int launch_gemm_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaStream_t st);
 // tcgen05 path (ellconv_tc.cu): returns 1 if it launched, 0 if the problem is not eligible, <0 on error.
 int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaStream_t st);
 bool tensor_cores_enabled();
@@ -67,7 +71,8 @@ int launch_dw_dense_tma(const cape_topology* t, const cape_dw_args* a, const OpV
 // experiment knobs (cape_set_tuning): [1] = 1 disables the TMA dense-dW kernel, [2] = its lo-part mode (1 = rna, wrong
 // on purpose: shows the tensor core truncates), [3] = 2: 128- instead of 256-wide G sub-tiles for wide outputs, [4] = 1: weight tiles of the wide conv kernel by the
 // producer warps instead of TMA, [5] = 1: one narrow-kernel CTA per SM (bigger L1), [6] = 1: identity-term basis
-// tiles by the producer warps instead of TMA, [7] = 1: thin-output layers on the generic kernels
-extern int g_tuning[8];
+// tiles by the producer warps instead of TMA, [7] = 1: thin-output layers on the generic kernels, [8] = 1: no TMA-fed
+// plain-operand kernel (gemm_tc.cu), [0]: operand-split experiment (ConvParams.split_rn)
+extern int g_tuning[16];
 
 }  // namespace cape

@@ -1,0 +1,465 @@
+// Dense multi-term contraction on TMA + tcgen05 (sm_100a):  out[R, c] = epi( sum_t A_t[R, 0:F_t] . B_t[0:F_t, c] )
+//
+// This is cape_cheb_fwd for calls whose terms are all PLAIN tensors (identity operators): 1x1 convs, the two halves
+// of the split convolution forms the host uses -- "contract first" (Z = X . [W_0 | W_1 | ...], the operators are then
+// applied to the narrower Z by cape_apply) and "basis first" (cape_apply writes the Chebyshev basis / the narrow-side
+// tensors op_k^T G, which are then contracted here) -- and the GroupNorm blocks' linear layers.  Nothing is gathered
+// in this kernel, so the operand pipeline is pure TMA:
+//
+//   * warp 13 issues the A boxes (128 rows x 32 k of term t, SWIZZLE_128B: a box IS a K-major UMMA operand tile; the
+//     raw fp32 words are the "hi" operand because kind::tf32 reads their top 19 bits), ring of `sr` stages;
+//   * warp 14 issues the weight boxes (hi = raw K-major copy, lo = pre-split copy, BN columns x 32 k), ring of `sb`;
+//   * warps 0-7 derive the lo tile of A (x - trunc_tf32(x)) from shared memory, ring of `sl` stages;
+//   * warp 8 issues tcgen05.mma kind::tf32 (3xTF32: hi*hi + lo*hi + hi*lo) into TMEM;
+//   * warps 9-12 drain TMEM: condition broadcast / bias / activation / backward masks, float4 stores.
+//
+// Output columns are processed in GROUPS of `gw` columns (<= 512 TMEM columns per group, `nsub` MMA sub-tiles of BN
+// columns); a persistent CTA walks (row tile, column group) pairs, so any ncols % 16 == 0 works (544-wide GroupNorm
+// blocks included) and a group's accumulators can be double-buffered against the previous group's epilogue.
+//
+// PRECISE mode (cape_conv_args.precise): the tensor core's fp32 accumulator TRUNCATES on every accumulate, which
+// shrinks a dot product by ~2^-25 per MMA on its chain -- 8.6e-6 relative for a 1024-long reduction at three MMAs per
+// k-step (measured, tests/gpu_tf32_accuracy.py), 2e-5 after the eight encoder layers, and the VAE's exp(logvar)
+// amplifies exactly that.  Precise groups are 128 columns wide and keep FOUR accumulators: the hi*hi products go
+// round-robin to three of them (chains a third as long), the small lo*hi + hi*lo corrections to the fourth (their
+// truncation error is 2^-11 smaller); the epilogue adds the four in fp32 with round-to-nearest.  Same MMA count,
+// more A traffic (one pass over the A tiles per 128 columns); used for the encoder's forward convs.
+#include "common.cuh"
+#include "ellconv_params.cuh"
+#include "tc_common.cuh"
+
+namespace cape {
+
+namespace {
+
+using namespace tc;
+
+constexpr int G_CONV_WARPS = 8;
+constexpr int G_CONV_THREADS = G_CONV_WARPS * 32;
+constexpr int G_MMA_WARP = 8, G_EPI_WARP0 = 9, G_TMA_A_WARP = 13, G_TMA_B_WARP = 14;
+constexpr int G_EPI_WARPS = 4;
+constexpr int G_THREADS = 15 * 32;
+constexpr int G_A_TILE = BM * 128;          // 128 rows x 32 fp32
+constexpr int G_MAX_STAGES = 8;
+constexpr int G_TERMS = 4;
+constexpr int G_QS_FLOATS = 2048;           // condition vectors of the group's columns, double-buffered halves
+constexpr int G_SMEM_LIMIT = 227 * 1024;
+
+struct GMaps {
+  CUtensorMap a[G_TERMS];      // source rows of term t: boxes of 32 f x 128 rows
+  CUtensorMap bh[G_TERMS];     // K-major weight copy (raw fp32 = hi operand): boxes of 32 f x BN columns
+  CUtensorMap bl[G_TERMS];     // its pre-split low part
+};
+
+struct GPlan {
+  int gw, nsub, ngroups, ntiles;       // group width (columns), BN-wide sub-tiles per group, groups per row tile, row tiles
+  int nchain, corr, nbuf, tmem_cols;   // main accumulators per group, 1 = separate correction accumulator, TMEM buffers
+  int sr, sl, sb;                      // ring depths: A raw (TMA), A lo (converters), B (TMA)
+};
+
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {     // K-major SWIZZLE_128B operand tile
+  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_constant__ ConvParams p,
+                                                               const __grid_constant__ GMaps maps,
+                                                               const __grid_constant__ GPlan g) {
+  constexpr int B_TILE = BN * 128;             // hi or lo tile of BN weight columns x 32 k
+  constexpr int B_STAGE = 2 * B_TILE;
+  extern __shared__ uint8_t smem_raw[];
+  char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  char* raw_ring = smem;
+  char* lo_ring = raw_ring + g.sr * G_A_TILE;
+  char* b_ring = lo_ring + g.sl * G_A_TILE;
+  float* qs_all = reinterpret_cast<float*>(b_ring + g.sb * B_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qs_all + G_QS_FLOATS);
+  // raw_full[8] raw_empty[8] lo_full[8] lo_empty[8] b_full[8] b_empty[8] t_full[2] t_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 * G_MAX_STAGES + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_rf = smem_u32(bars), bar_re = smem_u32(bars + G_MAX_STAGES);
+  const uint32_t bar_lf = smem_u32(bars + 2 * G_MAX_STAGES), bar_le = smem_u32(bars + 3 * G_MAX_STAGES);
+  const uint32_t bar_bf = smem_u32(bars + 4 * G_MAX_STAGES), bar_be = smem_u32(bars + 5 * G_MAX_STAGES);
+  const uint32_t bar_tf = smem_u32(bars + 6 * G_MAX_STAGES), bar_te = smem_u32(bars + 6 * G_MAX_STAGES + 2);
+
+  if (warp == G_MMA_WARP) {
+    if (lane == 0) {
+      for (int s = 0; s < G_MAX_STAGES; ++s) {
+        mbar_init(bar_rf + 8 * s, 1); mbar_init(bar_re + 8 * s, 1);
+        mbar_init(bar_lf + 8 * s, G_CONV_WARPS); mbar_init(bar_le + 8 * s, 1);
+        mbar_init(bar_bf + 8 * s, 1); mbar_init(bar_be + 8 * s, 1);
+      }
+      for (int s = 0; s < 2; ++s) { mbar_init(bar_tf + 8 * s, 1); mbar_init(bar_te + 8 * s, G_EPI_WARPS); }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), (uint32_t)g.tmem_cols);
+  }
+  if (warp == G_TMA_A_WARP && lane == 0)
+    for (int t = 0; t < p.nterms; ++t) tma_prefetch_desc(&maps.a[t]);
+  if (warp == G_TMA_B_WARP && lane == 0)
+    for (int t = 0; t < p.nterms; ++t) { tma_prefetch_desc(&maps.bh[t]); tma_prefetch_desc(&maps.bl[t]); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nacc = g.nchain + g.corr;
+  const int nwork = g.ntiles * g.ngroups;
+
+  if (warp < G_CONV_WARPS) {
+    // =========================== converters: lo tile of every A chunk ===========================
+    const int l8 = tid & 7, rs = tid >> 3;
+    int sr = 0, sl = 0;
+    uint32_t phr = 0, phl = 0;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+      for (int t = 0; t < p.nterms; ++t) {
+        for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+          mbar_wait(bar_rf + 8 * sr, (phr >> sr) & 1u);
+          mbar_wait(bar_le + 8 * sl, ((phl >> sl) & 1u) ^ 1u);
+          const char* hi = raw_ring + (size_t)sr * G_A_TILE;
+          char* lo = lo_ring + (size_t)sl * G_A_TILE;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = rs + 32 * i;
+            const uint32_t off = (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4));
+            const float4 v = *reinterpret_cast<const float4*>(hi + off);
+            float4 l;
+            l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+            l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+            l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+            l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+            *reinterpret_cast<float4*>(lo + off) = l;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_lf + 8 * sl);
+          phr ^= 1u << sr; phl ^= 1u << sl;
+          if (++sr == g.sr) sr = 0;
+          if (++sl == g.sl) sl = 0;
+        }
+      }
+    }
+  } else if (warp == G_TMA_A_WARP) {
+    // =========================== TMA: A tiles ===========================
+    if (lane == 0) {
+      int sr = 0;
+      uint32_t phr = 0;
+      for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int row0 = (w / g.ngroups) * BM;
+        for (int t = 0; t < p.nterms; ++t) {
+          for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+            mbar_wait(bar_re + 8 * sr, ((phr >> sr) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(bar_rf + 8 * sr, (uint32_t)G_A_TILE);
+            tma_load_2d(smem_u32(raw_ring + (size_t)sr * G_A_TILE), &maps.a[t], f0, row0, bar_rf + 8 * sr);
+            phr ^= 1u << sr;
+            if (++sr == g.sr) sr = 0;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == G_TMA_B_WARP) {
+    // =========================== TMA: weight tiles (hi = raw, lo = pre-split) ===========================
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t phb = 0;
+      for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int col0 = (w % g.ngroups) * g.gw;
+        for (int t = 0; t < p.nterms; ++t) {
+          for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+            for (int s = 0; s < g.nsub; ++s) {
+              mbar_wait(bar_be + 8 * sb, ((phb >> sb) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(bar_bf + 8 * sb, (uint32_t)B_STAGE);
+              const uint32_t dst = smem_u32(b_ring + (size_t)sb * B_STAGE);
+              tma_load_2d(dst, &maps.bh[t], f0, col0 + s * BN, bar_bf + 8 * sb);
+              tma_load_2d(dst + B_TILE, &maps.bl[t], f0, col0 + s * BN, bar_bf + 8 * sb);
+              phb ^= 1u << sb;
+              if (++sb == g.sb) sb = 0;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == G_MMA_WARP) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int sr = 0, sl = 0, sb = 0, it = 0;
+      uint32_t phr = 0, phl = 0, phb = 0;
+      for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+        const int buf = it % g.nbuf;
+        const uint32_t use = (uint32_t)(it / g.nbuf);
+        mbar_wait(bar_te + 8 * buf, (use & 1u) ^ 1u);            // the epilogue has drained this buffer
+        tc_fence_after();
+        const uint32_t tb = tmem_base + (uint32_t)(buf * g.gw * nacc);
+        const uint32_t corr_off = (uint32_t)(g.nchain * g.gw);
+        uint32_t init_main = 0, init_corr = 0;                    // bit set: that accumulator holds data already
+        int kstep = 0;
+        for (int t = 0; t < p.nterms; ++t) {
+          for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+            mbar_wait(bar_rf + 8 * sr, (phr >> sr) & 1u);         // TMA bytes of the raw tile
+            mbar_wait(bar_lf + 8 * sl, (phl >> sl) & 1u);         // its lo tile
+            tc_fence_after();
+            const uint64_t a_hi = make_desc_k(smem_u32(raw_ring + (size_t)sr * G_A_TILE));
+            const uint64_t a_lo = make_desc_k(smem_u32(lo_ring + (size_t)sl * G_A_TILE));
+            for (int s = 0; s < g.nsub; ++s) {
+              mbar_wait(bar_bf + 8 * sb, (phb >> sb) & 1u);
+              tc_fence_after();
+              const uint32_t baddr = smem_u32(b_ring + (size_t)sb * B_STAGE);
+              const uint64_t b_hi = make_desc_k(baddr), b_lo = make_desc_k(baddr + B_TILE);
+#pragma unroll
+              for (int ks = 0; ks < BK / 8; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);          // +32 bytes along K inside the swizzle row
+                const int chain = g.corr ? (kstep + ks) % g.nchain : 0;
+                const uint32_t d_main = tb + (uint32_t)(chain * g.gw + s * BN);
+                const uint32_t d_corr = g.corr ? tb + corr_off + (uint32_t)(s * BN) : d_main;
+                const uint32_t mbit = 1u << (chain * g.nsub + s);
+                umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (init_main & mbit) ? 1u : 0u);
+                init_main |= mbit;
+                umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, (!g.corr || (init_corr >> s) & 1u) ? 1u : 0u);
+                init_corr |= 1u << s;
+                umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+              }
+              umma_commit(bar_be + 8 * sb);
+              phb ^= 1u << sb;
+              if (++sb == g.sb) sb = 0;
+            }
+            kstep += BK / 8;
+            umma_commit(bar_re + 8 * sr);
+            umma_commit(bar_le + 8 * sl);
+            phr ^= 1u << sr; phl ^= 1u << sl;
+            if (++sr == g.sr) sr = 0;
+            if (++sl == g.sl) sl = 0;
+          }
+        }
+        umma_commit(bar_tf + 8 * buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== epilogue warps ===========================
+    const int et = tid - G_EPI_WARP0 * 32;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int total_ksteps = 0;
+    for (int t = 0; t < p.nterms; ++t) total_ksteps += (p.terms[t].F + BK - 1) / BK * (BK / 8);
+    const int nused = g.corr ? min(g.nchain, total_ksteps) : 1;   // main chains that received data
+    int it = 0;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+      const int buf = it % g.nbuf;
+      const uint32_t use = (uint32_t)(it / g.nbuf);
+      const int tile = w / g.ngroups, col0 = (w % g.ngroups) * g.gw;
+      const int gcols = min(g.gw, p.ncols - col0);                // real columns of this group (multiple of 16)
+      const long long row0 = (long long)tile * BM;
+      const long long R = row0 + row;
+      const bool valid = R < p.total_rows;
+      const int n = valid ? (int)(R / p.rows_out) : -1, r = valid ? (int)(R % p.rows_out) : 0;
+      const int n_first = (int)(row0 / p.rows_out);
+      float* qs = qs_all + (size_t)(it & 1) * (G_QS_FLOATS / 2);
+      if (p.nslots > 0) {
+        // condition broadcast vectors of this tile, group columns only: q[s][slot][c]
+        const long long rlast = min(p.total_rows, row0 + BM) - 1;
+        const int S = (int)(rlast / p.rows_out) - n_first + 1;
+        const int total = S * p.nslots * gcols;
+        for (int o = et; o < total; o += G_EPI_WARPS * 32) {
+          const int c = o % gcols;
+          const int slot = (o / gcols) % p.nslots;
+          const int s = o / (gcols * p.nslots);
+          const float* y = p.cond + (size_t)(n_first + s) * p.C;
+          const float* wc = p.slot_w[slot] + col0 + c;
+          const int ws = p.terms[p.slot_term[slot]].w_stride;
+          float q = 0.f;
+          for (int j = 0; j < p.C; ++j) q = fmaf(__ldg(y + j), __ldg(wc + (size_t)j * ws), q);
+          qs[o] = q;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+      }
+      mbar_wait(bar_tf + 8 * buf, use & 1u);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + (uint32_t)(buf * g.gw * nacc) + ((uint32_t)(quad * 32) << 16);
+      const size_t orow = (size_t)R * p.ncols + col0;
+      const bool use_aux = valid && (p.epilogue == CAPE_EPI_SLOPE || p.epilogue == CAPE_EPI_DUALMASK);
+      float4 axn[4];
+      if (use_aux) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) axn[j] = ldg4(p.aux + orow + 4 * j);
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < gcols; c0 += 16) {
+        float v0[16];
+        float4 axc[4];
+        if (use_aux) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) axc[j] = axn[j];
+          if (c0 + 16 < gcols) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) axn[j] = ldg4(p.aux + orow + c0 + 16 + 4 * j);
+          }
+        }
+        tmem_ld16(taddr_row + (uint32_t)c0, v0);
+        if (g.corr) {
+          // precise mode: the main chains and the correction accumulator are added here, in fp32 with round-to-nearest
+          float vc[16];
+          for (int ch = 1; ch < nused; ++ch) {
+            tmem_ld16(taddr_row + (uint32_t)(ch * g.gw + c0), vc);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v0[j] += vc[j];
+          }
+          tmem_ld16(taddr_row + (uint32_t)(g.nchain * g.gw + c0), vc);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v0[j] += vc[j];
+        }
+        if (!valid) continue;
+        for (int slot = 0; slot < p.nslots; ++slot) {
+          const TermDev& tm = p.terms[p.slot_term[slot]];
+          const float coef = tm.op.rowsum ? __ldg(tm.op.rowsum + r) : 1.f;
+          const float* q = qs + ((size_t)(n - n_first) * p.nslots + slot) * gcols + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v0[j] = fmaf(coef, q[j], v0[j]);
+        }
+        float o1[16], o2[16];
+        bool write2 = false;
+        if (p.epilogue == CAPE_EPI_LINEAR) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float v = v0[j];
+            if (p.bias != nullptr) v += __ldg(p.bias + (p.bias_per_row ? (size_t)r * p.ncols : 0) + col0 + c0 + j);
+            if (p.act == CAPE_ACT_LEAKY) v = v > 0.f ? v : p.alpha * v;
+            else if (p.act == CAPE_ACT_RELU) v = fmaxf(v, 0.f);
+            o1[j] = v;
+          }
+        } else {
+          float ax[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 a4 = axc[j >> 2];
+            ax[j] = a4.x; ax[j + 1] = a4.y; ax[j + 2] = a4.z; ax[j + 3] = a4.w;
+          }
+          if (p.epilogue == CAPE_EPI_SLOPE) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o1[j] = v0[j] * (ax[j] > 0.f ? 1.f : p.alpha);
+          } else {
+            write2 = p.out2 != nullptr;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { o1[j] = v0[j]; o2[j] = ax[j] > 0.f ? v0[j] : 0.f; }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          *reinterpret_cast<float4*>(p.out + orow + c0 + j) = make_float4(o1[j], o1[j + 1], o1[j + 2], o1[j + 3]);
+          if (write2)
+            *reinterpret_cast<float4*>(p.out2 + orow + c0 + j) = make_float4(o2[j], o2[j + 1], o2[j + 2], o2[j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_te + 8 * buf);
+    }
+  }
+
+  __syncthreads();
+  if (warp == G_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+  }
+}
+
+bool make_map(CUtensorMap* m, const float* base, unsigned long long inner, unsigned long long outer, int stride_floats,
+              int box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || base == nullptr || !aligned16(base) || stride_floats % 4 != 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  const cuuint64_t strides[1] = {(cuuint64_t)stride_floats * sizeof(float)};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN>
+int launch_gemm(const cape_topology* t, const ConvParams& p, const GMaps& maps, GPlan g, cudaStream_t st) {
+  constexpr int B_STAGE = 2 * BN * 128;
+  // ring depths from the shared-memory budget: two lo stages, three weight stages, the rest to the raw A ring
+  const int fixed = 1024 + G_QS_FLOATS * 4 + 1024;
+  g.sl = 2;
+  g.sb = 3;
+  int left = G_SMEM_LIMIT - fixed - g.sl * G_A_TILE - g.sb * B_STAGE;
+  g.sr = left / G_A_TILE;
+  if (g.sr > G_MAX_STAGES) g.sr = G_MAX_STAGES;
+  if (g.sr < 2) return 0;
+  left -= g.sr * G_A_TILE;
+  while (g.sb < G_MAX_STAGES && g.sb < 2 * g.nsub + 1 && left >= B_STAGE) { ++g.sb; left -= B_STAGE; }
+  const int smem = fixed + (g.sr + g.sl) * G_A_TILE + g.sb * B_STAGE;
+  static bool configured = false;
+  if (!configured) {
+    CAPE_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_LIMIT));
+    configured = true;
+  }
+  const int nwork = g.ntiles * g.ngroups;
+  const int grid = nwork < t->sm_count ? nwork : t->sm_count;
+  gemm_tc_kernel<BN><<<grid, G_THREADS, smem, st>>>(p, maps, g);
+  CAPE_CHECK_CUDA(cudaGetLastError());
+  count_launches(1);
+  return 1;
+}
+
+}  // namespace
+
+// 1 = launched, 0 = not eligible (the caller falls through to the gather kernels), <0 = error
+int launch_gemm_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaStream_t st) {
+  if (!tensor_cores_enabled() || g_tuning[8] == 1) return 0;
+  if (dual || p.epilogue == CAPE_EPI_AFFINE) return 0;
+  if (p.nterms > G_TERMS || p.ncols % 16 != 0 || p.ncols < 32 || !p.ovec) return 0;
+  if (p.total_rows >= (1LL << 31)) return 0;
+  long long kred = 0;
+  for (int i = 0; i < p.nterms; ++i) {
+    const TermDev& tm = p.terms[i];
+    if (tm.op.idx != nullptr || tm.src_rows != p.rows_out || !tm.vec || tm.stash != nullptr) return 0;
+    if (tm.wT == nullptr || tm.wT_lo == nullptr || (tm.wT_stride % 4) != 0 || !aligned16(tm.wT) || !aligned16(tm.wT_lo))
+      return 0;
+    kred += tm.F;
+  }
+  if (kred < 32) return 0;
+  GPlan g{};
+  const int BN = p.ncols > 64 ? 128 : (p.ncols > 32 ? 64 : 32);
+  g.ntiles = (int)((p.total_rows + BM - 1) / BM);
+  const int ncols_r = (p.ncols + BN - 1) / BN * BN;
+  if (p.precise) {
+    if (p.epilogue != CAPE_EPI_LINEAR) return 0;
+    g.gw = BN; g.nsub = 1; g.nchain = 3; g.corr = 1;
+    g.ngroups = ncols_r / BN;
+  } else {
+    g.nchain = 1; g.corr = 0;
+    g.ngroups = (ncols_r + 511) / 512;
+    const int per = (ncols_r / BN + g.ngroups - 1) / g.ngroups;      // sub-tiles per group
+    g.gw = per * BN; g.nsub = per;
+    g.ngroups = (ncols_r + g.gw - 1) / g.gw;
+  }
+  const int nacc = g.nchain + g.corr;
+  g.nbuf = (2 * g.gw * nacc <= 512) ? 2 : 1;
+  g.tmem_cols = 32;
+  while (g.tmem_cols < g.gw * nacc * g.nbuf) g.tmem_cols *= 2;
+  if (g.tmem_cols > 512) return 0;
+  if (p.nslots > 0) {
+    const long long max_samples = (BM - 1) / p.rows_out + 2;
+    if (max_samples * p.nslots * g.gw > G_QS_FLOATS / 2) return 0;
+    for (int s = 0; s < p.nslots; ++s)
+      if (p.slot_acc[s] != 0) return 0;
+  }
+  static GMaps maps;
+  for (int i = 0; i < p.nterms; ++i) {
+    const TermDev& tm = p.terms[i];
+    if (!make_map(&maps.a[i], tm.src, (unsigned long long)tm.F, (unsigned long long)p.total_rows, tm.src_stride, BM) ||
+        !make_map(&maps.bh[i], tm.wT, (unsigned long long)tm.F, (unsigned long long)p.ncols, tm.wT_stride, BN) ||
+        !make_map(&maps.bl[i], tm.wT_lo, (unsigned long long)tm.F, (unsigned long long)p.ncols, tm.wT_stride, BN))
+      return 0;
+  }
+  if (BN == 128) return launch_gemm<128>(t, p, maps, g, st);
+  if (BN == 64) return launch_gemm<64>(t, p, maps, g, st);
+  return launch_gemm<32>(t, p, maps, g, st);
+}
+
+}  // namespace cape

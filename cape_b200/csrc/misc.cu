@@ -192,6 +192,42 @@ __global__ void wtrans_kernel(const float* __restrict__ w, int Fin, int K, int F
   }
 }
 
+// All derived weight layouts of many layers in one launch (cape_weight_prep): blockIdx.y = descriptor, the blocks of a
+// row walk its (k, 32 x 32) tiles.  wt (k, c, f) goes through a shared-memory transpose, wk (k, f, c) is a straight copy.
+__global__ void __launch_bounds__(256) wprep_kernel(const cape_wprep* __restrict__ descs) {
+  __shared__ float tile[32][33];
+  const cape_wprep d = descs[blockIdx.y];
+  const int tf = (d.Fin + 31) / 32, tc = (d.Fout + 31) / 32;
+  const int ntiles = d.K * tf * tc;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+    const int k = tl / (tf * tc), f0 = ((tl / tc) % tf) * 32, c0 = (tl % tc) * 32;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int f = f0 + i, c = c0 + tx;
+      const float v = (f < d.Fin && c < d.Fout) ? d.w[((size_t)f * d.K + k) * d.Fout + c] : 0.f;
+      tile[i][tx] = v;
+      if (d.wk != nullptr && f < d.Fin && c < d.Fout) {
+        const size_t o = ((size_t)k * d.Fin + f) * d.Fout + c;
+        d.wk[o] = v;
+        if (d.wk_lo != nullptr) d.wk_lo[o] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      }
+    }
+    __syncthreads();
+    if (d.wt != nullptr) {
+      for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, f = f0 + tx;
+        if (c < d.Fout && f < d.Fin) {
+          const float v = tile[tx][i];
+          const size_t o = ((size_t)k * d.Fout + c) * d.Fin + f;
+          d.wt[o] = v;
+          if (d.wt_lo != nullptr) d.wt_lo[o] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        }
+      }
+    }
+  }
+}
+
 __global__ void tf32_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i];
@@ -307,6 +343,16 @@ extern "C" int cape_cheb_weight_transpose(const float* w, int Fin, int K, int Fo
   CAPE_REQUIRE(w && wt && Fin > 0 && K > 0 && Fout > 0, "bad arguments");
   dim3 grid((Fin + 31) / 32, (Fout + 31) / 32, K), block(32, 8);
   wtrans_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, Fin, K, Fout, wt, wt_lo);
+  CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
+  return 0;
+}
+
+extern "C" int cape_weight_prep(const cape_wprep* descs_device, int n, int blocks_per_desc, void* stream) {
+  CAPE_REQUIRE(descs_device && n > 0 && n <= 65535, "bad arguments");
+  if (blocks_per_desc < 1) blocks_per_desc = 8;
+  dim3 grid((unsigned)blocks_per_desc, (unsigned)n);
+  wprep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs_device);
   CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
   return 0;

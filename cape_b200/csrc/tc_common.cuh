@@ -82,6 +82,20 @@ __device__ __forceinline__ void split_store(float4 v, char* hi_tile, char* lo_ti
   *reinterpret_cast<float4*>(lo_tile + off) = l;
 }
 
+// Same with hi = the value ROUNDED to the nearest tf32 (low 13 bits zero, so the tensor core's truncation is a no-op):
+// lo = x - hi is then signed and at most half a tf32 ulp, the dropped lo*lo term and the truncation of lo are
+// zero-mean instead of a systematic shrink of every product.
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ void split_store_rn(float4 v, char* hi_tile, char* lo_tile, uint32_t off) {
+  float4 h, l;
+  h.x = tf32_rn(v.x); l.x = v.x - h.x;
+  h.y = tf32_rn(v.y); l.y = v.y - h.y;
+  h.z = tf32_rn(v.z); l.z = v.z - h.z;
+  h.w = tf32_rn(v.w); l.w = v.w - h.w;
+  *reinterpret_cast<float4*>(hi_tile + off) = h;
+  *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
 // MN-major SWIZZLE_128B_BASE32B operand descriptor (layout_type 1), the only MN-major layout tcgen05 accepts for
 // 32-bit operands: 32-element MN blocks of 4096 B (LBO), 4-row K groups of 512 B (SBO), 128-byte rows whose 32-byte
 // chunks are XOR-ed with (row & 3)  [cute Layout_MN_SW128_32B_Atom, Swizzle<2,5,2>].  A TMA box of 32 floats x 32 rows

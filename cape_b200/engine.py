@@ -10,8 +10,8 @@ import torch
 
 from . import _lib
 from . import topology as topo
-from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, EPI_AFFINE, EPI_DUALMASK, EPI_LINEAR, EPI_SLOPE, ConvArgs, DwArgs,
-                   check)
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, EPI_AFFINE, EPI_DUALMASK, EPI_LINEAR, EPI_SLOPE, ApplyArgs, ConvArgs,
+                   DwArgs, WPrep, check)
 
 LEAKY_ALPHA = 0.2  # tf.nn.leaky_relu default (lib/models.py:109,506,582)
 
@@ -157,9 +157,12 @@ def gemm(tp, A, B, Cout, bias=None, act=ACT_NONE, alpha=1.0, beta=0.0, tag=None)
 
 
 def cheb_call(tp, N, rows_out, ncols, terms, out, out2=None, cond=None, epilogue=EPI_LINEAR, act=ACT_NONE,
-              alpha=LEAKY_ALPHA, bias=None, bias_per_row=False, aux=None, tag=None):
-    """terms: list of dicts(src, op, F, src_rows, src_stride, w, w_stride, w2, wc, wc2) with torch tensors."""
+              alpha=LEAKY_ALPHA, bias=None, bias_per_row=False, aux=None, tag=None, precise=False, plain_only=False,
+              family="ellconv"):
+    """terms: list of dicts(src, op, F, src_rows, src_stride, w, w_stride, w2, wc, wc2) with torch tensors.
+    precise / plain_only: cape_conv_args fields of the same names (short accumulation chains; TMA-fed kernel or error)."""
     a = ConvArgs()
+    a.precise, a.plain_only = (1 if precise else 0), (1 if plain_only else 0)
     a.N, a.rows_out, a.ncols, a.nterms = N, rows_out, ncols, len(terms)
     for i, t in enumerate(terms):
         d = a.terms[i]
@@ -170,7 +173,7 @@ def cheb_call(tp, N, rows_out, ncols, terms, out, out2=None, cond=None, epilogue
         d.src_stride = t["src_stride"]
         d.w_stride = t["w_stride"]
         d.w2_stride = t.get("w2_stride", 0)
-        d.w = t["w"].data_ptr()
+        d.w = t["w"].data_ptr() if t.get("w") is not None else None
         for k in ("w2", "wc", "wc2", "wT", "w2T", "stash", "wT_lo", "w2T_lo"):
             v = t.get(k)
             setattr(d, k, v.data_ptr() if v is not None else None)
@@ -189,10 +192,68 @@ def cheb_call(tp, N, rows_out, ncols, terms, out, out2=None, cond=None, epilogue
     a.out2 = out2.data_ptr() if out2 is not None else None
     if TRACE:
         print("cheb_fwd", tag[0] if tag else None, N, rows_out, ncols, [(t["op"], t["F"]) for t in terms], flush=True)
-    with _Prof("ellconv", tag):
+    with _Prof(family, tag):
         check(tp.lib.cape_cheb_fwd(tp.h, C.byref(a), _stream()))
     if TRACE:
         torch.cuda.synchronize()
+
+
+def apply_call(tp, N, rows_out, ncols, terms, out, out2=None, out_stride=0, cond=None, epilogue=EPI_LINEAR,
+               act=ACT_NONE, alpha=LEAKY_ALPHA, bias=None, bias_per_row=False, aux=None, tag=None, family="ellconv"):
+    """cape_apply: terms = list of dicts(src, op, src_rows, src_stride, acc=0, scale=1.0, wc=None, wc_stride=0)."""
+    a = ApplyArgs()
+    a.N, a.rows_out, a.ncols, a.nterms = N, rows_out, ncols, len(terms)
+    for i, t in enumerate(terms):
+        d = a.terms[i]
+        d.src, d.op, d.src_rows, d.src_stride = t["src"].data_ptr(), t["op"], t["src_rows"], t["src_stride"]
+        d.acc, d.scale = t.get("acc", 0), t.get("scale", 1.0)
+        wc = t.get("wc")
+        d.wc = wc.data_ptr() if wc is not None else None
+        d.wc_stride = t.get("wc_stride", 0)
+    if cond is not None:
+        a.cond, a.C = cond.data_ptr(), cond.shape[1]
+        assert cond.is_contiguous()
+    a.epilogue, a.act, a.alpha = epilogue, act, alpha
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.bias_per_row = 1 if bias_per_row else 0
+    a.aux = aux.data_ptr() if aux is not None else None
+    a.out, a.out_stride = out.data_ptr(), out_stride
+    a.out2 = out2.data_ptr() if out2 is not None else None
+    if TRACE:
+        print("apply", tag[0] if tag else None, N, rows_out, ncols, [(t["op"], t.get("scale", 1.0)) for t in terms], flush=True)
+    with _Prof(family, tag):
+        check(tp.lib.cape_apply(tp.h, C.byref(a), _stream()))
+    if TRACE:
+        torch.cuda.synchronize()
+
+
+class WeightPrep:
+    """All derived weight layouts of a network in ONE launch per optimiser step (cape_weight_prep): collect the layers'
+    descriptors, upload the table once, then `run()` after every update."""
+
+    def __init__(self, tp):
+        self.tp, self.items, self.table = tp, [], None
+
+    def add(self, w, Fin, K, Fout, wt=None, wt_lo=None, wk=None, wk_lo=None):
+        self.items.append((w, Fin, K, Fout, wt, wt_lo, wk, wk_lo))
+
+    def run(self):
+        if not self.items:
+            return
+        if self.table is None:
+            arr = (WPrep * len(self.items))()
+            for d, (w, Fin, K, Fout, wt, wt_lo, wk, wk_lo) in zip(arr, self.items):
+                d.w, d.Fin, d.K, d.Fout = w.data_ptr(), Fin, K, Fout
+                for nm, t in (("wt", wt), ("wt_lo", wt_lo), ("wk", wk), ("wk_lo", wk_lo)):
+                    setattr(d, nm, t.data_ptr() if t is not None else None)
+            raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+            self.table = torch.from_numpy(raw).to(self.tp.device)
+            torch.cuda.synchronize()
+        check(self.tp.lib.cape_weight_prep(C.c_void_p(self.table.data_ptr()), len(self.items), 16, _stream()))
+
+
+def tensor_cores_enabled(tp):
+    return bool(tp.lib.cape_tensor_cores_enabled())
 
 
 def cheb_dw(tp, N, rows_out, ncols, src, op, F, src_rows, src_stride, g, dw, dw_stride, accumulate=False, tag=None,

@@ -16,7 +16,7 @@ from . import _lib
 from . import engine as E
 from . import topology as topo
 from .engine import (ACT_LEAKY, ACT_NONE, EPI_AFFINE, EPI_DUALMASK, EPI_LINEAR, EPI_SLOPE, ConvSite, Topology,
-                     act_bwd, axpy, cheb_call, cheb_dw, colsum, gemm, weight_transpose)
+                     act_bwd, axpy, cheb_call, cheb_dw, colsum, gemm)
 from .params import init_params, is_d_param, is_g_param, param_specs
 
 
@@ -113,7 +113,7 @@ class ChebLayer:
     branch) with its backward."""
 
     def __init__(self, net, site, F, C, Fout, W, gW, bias=None, gbias=None, act=ACT_NONE, Wa=None, gWa=None,
-                 bias_per_row=False, need_dx=True, maxN=1, n_cs_slots=1, name=""):
+                 bias_per_row=False, need_dx=True, maxN=1, n_cs_slots=1, name="", precise=False):
         self.net, self.tp, self.site, self.name = net, net.tp, site, name
         if (bias is not None or act != ACT_NONE) and not site.pool_is_selection:
             raise NotImplementedError("%s: the down-sampling matrix is not a pure row selection, so pooling cannot be "
@@ -128,13 +128,20 @@ class ChebLayer:
         if self.affine:
             self.Wa, self.Wa2, self.gWa2 = Wa, Wa.view(F + C, Fout), gWa.view(F + C, Fout)
         self.need_dx = need_dx
+        self.precise = bool(precise)
         dev = W.device
-        # K-major copies of the weights: B operand of the tcgen05 forward, and N-major operand of the data gradient
-        self.Wt, self.Wt_lo = torch.empty(Fout, K, F, device=dev), torch.empty(Fout, K, F, device=dev)
+        # Derived weight layouts, refreshed after every update by ONE batched launch (net.wprep):
+        #   Wt [K(+1), Fout, F]: per-order K-major copies (+ the affine branch as order K): B operand of the tensor-core
+        #      forward, fp32-pipe operand of the data gradient; read as [(k, c), f] it is the B operand of the
+        #      contract-first forward Z = X @ [W_0 | W_1 | ... | W_a];
+        #   Wk [K, F, Fout]: per-order plain copies, B operand of the contract-first data gradient Z = G @ [W_k^T]_k.
+        A = 1 if self.affine else 0
+        self.Wt, self.Wt_lo = torch.empty(K + A, Fout, F, device=dev), torch.empty(K + A, Fout, F, device=dev)
         self.W3_lo = net.lo_of(W).view(F + C, K, Fout)
+        net.wprep.add(W, F, K, Fout, wt=self.Wt[:K], wt_lo=self.Wt_lo[:K])
         if self.affine:
-            self.Wat, self.Wat_lo = torch.empty(Fout, F, device=dev), torch.empty(Fout, F, device=dev)
             self.Wa2_lo = net.lo_of(Wa).view(F + C, Fout)
+            net.wprep.add(Wa, F, 1, Fout, wt=self.Wt[K:], wt_lo=self.Wt_lo[K:])
         # Where the weight gradient gets its operands (all three end in the same contraction  dW = A^T G over rows):
         #   "aside":  the forward kernel also writes the gathered basis B_k = op_k x (cape_term.stash), dW_k = B_k^T G;
         #   "gside":  the data-gradient kernel also writes H_k = op_k^T G, dW_k = x^T H_k -- all K terms in ONE pass
@@ -157,6 +164,40 @@ class ChebLayer:
                                 for k in range(K)]
             if self.affine and site.opsT[0] != -1:
                 self.stash_ga = torch.empty(maxN, site.rows_in, Fout, device=dev)
+        # How the forward / data-gradient passes are organised (the math is the same):
+        #   "fused":    one kernel gathers the basis and contracts it (ellconv_tc.cu; thin layers: thin.cu);
+        #   "basis":    cape_apply writes B_k = op_k x (forward: the stash the weight gradient reads anyway) or
+        #               H_k = op_k^T G (data gradient), then the TMA-fed kernel contracts plain tensors;
+        #   "contract": the TMA-fed kernel computes Z = x @ [W_0 | W_1 | ..] (or G @ [W_k^T]_k) on the SOURCE rows, then
+        #               cape_apply applies the operators to the narrower Z and runs the epilogue.
+        # Gather on the narrower side, contract on the level with fewer rows; layers with condition channels contract
+        # first (the condition term then lives in cape_apply, scaled by the operator's row sums).
+        env = os.environ.get
+        thin = F <= 4 or Fout <= 4
+        plain = all(o == -1 for o in site.ops)
+        split_ok = not thin and not plain and F % 16 == 0 and Fout % 16 == 0 and F >= 32 and Fout >= 32
+        self.fwd_mode, self.dx_mode = "fused", "fused"
+        if split_ok:
+            if C == 0 and not self.affine and self.dw_mode == "aside":
+                self.fwd_mode = "basis"
+            elif (C > 0 or self.affine) and site.rows_in < site.rows_out:
+                self.fwd_mode = "contract"
+            if need_dx and self.dw_mode == "gside":
+                self.dx_mode = "basis"
+            elif need_dx and self.dw_mode == "aside":
+                self.dx_mode = "contract"
+        fm, dm = env("CAPE_FWD_MODE", ""), env("CAPE_DX_MODE", "")
+        if fm and split_ok and (fm != "basis" or (C == 0 and not self.affine and self.dw_mode == "aside")):
+            self.fwd_mode = fm
+        if dm and split_ok and need_dx and (dm != "basis" or self.dw_mode == "gside") and (dm != "contract" or
+                                                                                         self.dw_mode != "gside"):
+            self.dx_mode = dm
+        if self.dx_mode == "contract":
+            self.Wk, self.Wk_lo = torch.empty(K, F, Fout, device=dev), torch.empty(K, F, Fout, device=dev)
+            net.wprep.add(W, F, K, Fout, wk=self.Wk, wk_lo=self.Wk_lo)
+            net.scratch_req(maxN * site.rows_out * K * F)
+        if self.fwd_mode == "contract":
+            net.scratch_req(maxN * site.rows_in * (K + A) * Fout)
         # colsum targets: [bias?] + K condition sums (+1 for the affine branch)
         self.cs_ops = []
         if bias is not None and not bias_per_row:
@@ -188,32 +229,58 @@ class ChebLayer:
             return conv + res
         return 4 * N * s.M * Fin * (2 if self.affine else 1) + wbytes      # all dW launches of the layer together
 
-    def prep(self):
-        weight_transpose(self.tp, self.W, self.F, self.K, self.Fout, self.Wt, self.Wt_lo)
-        if self.affine:
-            weight_transpose(self.tp, self.Wa, self.F, 1, self.Fout, self.Wat, self.Wat_lo)
+    def _split(self):
+        """The split forms need the tensor-core kernels (they pass K-major weights only)."""
+        return E.tensor_cores_enabled(self.tp)
 
     def fwd(self, x, ycat, out, out2=None):
         N = x.shape[0]
         s, F, C, K, Fout = self.site, self.F, self.C, self.K, self.Fout
         assert x.shape[1] == s.rows_in and x.shape[2] >= F and out.shape[1] == s.rows_out
+        sx = x.shape[2]
+        tag = (self.name + ":fwd", self.alg_bytes(N, "fwd"))
+        sub = lambda what: (self.name + ":fwd/" + what, 0)           # bytes are booked on the layer's main launch
+        if self.fwd_mode == "contract" and self._split():
+            A = 1 if self.affine else 0
+            ncz = (K + A) * Fout
+            Z = self.net.scratch[: N * s.rows_in * ncz].view(N, s.rows_in, ncz)
+            cheb_call(self.tp, N, s.rows_in, ncz,
+                      [dict(src=x, op=-1, F=F, src_rows=s.rows_in, src_stride=sx, w=None, w_stride=0,
+                            wT=self.Wt.view(ncz, F), wT_stride=F, wT_lo=self.Wt_lo.view(ncz, F))],
+                      Z, plain_only=True, tag=sub("project"))
+            terms = [dict(src=Z[:, :, k * Fout:], op=s.ops[k], src_rows=s.rows_in, src_stride=ncz, acc=0,
+                          wc=self.W3[F:, k, :] if C else None, wc_stride=K * Fout) for k in range(K)]
+            if self.affine:
+                terms.append(dict(src=Z[:, :, K * Fout:], op=s.ops[0], src_rows=s.rows_in, src_stride=ncz, acc=1,
+                                  wc=self.Wa2[F:] if C else None, wc_stride=Fout))
+            E.apply_call(self.tp, N, s.rows_out, Fout, terms, out, out2=out2, cond=ycat if C else None,
+                         epilogue=EPI_AFFINE if self.affine else EPI_LINEAR, act=self.act, bias=self.bias,
+                         bias_per_row=self.bias_per_row, tag=tag)
+            return
+        basis = self.fwd_mode == "basis" and self._split()
         terms = []
         for k in range(K):
-            t = dict(src=x, op=s.ops[k], F=F, src_rows=s.rows_in, src_stride=x.shape[2], w=self.W3[:, k, :],
-                     w_stride=K * Fout, wT=self.Wt[:, k, :], wT_stride=K * F, wT_lo=self.Wt_lo[:, k, :])
+            t = dict(src=x, op=s.ops[k], F=F, src_rows=s.rows_in, src_stride=sx, w=self.W3[:, k, :],
+                     w_stride=K * Fout, wT=self.Wt[k], wT_stride=F, wT_lo=self.Wt_lo[k])
             if C:
                 t["wc"] = self.W3[F:, k, :]
-            if self.stash_a[k] is not None:
+            if basis and s.ops[k] != -1:
+                # B_k = op_k x by the gather kernel, written where the weight gradient reads it; contracted as a plain tensor
+                B = self.stash_a[k][:N]
+                E.apply_call(self.tp, N, s.rows_out, F, [dict(src=x, op=s.ops[k], src_rows=s.rows_in, src_stride=sx)], B,
+                             tag=sub("basis%d" % k))
+                t.update(src=B, op=-1, src_rows=s.rows_out, src_stride=F)
+            elif self.stash_a[k] is not None:
                 t["stash"], t["stash_stride"] = self.stash_a[k][:N], F
             if self.affine and k == 0:
                 t["w2"], t["w2_stride"] = self.Wa2, Fout
-                t["w2T"], t["w2T_stride"], t["w2T_lo"] = self.Wat, F, self.Wat_lo
+                t["w2T"], t["w2T_stride"], t["w2T_lo"] = self.Wt[K], F, self.Wt_lo[K]
                 if C:
                     t["wc2"] = self.Wa2[F:]
             terms.append(t)
         cheb_call(self.tp, N, s.rows_out, Fout, terms, out, out2=out2, cond=ycat if C else None,
                   epilogue=EPI_AFFINE if self.affine else EPI_LINEAR, act=self.act, bias=self.bias,
-                  bias_per_row=self.bias_per_row, tag=(self.name + ":fwd", self.alg_bytes(N, "fwd")))
+                  bias_per_row=self.bias_per_row, tag=tag, precise=self.precise)
 
     def bwd(self, x, ycat, g, g_aff=None, dx=None, dx2=None, dx_epi=EPI_LINEAR, dx_aux=None, dx_alpha=E.LEAKY_ALPHA,
             dycat=None, want_dw=True, cs_slot=0):
@@ -288,22 +355,45 @@ class ChebLayer:
         if dx is not None:
             assert self.need_dx
             gs = want_dw and mode == "gside"
-            terms = []
-            if self.affine:
-                t = dict(src=g_aff, op=s.opsT[0], F=Fout, src_rows=s.rows_out, src_stride=Fout, w=self.Wat,
-                         w_stride=F, wT=self.Wa2, wT_stride=Fout, wT_lo=self.Wa2_lo)
-                if gs and self.stash_ga is not None:
-                    t["stash"], t["stash_stride"] = self.stash_ga[:N], Fout
-                terms.append(t)
-            for k in range(K):
-                t = dict(src=g, op=s.opsT[k], F=Fout, src_rows=s.rows_out, src_stride=Fout,
-                         w=self.Wt[:, k, :], w_stride=K * F, wT=self.W3[:, k, :], wT_stride=K * Fout,
-                         wT_lo=self.W3_lo[:, k, :])
-                if gs and self.stash_g[k] is not None:
-                    t["stash"], t["stash_stride"] = self.stash_g[k][:N], self.stash_g[k].stride(1)
-                terms.append(t)
-            cheb_call(tp, N, s.rows_in, F, terms, dx, out2=dx2, epilogue=dx_epi, aux=dx_aux, alpha=dx_alpha,
-                      tag=(self.name + ":dx", self.alg_bytes(N, "dx")))
+            dtag = (self.name + ":dx", self.alg_bytes(N, "dx"))
+            sub = lambda what: (self.name + ":dx/" + what, 0)
+            if self.dx_mode == "contract" and self._split():
+                # Z = G @ [W_0^T | W_1^T | ..] on the (pooled / narrower) output rows, then dX = epi(sum_k op_k^T Z_k)
+                Z = self.net.scratch[: N * s.rows_out * K * F].view(N, s.rows_out, K * F)
+                cheb_call(tp, N, s.rows_out, K * F,
+                          [dict(src=g, op=-1, F=Fout, src_rows=s.rows_out, src_stride=Fout, w=None, w_stride=0,
+                                wT=self.Wk.view(K * F, Fout), wT_stride=Fout, wT_lo=self.Wk_lo.view(K * F, Fout))],
+                          Z, plain_only=True, tag=sub("project"))
+                E.apply_call(tp, N, s.rows_in, F,
+                             [dict(src=Z[:, :, k * F:], op=s.opsT[k], src_rows=s.rows_out, src_stride=K * F)
+                              for k in range(K)], dx, out2=dx2, epilogue=dx_epi, aux=dx_aux, alpha=dx_alpha, tag=dtag)
+            else:
+                basis = gs and self.dx_mode == "basis" and self._split()
+                terms = []
+                if self.affine:
+                    t = dict(src=g_aff, op=s.opsT[0], F=Fout, src_rows=s.rows_out, src_stride=Fout, w=self.Wt[K],
+                             w_stride=F, wT=self.Wa2, wT_stride=Fout, wT_lo=self.Wa2_lo)
+                    if gs and self.stash_ga is not None:
+                        t["stash"], t["stash_stride"] = self.stash_ga[:N], Fout
+                    terms.append(t)
+                for k in range(K):
+                    t = dict(src=g, op=s.opsT[k], F=Fout, src_rows=s.rows_out, src_stride=Fout,
+                             w=self.Wt[k], w_stride=F, wT=self.W3[:, k, :], wT_stride=K * Fout,
+                             wT_lo=self.W3_lo[:, k, :])
+                    if gs and self.stash_g[k] is not None:
+                        t["stash"], t["stash_stride"] = self.stash_g[k][:N], self.stash_g[k].stride(1)
+                    terms.append(t)
+                if basis:
+                    # H = op^T G by the gather kernel into the buffers the weight gradient reads; contracted as plain tensors
+                    for i, t in enumerate(terms):
+                        if t["op"] == -1:
+                            continue
+                        H, hs = t.pop("stash"), t.pop("stash_stride")
+                        E.apply_call(tp, N, s.rows_in, Fout,
+                                     [dict(src=t["src"], op=t["op"], src_rows=s.rows_out, src_stride=Fout)], H,
+                                     out_stride=hs, tag=sub("narrow%d" % i))
+                        t.update(src=H, op=-1, src_rows=s.rows_in, src_stride=hs)
+                cheb_call(tp, N, s.rows_in, F, terms, dx, out2=dx2, epilogue=dx_epi, aux=dx_aux, alpha=dx_alpha, tag=dtag)
             if gs:
                 # dW_k = x^T (op_k^T G): the data-gradient kernel above left op_k^T G in the stash buffers
                 nl = (1 if self.g_merged else K) + (1 if self.affine else 0)
@@ -414,10 +504,10 @@ class GNBlock:
         E.gn_relu_fwd(tp, self.H2, g2["gamma"], g2["beta"], self.A3, g2["stats"], g2["G"])
         l2, li = self.lin2, self.lin_in
         terms = [dict(src=self.A3, op=-1, F=self.mid, src_rows=self.rows, src_stride=self.mid, w=l2.W3[:, 0, :],
-                      w_stride=self.Fo, wT=l2.Wt[:, 0, :], wT_stride=self.mid)]
+                      w_stride=self.Fo, wT=l2.Wt[0], wT_stride=self.mid, wT_lo=l2.Wt_lo[0])]
         if li is not None:
             terms.append(dict(src=self.Z, op=-1, F=self.Ft, src_rows=self.rows, src_stride=self.Ft, w=li.W3[:, 0, :],
-                              w_stride=self.Fo, wT=li.Wt[:, 0, :], wT_stride=self.Ft))
+                              w_stride=self.Fo, wT=li.Wt[0], wT_stride=self.Ft, wT_lo=li.Wt_lo[0]))
         cheb_call(tp, N, self.rows, self.Fo, terms, out,
                   tag=("dec/res:out", l2.alg_bytes(N, "fwd") + (li.alg_bytes(N, "fwd") if li is not None else 0)))
         if li is None:
@@ -491,6 +581,8 @@ class CapeNetwork:
         self.PG.load(vals)
         self.PD.load(vals)
         self.arena = Arena()
+        self.wprep = E.WeightPrep(tp)
+        self._scratch_need = 4
         self.ones = torch.ones(1, 2 * N, device=dev)
         w, g = self._w, self._g
 
@@ -502,6 +594,10 @@ class CapeNetwork:
         else:
             og, od = [None] * (nl + 1), [None] * (len(D_d) + 1)
         self.order_g, self.order_d = og, od
+        # The encoder's forward convs keep their tensor-core accumulation chains short (cape_conv_args.precise): their
+        # rounding error is what exp(logvar) amplifies (sigma = exp(logvar / 2) reaches 1e2 with the reference's
+        # initialisers); everywhere else the plain 3xTF32 accumulation is well inside the 1e-4 gate.
+        precise_enc = os.environ.get("CAPE_PRECISE_ENCODER", "1") != "0"
         self.enc = []
         fin = c["nn_input_channel"]
         for i in range(nl):
@@ -509,13 +605,13 @@ class CapeNetwork:
             sc = "generator/encoder/encoder_conv%d" % (i + 1)
             self.enc.append(ChebLayer(self, site, fin, 0, F[i], w(sc + "/weights"), g(sc + "/weights"),
                                       bias=w(sc + "/bias"), gbias=g(sc + "/bias"), act=ACT_LEAKY, need_dx=(i > 0),
-                                      maxN=N, name="enc/conv%d" % (i + 1)))
+                                      maxN=N, name="enc/conv%d" % (i + 1), precise=precise_enc))
             fin = F[i]
         red = specs["generator/encoder/1x1-conv/weights"][1]
         self.red = red
         self.enc_1x1 = ChebLayer(self, ConvSite(tp, L[-1], 1, order_in=og[nl]), F[-1], 0, red,
                                  w("generator/encoder/1x1-conv/weights"),
-                                 g("generator/encoder/1x1-conv/weights"), maxN=N, name="enc/1x1")
+                                 g("generator/encoder/1x1-conv/weights"), maxN=N, name="enc/1x1", precise=precise_enc)
         flat = self.p[-1] * red
         self.flat = flat
         dn = lambda s, act=ACT_NONE: Dense(self, w(s + "/dense/kernel").view(specs[s + "/dense/kernel"]),
@@ -569,6 +665,7 @@ class CapeNetwork:
         self.nbr_op = tp.add_operator(_adjacency(L[0]))
         self.n_edges = int(_adjacency(L[0]).nnz // 2)
         self.arena.build(dev)
+        self.scratch = torch.empty(self._scratch_need, device=dev)
 
         # ---- buffers -----------------------------------------------------------------------------------
         z = lambda *s: torch.zeros(*s, device=dev)
@@ -681,11 +778,16 @@ class CapeNetwork:
         return r if r is not None else self.PD.lo_of(t)
 
     def prep_weights(self):
-        """Copies derived from the weights (K-major transposes, tf32 low parts); run after every update."""
+        """Copies derived from the weights (K-major / per-order layouts, tf32 low parts); run after every update:
+        three launches for the whole network."""
         E.tf32_lo(self.tp, self.PG.flat, self.PG.lo)
         E.tf32_lo(self.tp, self.PD.flat, self.PD.lo)
-        for l in self.all_layers():
-            l.prep()
+        self.wprep.run()
+
+    def scratch_req(self, nfloats):
+        """Layers announce the size of the intermediate their split forms need (Z = X @ [W_k]: consumed by the next
+        launch on the same stream, so one buffer serves every layer)."""
+        self._scratch_need = max(getattr(self, "_scratch_need", 4), int(nfloats))
 
     # ---- inputs --------------------------------------------------------------------------------------------
     def set_inputs(self, x_g, cond_g, cond2_g, eps, x_d=None, cond_d=None, cond2_d=None, non_blocking=True):
@@ -700,7 +802,7 @@ class CapeNetwork:
             self.in_cond[:N].copy_(cond_d, non_blocking=non_blocking)
             self.in_cond2[:N].copy_(cond2_d, non_blocking=non_blocking)
 
-    def prefetch_inputs(self, x_g, cond_g, cond2_g, eps, x_d, cond_d, cond2_d):
+    def prefetch_inputs(self, x_g, cond_g, cond2_g, eps, x_d=None, cond_d=None, cond2_d=None):
         """Start the host->device copy of the NEXT step's batch (pinned host tensors) on a side stream, into one of two
         staging sets; `commit_inputs()` makes it the current batch.  The copy overlaps the step that is running."""
         if not hasattr(self, "_stage"):
@@ -715,8 +817,10 @@ class CapeNetwork:
                 e.record()
         slot = self._stage_slot
         self._copy_stream.wait_event(self._stage_free[slot])        # its previous contents have been consumed
+        srcs = (x_g, cond_g, cond2_g, eps) if x_d is None else (x_g, cond_g, cond2_g, eps, x_d, cond_d, cond2_d)
+        self._stage_n = len(srcs)                 # generator-only batches (forward / inference) stage four tensors
         with torch.cuda.stream(self._copy_stream):
-            for dst, src in zip(self._stage[slot], (x_g, cond_g, cond2_g, eps, x_d, cond_d, cond2_d)):
+            for dst, src in zip(self._stage[slot], srcs):
                 dst.copy_(src, non_blocking=True)
             self._stage_ev[slot].record(self._copy_stream)
 
@@ -725,7 +829,7 @@ class CapeNetwork:
         slot = self._stage_slot
         cur = torch.cuda.current_stream()
         cur.wait_event(self._stage_ev[slot])
-        self.set_inputs(*self._stage[slot])
+        self.set_inputs(*self._stage[slot][: self._stage_n])
         self._stage_free[slot].record(cur)
         self._stage_slot = 1 - slot
 
@@ -962,6 +1066,15 @@ class CapeNetwork:
             self.enqueue_fwd_bwd()
         with torch.cuda.graph(self.graph_up):
             self.enqueue_update()
+        torch.cuda.synchronize()
+
+    def capture_forward_graph(self):
+        """Capture the generator forward (condition nets + encoder + sampling + decoder, BASELINE configs[1]) into one
+        CUDA graph: `graph_fwd.replay()` then maps the staged inputs to `x_hat`."""
+        self.graph_fwd = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(self.graph_fwd):
+            self.forward_generator()
         torch.cuda.synchronize()
 
     def train_step(self, step=None, update=True, allreduce=None, use_graph=False):

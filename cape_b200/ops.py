@@ -34,7 +34,7 @@ def _site(tp, L, K, U, D):
 
 class _ChebFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, W, bias, site, tp, act):
+    def forward(ctx, x, W, bias, site, tp, act, precise=False):
         N, M, Fin = x.shape
         K = site.K
         Fout = W.shape[1]
@@ -42,12 +42,12 @@ class _ChebFn(torch.autograd.Function):
         W = W.contiguous()
         out = torch.empty(N, site.rows_out, Fout, device=x.device)
         W3 = W.view(Fin, K, Fout)
-        Wt = torch.empty(Fout, K, Fin, device=x.device)
-        E.weight_transpose(tp, W, Fin, K, Fout, Wt)
+        Wt, Wt_lo = torch.empty(Fout, K, Fin, device=x.device), torch.empty(Fout, K, Fin, device=x.device)
+        E.weight_transpose(tp, W, Fin, K, Fout, Wt, Wt_lo)
         terms = [dict(src=x, op=site.ops[k], F=Fin, src_rows=site.rows_in, src_stride=Fin, w=W3[:, k, :],
-                      w_stride=K * Fout, wT=Wt[:, k, :], wT_stride=K * Fin) for k in range(K)]
+                      w_stride=K * Fout, wT=Wt[:, k, :], wT_stride=K * Fin, wT_lo=Wt_lo[:, k, :]) for k in range(K)]
         b = bias.contiguous().view(-1) if bias is not None else None
-        E.cheb_call(tp, N, site.rows_out, Fout, terms, out, epilogue=EPI_LINEAR, act=act, bias=b)
+        E.cheb_call(tp, N, site.rows_out, Fout, terms, out, epilogue=EPI_LINEAR, act=act, bias=b, precise=precise)
         ctx.save_for_backward(x, W, out)
         ctx.site, ctx.tp, ctx.act, ctx.has_bias = site, tp, act, bias is not None
         return out
@@ -79,15 +79,18 @@ class _ChebFn(torch.autograd.Function):
             E.weight_transpose(tp, W, Fin, K, Fout, Wt)
             dx = torch.empty_like(x)
             W3 = W.view(Fin, K, Fout)
+            W_lo = torch.empty_like(W)
+            E.tf32_lo(tp, W, W_lo)
+            W3_lo = W_lo.view(Fin, K, Fout)
             terms = [dict(src=g, op=site.opsT[k], F=Fout, src_rows=site.rows_out, src_stride=Fout, w=Wt[:, k, :],
-                          w_stride=K * Fin, wT=W3[:, k, :], wT_stride=K * Fout) for k in range(K)]
+                          w_stride=K * Fin, wT=W3[:, k, :], wT_stride=K * Fout, wT_lo=W3_lo[:, k, :]) for k in range(K)]
             E.cheb_call(tp, N, site.rows_in, Fin, terms, dx)
-        return dx, dW, db, None, None, None
+        return dx, dW, db, None, None, None, None
 
 
-def chebyshev5(x, L, W, K, bias=None, activation=None, pool=None, unpool=None):
+def chebyshev5(x, L, W, K, bias=None, activation=None, pool=None, unpool=None, precise=False):
     """Chebyshev graph convolution y = sum_k T_k(L~) x W[k::K] (lib/models.py:69-103); W is [Fin*K, Fout] with row
-    index fin*K + k.  Optional fusions: `unpool` U applied to x first (models.py:750,782), `bias`+`activation`
+    index fin*K + k.  precise: short tensor-core accumulation chains (cape_conv_args.precise; K = 1 / plain operands).  Optional fusions: `unpool` U applied to x first (models.py:750,782), `bias`+`activation`
     ('b1leakyrelu' | 'b1relu' | None, models.py:105-121) and `pool` D applied last (models.py:168)."""
     tp = topology_for(x.device)
     act = {None: ACT_NONE, "b1leakyrelu": ACT_LEAKY, "b1relu": ACT_RELU}[activation]
@@ -96,10 +99,10 @@ def chebyshev5(x, L, W, K, bias=None, activation=None, pool=None, unpool=None):
         if not topo.is_selection(pool):
             # pooling commutes with the pointwise bias/activation only for row selections (the reference's D): a
             # general sampling matrix is applied after them, as the reference does (lib/models.py:164-168)
-            y = _ChebFn.apply(x, W, bias, _site(tp, L, K, unpool, None), tp, act)
+            y = _ChebFn.apply(x, W, bias, _site(tp, L, K, unpool, None), tp, act, precise)
             return poolwT(y, pool)
     site = _site(tp, L, K, unpool, pool)
-    return _ChebFn.apply(x, W, bias, site, tp, act)
+    return _ChebFn.apply(x, W, bias, site, tp, act, precise)
 
 
 class _ResampleFn(torch.autograd.Function):

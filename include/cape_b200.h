@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CAPE_ABI_VERSION 2
+#define CAPE_ABI_VERSION 3
 #define CAPE_MAX_TERMS 8
 
 typedef struct cape_topology cape_topology;
@@ -111,17 +111,63 @@ typedef struct {
   const float* aux;    /* [N, rows_out, ncols] (SLOPE / DUALMASK) */
   float* out;          /* [N, rows_out, ncols] */
   float* out2;         /* [N, rows_out, ncols] or NULL */
+  /* 1: keep the tensor-core accumulation chains short (several TMEM accumulators per output, summed in fp32 by the
+   * epilogue).  The tcgen05 accumulator truncates on every accumulate, which shrinks long dot products by ~2^-25 per
+   * MMA; the encoder's forward convs ask for this because the VAE's exp(logvar) amplifies their error.  Honoured by the
+   * plain-operand (all terms identity) LINEAR-epilogue path; ignored elsewhere. */
+  int precise;
+  /* 1: fail (rc < 0) instead of falling back to the gather / fp32-pipe kernels when the TMA-fed plain-operand kernel
+   * cannot take the call -- for callers that only filled wT / wT_lo (the `w` pointers are then never read). */
+  int plain_only;
 } cape_conv_args;
 
-/* Experiment knobs (process-wide, 8 integer slots, all 0 by default = the shipped configuration).  They switch single
+/* ---- operators without contraction: the gather half of the split conv forms -----------------------------
+ *   acc_a[n, r, c] = sum_{t: acc_t = a} scale_t * ( sum_j op_t[r, j] * src_t[n, idx_t[r, j], c]
+ *                                                   + rowsum(op_t)[r] * (cond[n, :C] @ wc_t[:C, c]) ),     c < ncols
+ * then the epilogue of cape_conv_args (LINEAR: bias + activation; AFFINE: out = acc1 + relu(acc0), out2 = relu(acc0);
+ * SLOPE / DUALMASK with aux).  With the TMA-fed contraction of plain tensors (cape_cheb_fwd, all terms identity) this
+ * gives the two split forms of chebyshev5 (+poolwT, +fit_cond_dim; lib/models.py:69-103,129-152,813-832):
+ *   contract first:  Z = X @ [W_0 | W_1 | ...]   (cape_cheb_fwd),   out = epi(sum_k op_k Z_k)   (cape_apply)
+ *   basis first:     B_k = op_k X                 (cape_apply),      out = epi(sum_k B_k W_k)    (cape_cheb_fwd)
+ * and single steps of the Chebyshev recurrence (T_k x = 2 L~ T_{k-1} x - T_{k-2} x: two terms, scales 2 and -1). */
+typedef struct {
+  const float* src;   /* [N, src_rows, src_stride]; channels [0, ncols) are used */
+  int op;             /* operator id ([rows_out x src_rows]), or -1 for identity */
+  int src_rows;
+  int src_stride;     /* floats between rows of src (>= ncols, % 4 == 0) */
+  int acc;            /* accumulator 0 or 1 */
+  float scale;        /* factor of the term (0 means 1) */
+  const float* wc;    /* optional condition rows [C, >= ncols] for this term (NULL: none) */
+  int wc_stride;      /* floats between rows of wc */
+} cape_apply_term;
+
+typedef struct {
+  int N, rows_out, ncols;    /* ncols % 4 == 0, <= 1024 */
+  int nterms;
+  cape_apply_term terms[CAPE_MAX_TERMS];
+  const float* cond;   /* [N, C] (NULL: none) */
+  int C;
+  int epilogue, act;   /* CAPE_EPI_*, CAPE_ACT_* */
+  float alpha;
+  const float* bias;   /* [ncols] or [rows_out, ncols] */
+  int bias_per_row;
+  const float* aux;    /* [N, rows_out, ncols] (SLOPE / DUALMASK) */
+  float* out;          /* rows out_stride floats apart (0: ncols) -- the result may land inside a wider buffer */
+  int out_stride;
+  float* out2;         /* same stride, or NULL */
+} cape_apply_args;
+int cape_apply(cape_topology* t, const cape_apply_args* a, void* stream);
+
+/* Experiment knobs (process-wide, 16 integer slots, all 0 by default = the shipped configuration).  They switch single
  * optimisations off for A/B measurements and fallback-path tests: [1]=1 no TMA dense weight-gradient kernel, [3]=2
  * 128- instead of 256-wide column sub-tiles in it, [4]=1 conv weight tiles by the producer warps instead of TMA,
  * [5]=1 one narrow-conv CTA per SM, [6]=1 identity-term basis tiles by the producer warps, [7]=1 thin-output layers
- * on the generic kernels ([2] is a diagnostic of the dense kernel).  Returns the previous value, <0 for an unknown key. */
+ * on the generic kernels, [8]=1 no TMA-fed plain-operand conv kernel ([0] and [2] are diagnostics of the operand split).  Returns the previous value, <0 for an unknown key. */
 int cape_set_tuning(int key, int value);
 
 /* Process-wide switch for the tcgen05 path of cape_cheb_fwd (default on); returns the previous setting. */
 int cape_set_tensor_cores(int enable);
+int cape_tensor_cores_enabled(void);
 
 /* Forward of chebyshev5 (+poolwT, +b1leakyrelu, +fit_cond_dim/concat) -- lib/models.py:69-103,105-109,
  * 129-152,813-832; also the data-gradient pass (same form with transposed operators and weights). */
@@ -174,6 +220,25 @@ int cape_resample(cape_topology* t, int op, const float* x, int x_stride, float*
  * for f < Fin (rows of w beyond Fin*K -- the condition channels -- are not touched); wt_lo (optional, same layout)
  * receives wt - tf32_trunc(wt). */
 int cape_cheb_weight_transpose(const float* w, int Fin, int K, int Fout, float* wt, float* wt_lo, void* stream);
+
+/* The derived weight layouts of MANY layers in one launch (run after every optimiser step).  Per descriptor, from the
+ * reference layout w[(f*K + k)*Fout + c] (rows f < Fin; condition rows beyond are not touched):
+ *   wt[(k*Fout + c)*Fin + f]   -- per-order K-major copies: tensor-core B operand of the forward pass (and, read as
+ *                                 [(k, c), f], of the contract-first form Z = X @ [W_0 | W_1 | ...]), fp32-pipe operand of
+ *                                 the data-gradient pass;
+ *   wk[(k*Fin + f)*Fout + c]   -- per-order plain copies: K-major B operand of the contract-first data gradient
+ *                                 Z = G @ [W_0^T | W_1^T | ...];
+ * each with its tf32 low part (x - tf32_trunc(x)) for the 3xTF32 scheme.  NULL outputs are skipped.  `descs_device`
+ * is a DEVICE array of n descriptors (the pointers never change, so the caller uploads it once). */
+typedef struct {
+  const float* w;
+  int Fin, K, Fout;
+  float* wt;
+  float* wt_lo;
+  float* wk;
+  float* wk_lo;
+} cape_wprep;
+int cape_weight_prep(const cape_wprep* descs_device, int n, int blocks_per_desc, void* stream);
 
 /* lo[i] = x[i] - tf32_trunc(x[i]): the second operand of the 3xTF32 scheme for a tensor the tensor cores read raw */
 int cape_tf32_lo(const float* x, float* lo, long long n, void* stream);

@@ -23,7 +23,8 @@ def main():
     cfg = dict(NZ64_AFFINE, decay_steps=10)
     only = sys.argv[1:]
     jobs = [("golden", lambda: parity.golden_ops(h)), ("gemm", parity.gemm_cases),
-            ("cheb", lambda: parity.cheb_grad_cases(h)), ("gn", parity.gn_case), ("tc", lambda: parity.tc_vs_simt(h)),
+            ("cheb", lambda: parity.cheb_grad_cases(h)), ("plain", lambda: parity.plain_operand_cases(h)),
+            ("precise", lambda: parity.precise_vs_truth(h)), ("apply", lambda: parity.apply_cases(h)), ("gn", parity.gn_case), ("tc", lambda: parity.tc_vs_simt(h)),
             ("step", lambda: parity.train_step(h, cfg, N=2)),
             ("step_ref", lambda: parity.train_step(h, cfg, N=2, ref_compat=True)),
             ("step_rawinit", lambda: parity.train_step(h, cfg, N=2, fc_scale=1.0)),

@@ -93,6 +93,105 @@ def cheb_grad_cases(h):
     return out
 
 
+def plain_operand_cases(h):
+    """Calls whose terms are all plain tensors (1x1 convs) take the TMA-fed kernel (gemm_tc.cu): widths that are not
+    multiples of 128 or exceed the 512 TMEM columns (GroupNorm blocks: 544, 288, 160), multi-tile row counts, and the
+    precise (split accumulation chains) mode; forward, dX, dW against the oracle."""
+    out = {}
+    out.update(cheb_grads("plain L8 K=1 512->64", h["L"][8], 1, 512, 64, 4, act=None))
+    out.update(cheb_grads("plain L8 K=1 256->544", h["L"][8], 1, 256, 544, 3, act=None))
+    out.update(cheb_grads("plain L6 K=1 160->288 leaky", h["L"][6], 1, 160, 288, 2, seed=3))
+    out.update(cheb_grads("plain L4 K=1 96->32 multi-tile", h["L"][4], 1, 96, 32, 30, act=None, seed=4))
+    return out
+
+
+def precise_vs_truth(h):
+    """cape_conv_args.precise against a float64 truth: the plain-operand kernel with split accumulation chains must be
+    markedly closer to it than the default single-chain accumulation (entries: precise error / default error)."""
+    from cape_b200 import ops
+    o = O.Oracle(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], dict(F=[64] * 8, K=[2] * 8, Kd=3), dtype=torch.float64)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    out = {}
+    for tag, lvl, Fin, Fout, N in (("L8 1024->512", 8, 1024, 512, 8), ("L8 512->64", 8, 512, 64, 8)):
+        x = torch.randn(N, h["L"][lvl].shape[0], Fin, device="cuda", generator=g)
+        x = torch.where(x > 0, x, 0.2 * x)
+        W = torch.randn(Fin, Fout, device="cuda", generator=g) * 0.1
+        want = o.chebyshev5(x.cpu().double(), o.Lt[lvl], W.cpu().double(), 1).numpy()
+        e = {}
+        for precise in (False, True):
+            y = ops.chebyshev5(x, h["L"][lvl], W, 1, precise=precise).cpu().numpy()
+            e[precise] = rel(y, want)
+        out["precise %s (max-rel vs fp64)" % tag] = e[True]
+        out["default %s (max-rel vs fp64)" % tag] = e[False]
+    return out
+
+
+def apply_cases(h):
+    """cape_apply (operators without contraction) against scipy: composed conv operators, transposes, scaled two-term
+    recurrence steps, strided outputs, the condition term and every epilogue."""
+    import scipy.sparse as sp
+    from cape_b200 import engine as E
+    from cape_b200 import ops
+    from cape_b200 import topology as T
+    tp = ops.topology_for(torch.device("cuda", 0))
+    rng = np.random.RandomState(0)
+    out = {}
+
+    def dense_apply(m, x):
+        m = sp.csr_matrix(m).astype(np.float64)
+        return np.stack([m @ x[n].astype(np.float64) for n in range(x.shape[0])])
+
+    # (1) un-pooling conv operators on 128-wide rows, two accumulators, condition term, AFFINE epilogue
+    site = E.ConvSite(tp, h["L"][5], 2, U=h["U"][5])
+    N, Fo, C = 3, 128, 8
+    z = rng.normal(size=(N, site.rows_in, 3 * Fo)).astype(np.float32)
+    y = rng.normal(size=(N, C)).astype(np.float32)
+    wc = rng.normal(size=(3, C, Fo)).astype(np.float32)
+    zc, yc, wcc = _cuda(z), _cuda(y), _cuda(wc)
+    o1, o2 = torch.empty(N, site.rows_out, Fo, device="cuda"), torch.empty(N, site.rows_out, Fo, device="cuda")
+    terms = [dict(src=zc[:, :, k * Fo:], op=site.ops[k], src_rows=site.rows_in, src_stride=3 * Fo, acc=0, wc=wcc[k],
+                  wc_stride=Fo) for k in range(2)]
+    terms.append(dict(src=zc[:, :, 2 * Fo:], op=site.ops[0], src_rows=site.rows_in, src_stride=3 * Fo, acc=1, wc=wcc[2],
+                      wc_stride=Fo))
+    E.apply_call(tp, N, site.rows_out, Fo, terms, o1, out2=o2, cond=yc, epilogue=E.EPI_AFFINE)
+    rs = [np.asarray(m.sum(1)).reshape(1, -1, 1) for m in site.mats]
+    q = np.einsum("nc,kcf->knf", y.astype(np.float64), wc.astype(np.float64))[:, :, None, :]
+    acc0 = sum(dense_apply(site.mats[k], z[:, :, k * Fo:(k + 1) * Fo]) + rs[k] * q[k] for k in range(2))
+    acc1 = dense_apply(site.mats[0], z[:, :, 2 * Fo:]) + rs[0] * q[2]
+    out["apply unpool affine out"] = rel(o1.cpu().numpy(), acc1 + np.maximum(acc0, 0))
+    out["apply unpool affine out2"] = rel(o2.cpu().numpy(), np.maximum(acc0, 0))
+    # (2) transposed pooled K=3 operators on 64-wide rows, SLOPE epilogue
+    site = E.ConvSite(tp, h["L_d"][1], 3, D=h["D_d"][1])
+    N, F = 2, 64
+    z = rng.normal(size=(N, site.rows_out, 3 * F)).astype(np.float32)
+    aux = rng.normal(size=(N, site.rows_in, F)).astype(np.float32)
+    o1 = torch.empty(N, site.rows_in, F, device="cuda")
+    zc = _cuda(z)
+    E.apply_call(tp, N, site.rows_in, F, [dict(src=zc[:, :, k * F:], op=site.opsT[k], src_rows=site.rows_out,
+                                               src_stride=3 * F) for k in range(3)], o1, epilogue=E.EPI_SLOPE,
+                 aux=_cuda(aux), alpha=0.2)
+    want = sum(dense_apply(site.mats[k].T, z[:, :, k * F:(k + 1) * F]) for k in range(3)) * np.where(aux > 0, 1.0, 0.2)
+    out["apply pooled^T K=3 slope"] = rel(o1.cpu().numpy(), want)
+    # (3) one step of the recurrence, T_2 x = 2 L~ (L~ x) - x, odd width, strided output, bias + leaky
+    L = h["L"][3]
+    Lt = T.rescale_L(L)
+    op = tp.add_operator(Lt)
+    N, F = 2, 36
+    x = rng.normal(size=(N, L.shape[0], F)).astype(np.float32)
+    b = rng.normal(size=(F,)).astype(np.float32)
+    xc = _cuda(x)
+    b1 = torch.empty(N, L.shape[0], F, device="cuda")
+    E.apply_call(tp, N, L.shape[0], F, [dict(src=xc, op=op, src_rows=L.shape[0], src_stride=F)], b1)
+    wide = torch.zeros(N, L.shape[0], 2 * F, device="cuda")
+    E.apply_call(tp, N, L.shape[0], F, [dict(src=b1, op=op, src_rows=L.shape[0], src_stride=F, scale=2.0),
+                                        dict(src=xc, op=-1, src_rows=L.shape[0], src_stride=F, scale=-1.0)],
+                 wide[:, :, F:], out_stride=2 * F, bias=_cuda(b), act=E.ACT_LEAKY)
+    t2 = 2 * dense_apply(Lt, dense_apply(Lt, x)) - x + b
+    out["apply recurrence T2 (strided, bias, leaky)"] = rel(wide[:, :, F:].cpu().numpy(), np.where(t2 > 0, t2, 0.2 * t2))
+    out["apply strided output leaves the rest"] = float(wide[:, :, :F].abs().max())
+    return out
+
+
 def gemm_cases():
     from cape_b200 import ops
     from cape_b200.engine import gemm, ACT_LEAKY
@@ -194,6 +293,7 @@ def cuda_masks(net, h, N):
             if r is not None:
                 rows["disc%d%s" % (i + 1, tag)] = r
     masks["cond_pose_d"], masks["cond_pose_g"] = (net.cp_h[:N] > 0).cpu(), (net.cp_h[N:] > 0).cpu()
+    masks["l1_sign"] = ((net.x_hat - net.in_x) > 0).cpu()     # sign decisions of the L1 reconstruction loss
     return masks, rows
 
 

@@ -24,7 +24,7 @@ def test_header_symbols_exported(lib_built):
 
 
 def test_abi_version_and_error_string(lib_built):
-    assert lib_built.cape_abi_version() == 2
+    assert lib_built.cape_abi_version() == 3
     assert isinstance(lib_built.cape_last_error(), bytes)
 
 
@@ -47,6 +47,9 @@ def test_struct_layout_matches_header():
     assert fields("cape_term") == [f[0] for f in _lib.Term._fields_]
     assert fields("cape_conv_args") == [f[0] for f in _lib.ConvArgs._fields_]
     assert fields("cape_dw_args") == [f[0] for f in _lib.DwArgs._fields_]
+    assert fields("cape_wprep") == [f[0] for f in _lib.WPrep._fields_]
+    assert fields("cape_apply_term") == [f[0] for f in _lib.ApplyTerm._fields_]
+    assert fields("cape_apply_args") == [f[0] for f in _lib.ApplyArgs._fields_]
 
 
 def test_no_cpu_fallback():

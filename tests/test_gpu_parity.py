@@ -35,6 +35,25 @@ def test_chebyshev_forward_and_gradients(hierarchy):
     _assert_all(parity.cheb_grad_cases(hierarchy))
 
 
+def test_plain_operand_kernel(hierarchy):
+    """1x1 convs / plain-tensor terms on the TMA-fed kernel: odd widths, > 512 columns, multi-tile, all gradients."""
+    _assert_all(parity.plain_operand_cases(hierarchy))
+
+
+def test_precise_accumulation(hierarchy):
+    """cape_conv_args.precise: split tensor-core accumulation chains -- close to fp32 SIMT accuracy, and at least three
+    times closer to the float64 truth than the single-chain default on a 1024-long reduction."""
+    res = parity.precise_vs_truth(hierarchy)
+    assert res["precise L8 1024->512 (max-rel vs fp64)"] < 4e-6, res
+    assert res["precise L8 1024->512 (max-rel vs fp64)"] * 3 < res["default L8 1024->512 (max-rel vs fp64)"], res
+    assert res["precise L8 512->64 (max-rel vs fp64)"] < 3e-6, res
+
+
+def test_apply_operators(hierarchy):
+    """cape_apply against scipy sparse products (float64)."""
+    _assert_all(parity.apply_cases(hierarchy), tol=2e-6)
+
+
 def test_group_norm():
     _assert_all(parity.gn_case())
     _assert_all(parity.gn_case(N=3, rows=6890, C=32, seed=1))
