@@ -63,6 +63,7 @@ SIGNATURES = {
     "cape_topology_reserve_workspace": (C.c_int, [C.c_void_p, C.c_int64]),
     "cape_set_tensor_cores": (C.c_int, [C.c_int]),
     "cape_tensor_cores_enabled": (C.c_int, []),
+    "cape_gather_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "cape_weight_prep": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "cape_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "cape_cheb_fwd": (C.c_int, [C.c_void_p, C.POINTER(ConvArgs), C.c_void_p]),

@@ -8,8 +8,11 @@
 //
 //   * warp 13 issues the A boxes (128 rows x 32 k of term t, SWIZZLE_128B: a box IS a K-major UMMA operand tile; the
 //     raw fp32 words are the "hi" operand because kind::tf32 reads their top 19 bits), ring of `sr` stages;
-//   * warp 14 issues the weight boxes (hi = raw K-major copy, lo = pre-split copy, BN columns x 32 k), ring of `sb`;
-//   * warps 0-7 derive the lo tile of A (x - trunc_tf32(x)) from shared memory, ring of `sl` stages;
+//   * warp 14 issues the weight boxes (raw K-major copy, BN columns x 32 k), ring of `sbr` stages -- only the raw words
+//     travel: with the pre-split low parts a CTA would stream 8 bytes per weight element and 128-row tile, 43 B/clk per
+//     SM at the tensor-core rate, which is the whole L2 -> SM bandwidth of the chip (~42 B/clk/SM);
+//   * warps 0-7 derive the lo tiles of A and of the weights (x - trunc_tf32(x)) from shared memory, rings of `sl` /
+//     `sbl` stages;
 //   * warp 8 issues tcgen05.mma kind::tf32 (3xTF32: hi*hi + lo*hi + hi*lo) into TMEM;
 //   * warps 9-12 drain TMEM: condition broadcast / bias / activation / backward masks, float4 stores.
 //
@@ -48,13 +51,12 @@ constexpr int G_SMEM_LIMIT = 227 * 1024;
 struct GMaps {
   CUtensorMap a[G_TERMS];      // source rows of term t: boxes of 32 f x 128 rows
   CUtensorMap bh[G_TERMS];     // K-major weight copy (raw fp32 = hi operand): boxes of 32 f x BN columns
-  CUtensorMap bl[G_TERMS];     // its pre-split low part
 };
 
 struct GPlan {
   int gw, nsub, ngroups, ntiles;       // group width (columns), BN-wide sub-tiles per group, groups per row tile, row tiles
   int nchain, corr, nbuf, tmem_cols;   // main accumulators per group, 1 = separate correction accumulator, TMEM buffers
-  int sr, sl, sb;                      // ring depths: A raw (TMA), A lo (converters), B (TMA)
+  int sr, sl, sbr, sbl;                // ring depths: A raw (TMA), A lo (converters), B raw (TMA), B lo (converters)
 };
 
 __device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {     // K-major SWIZZLE_128B operand tile
@@ -66,22 +68,23 @@ template <int BN>
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_constant__ ConvParams p,
                                                                const __grid_constant__ GMaps maps,
                                                                const __grid_constant__ GPlan g) {
-  constexpr int B_TILE = BN * 128;             // hi or lo tile of BN weight columns x 32 k
-  constexpr int B_STAGE = 2 * B_TILE;
+  constexpr int B_TILE = BN * 128;             // raw (= hi) or lo tile of BN weight columns x 32 k
   extern __shared__ uint8_t smem_raw[];
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   char* raw_ring = smem;
   char* lo_ring = raw_ring + g.sr * G_A_TILE;
-  char* b_ring = lo_ring + g.sl * G_A_TILE;
-  float* qs_all = reinterpret_cast<float*>(b_ring + g.sb * B_STAGE);
+  char* braw_ring = lo_ring + g.sl * G_A_TILE;
+  char* blo_ring = braw_ring + g.sbr * B_TILE;
+  float* qs_all = reinterpret_cast<float*>(blo_ring + g.sbl * B_TILE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(qs_all + G_QS_FLOATS);
-  // raw_full[8] raw_empty[8] lo_full[8] lo_empty[8] b_full[8] b_empty[8] t_full[2] t_empty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 * G_MAX_STAGES + 4);
+  // raw_full[8] raw_empty[8] lo_full[8] lo_empty[8] braw_full[8] braw_empty[8] blo_full[8] blo_empty[8] t_full[2] t_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 * G_MAX_STAGES + 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_rf = smem_u32(bars), bar_re = smem_u32(bars + G_MAX_STAGES);
   const uint32_t bar_lf = smem_u32(bars + 2 * G_MAX_STAGES), bar_le = smem_u32(bars + 3 * G_MAX_STAGES);
   const uint32_t bar_bf = smem_u32(bars + 4 * G_MAX_STAGES), bar_be = smem_u32(bars + 5 * G_MAX_STAGES);
-  const uint32_t bar_tf = smem_u32(bars + 6 * G_MAX_STAGES), bar_te = smem_u32(bars + 6 * G_MAX_STAGES + 2);
+  const uint32_t bar_blf = smem_u32(bars + 6 * G_MAX_STAGES), bar_ble = smem_u32(bars + 7 * G_MAX_STAGES);
+  const uint32_t bar_tf = smem_u32(bars + 8 * G_MAX_STAGES), bar_te = smem_u32(bars + 8 * G_MAX_STAGES + 2);
 
   if (warp == G_MMA_WARP) {
     if (lane == 0) {
@@ -89,6 +92,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
         mbar_init(bar_rf + 8 * s, 1); mbar_init(bar_re + 8 * s, 1);
         mbar_init(bar_lf + 8 * s, G_CONV_WARPS); mbar_init(bar_le + 8 * s, 1);
         mbar_init(bar_bf + 8 * s, 1); mbar_init(bar_be + 8 * s, 1);
+        mbar_init(bar_blf + 8 * s, G_CONV_WARPS); mbar_init(bar_ble + 8 * s, 1);
       }
       for (int s = 0; s < 2; ++s) { mbar_init(bar_tf + 8 * s, 1); mbar_init(bar_te + 8 * s, G_EPI_WARPS); }
       fence_mbar_init();
@@ -99,37 +103,44 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
   if (warp == G_TMA_A_WARP && lane == 0)
     for (int t = 0; t < p.nterms; ++t) tma_prefetch_desc(&maps.a[t]);
   if (warp == G_TMA_B_WARP && lane == 0)
-    for (int t = 0; t < p.nterms; ++t) { tma_prefetch_desc(&maps.bh[t]); tma_prefetch_desc(&maps.bl[t]); }
+    for (int t = 0; t < p.nterms; ++t) tma_prefetch_desc(&maps.bh[t]);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int nacc = g.nchain + g.corr;
   const int nwork = g.ntiles * g.ngroups;
+  // sub-tiles of work item w's column group (the last group of a layer may be narrower than gw)
+  auto nsub_of = [&](int w) { return (min(g.gw, p.ncols - (w % g.ngroups) * g.gw) + BN - 1) / BN; };
 
   if (warp < G_CONV_WARPS) {
-    // =========================== converters: lo tile of every A chunk ===========================
+    // =========================== converters: lo tiles of every A chunk and every weight sub-tile ===========================
     const int l8 = tid & 7, rs = tid >> 3;
-    int sr = 0, sl = 0;
-    uint32_t phr = 0, phl = 0;
+    int sr = 0, sl = 0, sbr = 0, sbl = 0;
+    uint32_t phr = 0, phl = 0, phb = 0, phbl = 0;
+    auto lo4 = [](float4 v) {
+      float4 l;
+      l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+      l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+      l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+      l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+      return l;
+    };
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+      const int nsub = nsub_of(w);
       for (int t = 0; t < p.nterms; ++t) {
         for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
           mbar_wait(bar_rf + 8 * sr, (phr >> sr) & 1u);
           mbar_wait(bar_le + 8 * sl, ((phl >> sl) & 1u) ^ 1u);
-          const char* hi = raw_ring + (size_t)sr * G_A_TILE;
-          char* lo = lo_ring + (size_t)sl * G_A_TILE;
+          {
+            const char* hi = raw_ring + (size_t)sr * G_A_TILE;
+            char* lo = lo_ring + (size_t)sl * G_A_TILE;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = rs + 32 * i;
-            const uint32_t off = (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4));
-            const float4 v = *reinterpret_cast<const float4*>(hi + off);
-            float4 l;
-            l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-            l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-            l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-            l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-            *reinterpret_cast<float4*>(lo + off) = l;
+            for (int i = 0; i < 4; ++i) {
+              const int row = rs + 32 * i;
+              const uint32_t off = (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4));
+              *reinterpret_cast<float4*>(lo + off) = lo4(*reinterpret_cast<const float4*>(hi + off));
+            }
           }
           fence_proxy_async();
           __syncwarp();
@@ -137,6 +148,23 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
           phr ^= 1u << sr; phl ^= 1u << sl;
           if (++sr == g.sr) sr = 0;
           if (++sl == g.sl) sl = 0;
+          for (int s = 0; s < nsub; ++s) {
+            mbar_wait(bar_bf + 8 * sbr, (phb >> sbr) & 1u);
+            mbar_wait(bar_ble + 8 * sbl, ((phbl >> sbl) & 1u) ^ 1u);
+            const char* hi = braw_ring + (size_t)sbr * B_TILE;
+            char* lo = blo_ring + (size_t)sbl * B_TILE;
+#pragma unroll
+            for (int i = 0; i < BN / 32; ++i) {
+              const uint32_t off = (uint32_t)((i * G_CONV_THREADS + tid) * 16);   // the lo tile mirrors the hi tile byte for byte
+              *reinterpret_cast<float4*>(lo + off) = lo4(*reinterpret_cast<const float4*>(hi + off));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_blf + 8 * sbl);
+            phb ^= 1u << sbr; phbl ^= 1u << sbl;
+            if (++sbr == g.sbr) sbr = 0;
+            if (++sbl == g.sbl) sbl = 0;
+          }
         }
       }
     }
@@ -160,22 +188,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
     }
     __syncwarp();
   } else if (warp == G_TMA_B_WARP) {
-    // =========================== TMA: weight tiles (hi = raw, lo = pre-split) ===========================
+    // =========================== TMA: raw weight tiles ===========================
     if (lane == 0) {
       int sb = 0;
       uint32_t phb = 0;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
         const int col0 = (w % g.ngroups) * g.gw;
+        const int nsub = nsub_of(w);
         for (int t = 0; t < p.nterms; ++t) {
           for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
-            for (int s = 0; s < g.nsub; ++s) {
+            for (int s = 0; s < nsub; ++s) {
               mbar_wait(bar_be + 8 * sb, ((phb >> sb) & 1u) ^ 1u);
-              mbar_arrive_expect_tx(bar_bf + 8 * sb, (uint32_t)B_STAGE);
-              const uint32_t dst = smem_u32(b_ring + (size_t)sb * B_STAGE);
-              tma_load_2d(dst, &maps.bh[t], f0, col0 + s * BN, bar_bf + 8 * sb);
-              tma_load_2d(dst + B_TILE, &maps.bl[t], f0, col0 + s * BN, bar_bf + 8 * sb);
+              mbar_arrive_expect_tx(bar_bf + 8 * sb, (uint32_t)B_TILE);
+              tma_load_2d(smem_u32(braw_ring + (size_t)sb * B_TILE), &maps.bh[t], f0, col0 + s * BN, bar_bf + 8 * sb);
               phb ^= 1u << sb;
-              if (++sb == g.sb) sb = 0;
+              if (++sb == g.sbr) sb = 0;
             }
           }
         }
@@ -185,9 +212,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
   } else if (warp == G_MMA_WARP) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int sr = 0, sl = 0, sb = 0, it = 0;
-      uint32_t phr = 0, phl = 0, phb = 0;
+      // instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128; N (a multiple of 16) is set per sub-tile
+      constexpr uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BM >> 4) << 24);
+      int sr = 0, sl = 0, sbr = 0, sbl = 0, it = 0;
+      uint32_t phr = 0, phl = 0, phb = 0, phbl = 0;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
         const int buf = it % g.nbuf;
         const uint32_t use = (uint32_t)(it / g.nbuf);
@@ -197,6 +225,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
         const uint32_t corr_off = (uint32_t)(g.nchain * g.gw);
         uint32_t init_main = 0, init_corr = 0;                    // bit set: that accumulator holds data already
         int kstep = 0;
+        const int gcols = min(g.gw, p.ncols - (w % g.ngroups) * g.gw);
+        const int nsub = (gcols + BN - 1) / BN;
         for (int t = 0; t < p.nterms; ++t) {
           for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
             mbar_wait(bar_rf + 8 * sr, (phr >> sr) & 1u);         // TMA bytes of the raw tile
@@ -204,11 +234,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
             tc_fence_after();
             const uint64_t a_hi = make_desc_k(smem_u32(raw_ring + (size_t)sr * G_A_TILE));
             const uint64_t a_lo = make_desc_k(smem_u32(lo_ring + (size_t)sl * G_A_TILE));
-            for (int s = 0; s < g.nsub; ++s) {
-              mbar_wait(bar_bf + 8 * sb, (phb >> sb) & 1u);
+            for (int s = 0; s < nsub; ++s) {
+              // the last sub-tile of a group may be narrower: N = its real columns (ncols % 16 == 0)
+              const uint32_t idesc = idesc0 | ((uint32_t)(min(BN, gcols - s * BN) >> 3) << 17);
+              mbar_wait(bar_bf + 8 * sbr, (phb >> sbr) & 1u);      // TMA bytes of the raw weight tile
+              mbar_wait(bar_blf + 8 * sbl, (phbl >> sbl) & 1u);    // its lo tile
               tc_fence_after();
-              const uint32_t baddr = smem_u32(b_ring + (size_t)sb * B_STAGE);
-              const uint64_t b_hi = make_desc_k(baddr), b_lo = make_desc_k(baddr + B_TILE);
+              const uint64_t b_hi = make_desc_k(smem_u32(braw_ring + (size_t)sbr * B_TILE));
+              const uint64_t b_lo = make_desc_k(smem_u32(blo_ring + (size_t)sbl * B_TILE));
 #pragma unroll
               for (int ks = 0; ks < BK / 8; ++ks) {
                 const uint64_t adv = (uint64_t)(ks * 2);          // +32 bytes along K inside the swizzle row
@@ -222,9 +255,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
                 init_corr |= 1u << s;
                 umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
               }
-              umma_commit(bar_be + 8 * sb);
-              phb ^= 1u << sb;
-              if (++sb == g.sb) sb = 0;
+              umma_commit(bar_be + 8 * sbr);
+              umma_commit(bar_ble + 8 * sbl);
+              phb ^= 1u << sbr; phbl ^= 1u << sbl;
+              if (++sbr == g.sbr) sbr = 0;
+              if (++sbl == g.sbl) sbl = 0;
             }
             kstep += BK / 8;
             umma_commit(bar_re + 8 * sr);
@@ -381,18 +416,20 @@ bool make_map(CUtensorMap* m, const float* base, unsigned long long inner, unsig
 
 template <int BN>
 int launch_gemm(const cape_topology* t, const ConvParams& p, const GMaps& maps, GPlan g, cudaStream_t st) {
-  constexpr int B_STAGE = 2 * BN * 128;
-  // ring depths from the shared-memory budget: two lo stages, three weight stages, the rest to the raw A ring
+  constexpr int B_TILE = BN * 128;
+  // Ring depths from the shared-memory budget.  An A chunk lives for nsub sub-tiles (>= 768 clocks each), so three raw
+  // stages cover the TMA latency; a weight sub-tile lives for one, so the weight rings get what is left (two lo stages
+  // each: the converters run one tile ahead of the MMAs).
   const int fixed = 1024 + G_QS_FLOATS * 4 + 1024;
-  g.sl = 2;
-  g.sb = 3;
-  int left = G_SMEM_LIMIT - fixed - g.sl * G_A_TILE - g.sb * B_STAGE;
-  g.sr = left / G_A_TILE;
-  if (g.sr > G_MAX_STAGES) g.sr = G_MAX_STAGES;
-  if (g.sr < 2) return 0;
-  left -= g.sr * G_A_TILE;
-  while (g.sb < G_MAX_STAGES && g.sb < 2 * g.nsub + 1 && left >= B_STAGE) { ++g.sb; left -= B_STAGE; }
-  const int smem = fixed + (g.sr + g.sl) * G_A_TILE + g.sb * B_STAGE;
+  g.sl = 2; g.sbl = 2;
+  g.sr = g.nsub >= 2 ? 3 : 4;
+  int left = G_SMEM_LIMIT - fixed - (g.sr + g.sl) * G_A_TILE - g.sbl * B_TILE;
+  g.sbr = left / B_TILE;
+  if (g.sbr > G_MAX_STAGES) g.sbr = G_MAX_STAGES;
+  if (g.sbr < 2) return 0;
+  left -= g.sbr * B_TILE;
+  while (g.sr < G_MAX_STAGES && left >= G_A_TILE) { ++g.sr; left -= G_A_TILE; }
+  const int smem = fixed + (g.sr + g.sl) * G_A_TILE + (g.sbr + g.sbl) * B_TILE;
   static bool configured = false;
   if (!configured) {
     CAPE_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_LIMIT));
@@ -418,15 +455,17 @@ int launch_gemm_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaS
   for (int i = 0; i < p.nterms; ++i) {
     const TermDev& tm = p.terms[i];
     if (tm.op.idx != nullptr || tm.src_rows != p.rows_out || !tm.vec || tm.stash != nullptr) return 0;
-    if (tm.wT == nullptr || tm.wT_lo == nullptr || (tm.wT_stride % 4) != 0 || !aligned16(tm.wT) || !aligned16(tm.wT_lo))
-      return 0;
+    if (tm.wT == nullptr || (tm.wT_stride % 4) != 0 || !aligned16(tm.wT)) return 0;
     kred += tm.F;
   }
   if (kred < 32) return 0;
   GPlan g{};
-  const int BN = p.ncols > 64 ? 128 : (p.ncols > 32 ? 64 : 32);
+  // MMA N: 256 halves the A-operand reads per flop (the tensor core fetches both operands from shared memory for
+  // every instruction); the precise mode keeps four 128-wide accumulators
+  const int BN = p.precise ? (p.ncols > 64 ? 128 : (p.ncols > 32 ? 64 : 32))
+                           : (p.ncols > 128 ? 256 : (p.ncols > 64 ? 128 : (p.ncols > 32 ? 64 : 32)));
   g.ntiles = (int)((p.total_rows + BM - 1) / BM);
-  const int ncols_r = (p.ncols + BN - 1) / BN * BN;
+  const int ncols_r = (p.ncols + BN - 1) / BN * BN;      // TMEM columns are reserved in whole sub-tiles
   if (p.precise) {
     if (p.epilogue != CAPE_EPI_LINEAR) return 0;
     g.gw = BN; g.nsub = 1; g.nchain = 3; g.corr = 1;
@@ -453,10 +492,10 @@ int launch_gemm_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaS
   for (int i = 0; i < p.nterms; ++i) {
     const TermDev& tm = p.terms[i];
     if (!make_map(&maps.a[i], tm.src, (unsigned long long)tm.F, (unsigned long long)p.total_rows, tm.src_stride, BM) ||
-        !make_map(&maps.bh[i], tm.wT, (unsigned long long)tm.F, (unsigned long long)p.ncols, tm.wT_stride, BN) ||
-        !make_map(&maps.bl[i], tm.wT_lo, (unsigned long long)tm.F, (unsigned long long)p.ncols, tm.wT_stride, BN))
+        !make_map(&maps.bh[i], tm.wT, (unsigned long long)tm.F, (unsigned long long)p.ncols, tm.wT_stride, BN))
       return 0;
   }
+  if (BN == 256) return launch_gemm<256>(t, p, maps, g, st);
   if (BN == 128) return launch_gemm<128>(t, p, maps, g, st);
   if (BN == 64) return launch_gemm<64>(t, p, maps, g, st);
   return launch_gemm<32>(t, p, maps, g, st);

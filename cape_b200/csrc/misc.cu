@@ -192,6 +192,25 @@ __global__ void wtrans_kernel(const float* __restrict__ w, int Fin, int K, int F
   }
 }
 
+// dst[i, :] = src[idx[i], :]: batch assembly from a device-resident dataset (cape_gather_rows)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, long long row_floats,
+                                                          const int32_t* __restrict__ idx, int n, int n_src,
+                                                          float* __restrict__ dst, int vec) {
+  const int i = blockIdx.y;
+  int r = __ldg(idx + i);
+  r = min(max(r, 0), n_src - 1);
+  const float* s = src + (size_t)r * row_floats;
+  float* d = dst + (size_t)i * row_floats;
+  if (vec) {
+    const long long n4 = row_floats >> 2;
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n4; j += (long long)gridDim.x * blockDim.x)
+      reinterpret_cast<float4*>(d)[j] = __ldg(reinterpret_cast<const float4*>(s) + j);
+  } else {
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < row_floats; j += (long long)gridDim.x * blockDim.x)
+      d[j] = __ldg(s + j);
+  }
+}
+
 // All derived weight layouts of many layers in one launch (cape_weight_prep): blockIdx.y = descriptor, the blocks of a
 // row walk its (k, 32 x 32) tiles.  wt (k, c, f) goes through a shared-memory transpose, wk (k, f, c) is a straight copy.
 __global__ void __launch_bounds__(256) wprep_kernel(const cape_wprep* __restrict__ descs) {
@@ -343,6 +362,20 @@ extern "C" int cape_cheb_weight_transpose(const float* w, int Fin, int K, int Fo
   CAPE_REQUIRE(w && wt && Fin > 0 && K > 0 && Fout > 0, "bad arguments");
   dim3 grid((Fin + 31) / 32, (Fout + 31) / 32, K), block(32, 8);
   wtrans_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, Fin, K, Fout, wt, wt_lo);
+  CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
+  return 0;
+}
+
+extern "C" int cape_gather_rows(const float* src, int64_t row_floats, int n_src, const int32_t* idx_device, int n,
+                                float* dst, void* stream) {
+  CAPE_REQUIRE(src && idx_device && dst && row_floats > 0 && n > 0 && n <= 65535 && n_src > 0, "bad arguments");
+  const int vec = (row_floats % 4 == 0) && aligned16(src) && aligned16(dst);
+  long long per = (vec ? row_floats / 4 : row_floats);
+  int bx = (int)((per + 255) / 256);
+  if (bx > 32) bx = 32;
+  dim3 grid((unsigned)bx, (unsigned)n);
+  gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, row_floats, idx_device, n, n_src, dst, vec);
   CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
   return 0;

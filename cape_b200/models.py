@@ -27,7 +27,7 @@ class CAPE(object):
                  lr=0.008, decay_rate=0.99, optimizer="sgd", decay_steps=None, momentum=0.9, cond_dim=0, nz_cond=0,
                  regularization=0, batch_size=32, seed=123, lambda_recon=1.0, lambda_edge=0.0, lambda_latent=1e-3,
                  restart=False, name="", loss_mask=None, device=0, ref_compat=True, checkpoint_dir="checkpoints",
-                 **unused):
+                 device_dataset=True, **unused):
         # name-based operator seam of base_model (lib/models.py:58-62): only the shipped choice has kernels
         if (filter, activation, pool, unpool) != ("chebyshev5", "b1leakyrelu", "poolwT", "poolwT"):
             raise NotImplementedError("kernels exist for filter='chebyshev5', activation='b1leakyrelu', "
@@ -44,6 +44,7 @@ class CAPE(object):
         self.cond_dim, self.cond2_dim = cond_dim, cond2_dim
         self.lambda_l1, self.lambda_edge, self.lambda_latent = lambda_recon, lambda_edge, lambda_latent
         self.device_index, self.ref_compat, self.checkpoint_dir = device, ref_compat, checkpoint_dir
+        self.device_dataset = bool(device_dataset)
         rd = reduce_dim if not isinstance(reduce_dim, bool) else (64 if reduce_dim else 0)
         if rd < 0:
             raise ValueError("reduce dim must be greater than 0!")           # lib/models.py:259
@@ -106,22 +107,50 @@ class CAPE(object):
         np.savez(fn, global_step=np.int64(self.global_step), **vals, **mom)
         return fn
 
+    def save_tf(self, step):
+        """Write the weights as a TensorFlow V2 checkpoint `model.ckpt-<step>` (the reference's tf.train.Saver format,
+        lib/models.py:351,923-924: variables by name, optimiser slots as `<variable>/Momentum`, `global_step`) so
+        that they can be handed back to the reference."""
+        from . import tf_checkpoint
+        path = self._get_path(self.checkpoint_dir)
+        vals = dict(self.net.get_params())
+        for k, v in {**self.net.PG.export(self.net.PG.mom), **self.net.PD.export(self.net.PD.mom)}.items():
+            vals[k + "/Momentum"] = v
+        vals["global_step"] = np.asarray(self.global_step, np.int64)
+        return tf_checkpoint.write_checkpoint(os.path.join(path, "model.ckpt-%d" % step), vals)
+
     def restore(self, filename=None):
-        """Load the newest checkpoint of this run (reference: _get_session, lib/models.py:209-215)."""
+        """Load the newest checkpoint of this run (reference: _get_session, lib/models.py:209-215): a `.npz` written
+        by `save`, or a TensorFlow checkpoint prefix (`model.ckpt-N`: the reference's own / published models,
+        README.md:104) read by cape_b200.tf_checkpoint -- the parameter names are the reference's variable names."""
+        from . import tf_checkpoint
         path = self._get_path(self.checkpoint_dir)
         if filename is None:
-            cands = sorted((f for f in os.listdir(path) if f.startswith("model-")),
+            cands = sorted((f for f in os.listdir(path) if f.startswith("model-") and f.endswith(".npz")),
                            key=lambda f: int(f[6:-4])) if os.path.isdir(path) else []
-            if not cands:
+            if cands:
+                filename = os.path.join(path, cands[-1])
+            else:
+                filename = tf_checkpoint.latest_checkpoint(path) if os.path.isdir(path) else None
+            if filename is None:
                 raise FileNotFoundError("no checkpoint under %s" % path)
-            filename = os.path.join(path, cands[-1])
-        z = np.load(filename)
-        self.net.set_params({k: z[k] for k in z.files if not k.startswith("momentum/") and k != "global_step"})
+        if tf_checkpoint.is_checkpoint(filename):
+            z = tf_checkpoint.read_checkpoint(filename)
+            files, mom_key = list(z), (lambda n: n + "/Momentum")
+        else:
+            z = np.load(filename)
+            files, mom_key = z.files, (lambda n: "momentum/" + n)
+        want = set(self.net.PG.names) | set(self.net.PD.names)
+        missing = sorted(want - set(files))
+        if missing:
+            raise KeyError("checkpoint %s lacks %d variables of this architecture, e.g. %s" % (filename, len(missing),
+                                                                                        missing[:3]))
+        self.net.set_params({k: np.asarray(z[k]).reshape(self.net.specs[k]) for k in want})
         for P in (self.net.PG, self.net.PD):
             for n in P.names:
-                if "momentum/" + n in z.files:
-                    P._view(P.mom, n).copy_(torch.as_tensor(z["momentum/" + n].reshape(-1)))
-        self.global_step = int(z["global_step"])
+                if mom_key(n) in files:
+                    P._view(P.mom, n).copy_(torch.as_tensor(np.asarray(z[mom_key(n)], np.float32).reshape(-1)))
+        self.global_step = int(z["global_step"]) if "global_step" in files else 0
         self._weights_source = "checkpoint"
         return filename
 
@@ -147,6 +176,14 @@ class CAPE(object):
 
     # ---- training (lib/models.py:837-929) ---------------------------------------------------------------------
     def fit(self, data_wrapper):
+        """Training loop of lib/models.py:837-929.  Two things differ from the reference, neither visible in the
+        results: the training split is uploaded to the GPU once and every batch is assembled there from indices
+        (load_data.DeviceDataset; `device_dataset=False` keeps the host path), and under torch.distributed (launch with
+        torchrun, one process per GPU) every rank trains on its own `batch_size` meshes per update with the gradients
+        averaged over ranks (cape_b200.distributed) -- weights stay identical on all ranks, rank 0 validates and saves."""
+        from . import distributed as DP
+        from .load_data import DeviceDataset
+        import torch.distributed as dist
         train_data, train_cond, train_cond2 = data_wrapper.vertices_train, data_wrapper.cond1_train, data_wrapper.cond2_train
         val = (data_wrapper.vertices_val, data_wrapper.cond1_val, data_wrapper.cond2_val, data_wrapper.vertices_val)
         N = self.batch_size
@@ -161,14 +198,26 @@ class CAPE(object):
                 raise ValueError("Please provide an expriment name by setting the --name flag.")   # models.py:858-859
             start_step, self.global_step = 1, 0
         self._weights_source = "fit"
+        net = self.net
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+        allreduce = DP.make_allreduce(world)
+        if world > 1:
+            DP.broadcast_params([net.PG.flat, net.PD.flat, net.PG.mom, net.PD.mom])
+            net.prep_weights()
+            draw = np.random.RandomState(DP.rank_seed(self.cfg["seed"], rank))       # every rank its own batches / noise
+            self.rng = np.random.RandomState(DP.rank_seed(self.cfg["seed"] + 1, rank))
+        else:
+            draw = np.random                                                            # the reference's global stream
+        dev = None
+        if self.device_dataset:
+            dev = DeviceDataset(train_data, train_cond, train_cond2, net.device)
         losses = []
         indices_g, indices_d = collections.deque(), collections.deque()
-        net = self.net
         for step in range(start_step, start_step + num_steps):
             if len(indices_g) < N:
-                indices_g.extend(np.random.permutation(train_data.shape[0]))
+                indices_g.extend(draw.permutation(train_data.shape[0]))
             if len(indices_d) < N:
-                indices_d.extend(np.random.permutation(train_data.shape[0]))
+                indices_d.extend(draw.permutation(train_data.shape[0]))
             idx_g = [indices_g.popleft() for _ in range(N)]
             idx_d = [indices_d.popleft() for _ in range(N)]
             t = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32))
@@ -176,12 +225,15 @@ class CAPE(object):
             # models.py:470-472,905-906), each with fresh eps; ref_compat keeps that, otherwise one update per step
             for _ in range(2 if self.ref_compat else 1):
                 eps = self.rng.normal(size=(N, self.nz)).astype(np.float32)
-                net.set_inputs(t(train_data[idx_g]), t(train_cond[idx_g]), t(train_cond2[idx_g]), t(eps),
-                               t(train_data[idx_d]), t(train_cond[idx_d]), t(train_cond2[idx_d]))
+                if dev is not None:
+                    dev.stage(net, idx_g, idx_d, eps)
+                else:
+                    net.set_inputs(t(train_data[idx_g]), t(train_cond[idx_g]), t(train_cond2[idx_g]), t(eps),
+                                   t(train_data[idx_d]), t(train_cond[idx_d]), t(train_cond2[idx_d]))
                 # both apply_gradients share global_step (models.py:462,467): it advances by 2 per update
-                net.train_step(step=self.global_step)
+                net.train_step(step=self.global_step, allreduce=allreduce)
                 self.global_step += 2
-            if step % num_steps_epoch == 0 or step == num_steps:
+            if (step % num_steps_epoch == 0 or step == num_steps) and rank == 0:
                 string, recon, latent, edge = self.evaluate(*val)
                 losses.append(recon)
                 print("step {} / {}: validation {}  time: {:.0f}s".format(step, num_steps, string, time.time() - t_start))

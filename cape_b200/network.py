@@ -186,11 +186,19 @@ class ChebLayer:
                 self.dx_mode = "basis"
             elif need_dx and self.dw_mode == "aside":
                 self.dx_mode = "contract"
+        # experiment overrides: CAPE_FWD_MODE / CAPE_DX_MODE for every layer, CAPE_MODES="enc/conv8:fwd=fused,disc/conv3:dx=contract"
+        # for single ones (ineligible requests are ignored)
         fm, dm = env("CAPE_FWD_MODE", ""), env("CAPE_DX_MODE", "")
-        if fm and split_ok and (fm != "basis" or (C == 0 and not self.affine and self.dw_mode == "aside")):
+        for item in filter(None, env("CAPE_MODES", "").split(",")):
+            key, val = item.split("=")
+            if key == name + ":fwd":
+                fm = val
+            elif key == name + ":dx":
+                dm = val
+        if fm and (fm == "fused" or (split_ok and (fm != "basis" or (C == 0 and not self.affine and self.dw_mode == "aside")))):
             self.fwd_mode = fm
-        if dm and split_ok and need_dx and (dm != "basis" or self.dw_mode == "gside") and (dm != "contract" or
-                                                                                         self.dw_mode != "gside"):
+        if dm and need_dx and (dm == "fused" or (split_ok and (dm != "basis" or self.dw_mode == "gside")
+                                                 and (dm != "contract" or self.dw_mode != "gside"))):
             self.dx_mode = dm
         if self.dx_mode == "contract":
             self.Wk, self.Wk_lo = torch.empty(K, F, Fout, device=dev), torch.empty(K, F, Fout, device=dev)

@@ -8,7 +8,8 @@ does NOT contain them or anything derived loss-free from them: the .npz is gener
 checkout of qianlim/CAPE and is git-ignored.  It holds the operators as plain CSR arrays
 (indptr/indices/data/shape), the SMPL edge table (data/edges_smpl.npy, used by lib/losses.py:9-25; = upper triangle
 of A[0], checked against the reference file), the per-vertex normalisation statistics
-(data/demo_data/trainset_stats.npz, demos.py:155) and the clothing-vertex index list (demos.py:341).
+(data/demo_data/trainset_stats.npz, demos.py:155), the clothing-vertex index list, the template mesh and the demo
+poses (demos.py:349-357).
 
     python -m cape_b200.pack_topology [--reference /path/to/CAPE]        (default: $CAPE_REFERENCE, /root/reference)
 
@@ -60,6 +61,17 @@ def pack(REF, OUT=OUT):
     out["stats.mean"] = st["mean"].astype(np.float32)
     out["stats.std"] = st["std"].astype(np.float32)
     out["clothing_verts_idx"] = np.load(os.path.join(REF, "data", "clothing_verts_idx.npy")).astype(np.int32)
+    # demo assets (demos.py:351-357): template mesh (minimal body shape + faces) and the demo poses
+    v, f = [], []
+    for ln in open(os.path.join(REF, "data", "template_mesh.obj")):
+        t = ln.split()
+        if t and t[0] == "v":
+            v.append([float(x) for x in t[1:4]])
+        elif t and t[0] == "f":
+            f.append([int(x.split("/")[0]) - 1 for x in t[1:4]])
+    out["template.v"], out["template.f"] = np.asarray(v, np.float64), np.asarray(f, np.int32)
+    dp = np.load(os.path.join(REF, "data", "demo_data", "demo_pose_params.npz"))
+    out["demo.rot"], out["demo.pose"] = dp["rot"], dp["pose"]
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     tmp = OUT + ".tmp.%d.npz" % os.getpid()
     np.savez_compressed(tmp, **out)

@@ -94,6 +94,22 @@ def clothing_verts_idx():
     return _npz()["clothing_verts_idx"]
 
 
+def template_mesh():
+    """(vertices [6890, 3] float64, faces [13776, 3] int32) of data/template_mesh.obj (demos.py:352-353)."""
+    z = _npz()
+    if "template.v" not in z.files:
+        raise FileNotFoundError("%s predates the demo assets: delete it and re-run cape_b200.pack_topology" % _DATA)
+    return z["template.v"], z["template.f"]
+
+
+def demo_pose_params():
+    """(rot [6, 216], pose [6, 72]) of data/demo_data/demo_pose_params.npz (demos.py:355-356)."""
+    z = _npz()
+    if "demo.rot" not in z.files:
+        raise FileNotFoundError("%s predates the demo assets: delete it and re-run cape_b200.pack_topology" % _DATA)
+    return z["demo.rot"], z["demo.pose"]
+
+
 # ---------------------------------------------------------------------------------------------------
 # operator algebra
 # ---------------------------------------------------------------------------------------------------

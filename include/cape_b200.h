@@ -255,6 +255,13 @@ int cape_vae_sample_fwd(const float* mean, const float* logvar, const float* eps
 int cape_vae_sample_bwd(const float* dz, int dz_stride, const float* mean, const float* logvar, const float* eps,
                         float* dmean, float* dlogvar, int N, int nz, float kl_scale, void* stream);
 
+/* ---- input pipeline -------------------------------------------------------------------------------
+ * dst[i, 0:row_floats] = src[idx[i], 0:row_floats] for i < n: assembles a training batch from a dataset that lives in
+ * HBM (replaces the numpy fancy-indexing + feed_dict of lib/models.py:877-903; only the indices cross PCIe).
+ * idx is a DEVICE array; out-of-range indices are clamped. */
+int cape_gather_rows(const float* src, int64_t row_floats, int n_src, const int32_t* idx_device, int n, float* dst,
+                     void* stream);
+
 /* ---- losses (CAPE.loss, lib/models.py:354-416; losses.edge_loss_calc, lib/losses.py:9-25) ----------
  * Reconstruction L1 (mean |pred-gt|), edge loss (mean over edges of ||(p_a-p_b)-(g_a-g_b)||_2; the
  * template added at models.py:375 cancels), KL (mean_n -0.5*sum(1+lv-mu^2-e^lv)); writes

@@ -230,7 +230,7 @@ class Oracle:
     def decoder_cond_vert(self, z_total, y, y2, P):
         """models.py:564-617 with use_res_block_dec=1."""
         s = "generator/decoder/"
-        x = self.dense(z_total, P, s + "fc1", act="leaky", site="dec_fc1")        # :582
+        x = self._keep("dec_fc", self.dense(z_total, P, s + "fc1", act="leaky", site="dec_fc1"))   # :582
         x = x.reshape(x.shape[0], self.p[-1], -1)                                # :584
         if self.reduce_dim > 0:
             x = self.chebyshev5(x, self.Lt[-1], P[s + "1x1-conv/weights"], 1)     # :588
@@ -248,7 +248,7 @@ class Oracle:
         """models.py:620-645; eps is vae_sampling's random_normal made explicit (:194)."""
         z_mean, z_logvar = self.encoder(x, P)
         z = z_mean + torch.sqrt(torch.exp(z_logvar)) * eps                        # :195
-        z_total = torch.cat([z, y, y2], 1)                                        # :641
+        z_total = self._keep("z_total", torch.cat([z, y, y2], 1))                 # :641
         return self.decoder_cond_vert(z_total, y, y2, P), z_mean, z_logvar
 
     def discriminator(self, x, y, y2, P, tag=""):
@@ -272,11 +272,12 @@ class Oracle:
         if self.masks is not None and "l1_sign" in self.masks:
             # |d| with the sign decisions of the implementation under test (same reason as the ReLU decisions: at
             # batch 64 a handful of the 1.3 M residuals lie within fp32 rounding of zero)
-            recon = torch.where(self.masks["l1_sign"], d, -d).mean()
+            # (three-valued: a residual that is exactly zero in the implementation under test has gradient 0 there)
+            recon = (self.masks["l1_sign"].to(d.dtype) * d).mean()
         else:
             recon = d.abs().mean()                                                 # :358-360
         if self.record is not None:
-            self.record["l1_sign"] = (d > 0).clone()
+            self.record["l1_sign"] = torch.sign(d.detach())
         latent = (-0.5 * (1 + z_logvar - z_mean ** 2 - torch.exp(z_logvar)).sum(1)).mean()  # :371-372
         e0 = torch.as_tensor(edges[:, 0].astype(np.int64))
         e1 = torch.as_tensor(edges[:, 1].astype(np.int64))

@@ -47,8 +47,9 @@ def main():
         d_real = o.discriminator(ob["x_d"], yd, y2d, P, tag="_real")
         d_fake = o.discriminator(x_hat, y, y2, P, tag="_fake")
         Ls = o.losses(x_hat, ob["gt"], zm, zl, d_real, d_fake, P, T.smpl_edges())
+        o.keep["x_hat"] = x_hat
         names = list(o.keep)
-        gr = torch.autograd.grad(Ls["loss_g"], [o.keep[k] for k in names] + [zm, zl], allow_unused=True)
+        gr = torch.autograd.grad(Ls["loss_g"], [o.keep[k] for k in names] + [zm, zl], allow_unused=True, retain_graph=True)
         G = dict(zip(names + ["z_mean", "z_logvar"], gr))
         print("==== tensor cores %s ====" % ("on" if tc_on else "off"))
         print("  z_mean      fwd %.2e   z_logvar fwd %.2e" % (parity.rel(net.z_mean.cpu().numpy(), zm.detach().numpy()),
@@ -57,6 +58,27 @@ def main():
                                               parity.rel(net.g_logvar.cpu().numpy(), G["z_logvar"].numpy())))
         print("  enc_red     fwd %.2e   grad %.2e" % (parity.rel(net.enc_red.cpu().numpy(), o.keep["enc_red"].detach().numpy()),
                                                      parity.rel(net.g_enc_red.cpu().numpy(), G["enc_red"].numpy())))
+        print("  z_total     fwd %.2e   (max |z| %.3e)" % (parity.rel(net.z_total.cpu().numpy(), o.keep["z_total"].detach().numpy()),
+                                                      float(o.keep["z_total"].abs().max())))
+        print("  x_hat       fwd %.2e   (max |x_hat| %.3e)   d_xhat %.2e (max %.3e)" % (
+            parity.rel(net.x_hat.cpu().numpy(), x_hat.detach().numpy()), float(x_hat.abs().max()),
+            parity.rel(net.d_xhat.cpu().numpy(), G["x_hat"].numpy()), float(G["x_hat"].abs().max())))
+        for nm, L_ in (("recon", Ls["recon"] * cfg["lambda_recon"]), ("edge", Ls["edge"] * cfg["lambda_edge"]),
+                       ("gan_g", Ls["gan_g"] * cfg["lambda_gan"])):
+            gg = torch.autograd.grad(L_, x_hat, retain_graph=True)[0]
+            err = (net.d_xhat.cpu().double() - G["x_hat"]).abs()
+            wi = np.unravel_index(int(err.argmax()), err.shape)
+            print("      d %-6s / d x_hat: max %.3e   at the worst element %s: %.4e  (cuda total %.4e, oracle total %.4e, "
+                  "x_hat - x there: cuda %.4e oracle %.4e)" % (nm, float(gg.abs().max()), wi, float(gg[wi]),
+                                                               float(net.d_xhat[wi]), float(G["x_hat"][wi]),
+                                                               float(net.x_hat[wi] - net.in_x[wi]),
+                                                               float(x_hat[wi] - ob["gt"][wi])))
+        a = o.keep["dec_fc"].detach()
+        slope = torch.where(a > 0, torch.ones_like(a), torch.full_like(a, 0.2))
+        print("  dec_fc      fwd %.2e   grad(pre) %.2e   grad(z_total) %.2e" % (
+            parity.rel(net.dec_fc.cpu().numpy(), a.numpy()),
+            parity.rel(net.g_dec_fc_t.cpu().numpy(), (G["dec_fc"] * slope).numpy()),
+            parity.rel(net.g_z.cpu().numpy(), G["z_total"][:, :net.nz].numpy())))
         for i in range(8, 0, -1):
             a = o.keep["enc_act%d" % i].detach()
             # net.g_enc[i-1] is the gradient w.r.t. the PRE-activation (slope already applied), pooled rows

@@ -13,6 +13,18 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 
+def truth_table(res):
+    """float64-truth mode: print (CUDA error, fp32-oracle error) per tensor, return the part that exceeds the gate
+    max(1e-4, 2 x fp32-oracle error) as ratios to it (> 1 fails)."""
+    out = {}
+    for k, (e, b) in res.items():
+        gate = max(1e-4, 2 * b)
+        if not k.startswith("param ") and not k.startswith("clipped"):
+            print("    %-72s cuda %.2e   fp32-oracle %.2e%s" % (k, e, b, "   <-- over the gate" if e >= gate else ""))
+        out[k + " (err / gate)"] = e / gate * 1e-4
+    return out
+
+
 def main():
     import torch
     import parity
@@ -28,7 +40,7 @@ def main():
             ("step", lambda: parity.train_step(h, cfg, N=2)),
             ("step_ref", lambda: parity.train_step(h, cfg, N=2, ref_compat=True)),
             ("step_rawinit", lambda: parity.train_step(h, cfg, N=2, fc_scale=1.0)),
-            ("step_truth", lambda: {k: v[0] for k, v in parity.train_step(h, cfg, N=2, fc_scale=1.0, truth=True).items()}),
+            ("step_truth", lambda: truth_table(parity.train_step(h, cfg, N=2, fc_scale=1.0, truth=True))),
             ("step3", lambda: parity.train_step(h, cfg, N=2, nsteps=3, fc_scale=1.0)),
             ("step_n64", lambda: parity.train_step(h, cfg, N=64, use_graph=True, fc_scale=1.0)),
             ("fwd_n32", lambda: parity.generator_forward(h, cfg, N=32)),

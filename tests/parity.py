@@ -100,7 +100,9 @@ def plain_operand_cases(h):
     out = {}
     out.update(cheb_grads("plain L8 K=1 512->64", h["L"][8], 1, 512, 64, 4, act=None))
     out.update(cheb_grads("plain L8 K=1 256->544", h["L"][8], 1, 256, 544, 3, act=None))
-    out.update(cheb_grads("plain L6 K=1 160->288 leaky", h["L"][6], 1, 160, 288, 2, seed=3))
+    r = cheb_grads("plain L6 K=1 160->288 leaky", h["L"][6], 1, 160, 288, 2, seed=3)
+    out.update({k: v for k, v in r.items() if k.endswith(" fwd")})      # no imposed decisions here: forward only
+    out.update(cheb_grads("plain L6 K=1 160->288", h["L"][6], 1, 160, 288, 2, act=None, seed=3))
     out.update(cheb_grads("plain L4 K=1 96->32 multi-tile", h["L"][4], 1, 96, 32, 30, act=None, seed=4))
     return out
 
@@ -293,7 +295,7 @@ def cuda_masks(net, h, N):
             if r is not None:
                 rows["disc%d%s" % (i + 1, tag)] = r
     masks["cond_pose_d"], masks["cond_pose_g"] = (net.cp_h[:N] > 0).cpu(), (net.cp_h[N:] > 0).cpu()
-    masks["l1_sign"] = ((net.x_hat - net.in_x) > 0).cpu()     # sign decisions of the L1 reconstruction loss
+    masks["l1_sign"] = torch.sign(net.x_hat - net.in_x).cpu()     # sign decisions (-1, 0, +1) of the L1 reconstruction loss
     return masks, rows
 
 
