@@ -242,6 +242,9 @@ def main():
     batch = [hb[k] for k in order]
     net.set_inputs(*batch)
     allreduce = DP.make_allreduce(world) if train else None   # forward-only replicas have nothing to exchange
+    overlap = train and world > 1 and os.environ.get("CAPE_DP_OVERLAP", "1") != "0"
+    if overlap:
+        net.set_data_parallel(world)                          # bucketed all-reduce inside the step, behind the backward
 
     use_graph = not args.no_graph
     c0 = lib.cape_launch_count()
@@ -256,13 +259,16 @@ def main():
         try:
             if train:
                 net.capture_graphs()
-                graph_note = "2 CUDA graphs/step (fwd+bwd, update)" + ("; NCCL all-reduce between them" if world > 1 else "")
+                graph_note = "2 CUDA graphs/step (fwd+bwd, update)" + (
+                    "" if world == 1 else ("; bucketed NCCL all-reduce captured inside the first, overlapping the backward"
+                                           if overlap else "; NCCL all-reduce between them"))
             else:
                 net.capture_forward_graph()
                 graph_note = "1 CUDA graph/step (generator forward)"
         except Exception as e:                              # pragma: no cover
             use_graph = False
             graph_note = "eager (graph capture failed: %s)" % str(e)[:80]
+            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:

@@ -45,6 +45,12 @@ class WPrep(C.Structure):
                 ("wt_lo", C.c_void_p), ("wk", C.c_void_p), ("wk_lo", C.c_void_p)]
 
 
+class GemmItem(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("a_rs", C.c_int64), ("a_cs", C.c_int64), ("b", C.c_void_p), ("b_rs", C.c_int64),
+                ("b_cs", C.c_int64), ("c", C.c_void_p), ("c_rs", C.c_int64), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+                ("alpha", C.c_float), ("beta", C.c_float)]
+
+
 class DwArgs(C.Structure):
     _fields_ = [("N", C.c_int), ("rows_out", C.c_int), ("ncols", C.c_int), ("src", C.c_void_p), ("op", C.c_int),
                 ("F", C.c_int), ("src_rows", C.c_int), ("src_stride", C.c_int), ("g", C.c_void_p),
@@ -63,6 +69,8 @@ SIGNATURES = {
     "cape_topology_reserve_workspace": (C.c_int, [C.c_void_p, C.c_int64]),
     "cape_set_tensor_cores": (C.c_int, [C.c_int]),
     "cape_tensor_cores_enabled": (C.c_int, []),
+    "cape_gemm_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "cape_gemm_item_bytes": (C.c_int, []),
     "cape_gather_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "cape_weight_prep": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "cape_set_tuning": (C.c_int, [C.c_int, C.c_int]),

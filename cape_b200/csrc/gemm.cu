@@ -82,15 +82,12 @@ __device__ __forceinline__ void gemm_store(const GemmParams& p, int tid, const f
   }
 }
 
-__global__ void __launch_bounds__(256, 2) gemm_kernel(const __grid_constant__ GemmParams p) {
-  __shared__ __align__(16) float As[G_BK * G_STRIDE];
-  __shared__ __align__(16) float Bs[G_BK * G_STRIDE];
+// One 64 x 64 output tile over the reduction range [kbeg, kend).  mode 0: epilogue store (alpha, bias, act, beta),
+// 1: raw partial sums to the split-K workspace slice `z`, 2: alpha * acc added atomically to c (batched accumulations).
+__device__ __forceinline__ void gemm_tile(const GemmParams& p, int m0, int n0, int kbeg, int kend, int z, int mode,
+                                          float* As, float* Bs) {
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int n0 = blockIdx.x * G_BN, m0 = blockIdx.y * G_BM;
-  const int kbeg = blockIdx.z * p.k_per_split;
-  const int kend = min(p.K, kbeg + p.k_per_split);
-
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -127,8 +124,10 @@ __global__ void __launch_bounds__(256, 2) gemm_kernel(const __grid_constant__ Ge
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= p.N) continue;
-      if (p.nsplit > 1) {
-        p.ws[((size_t)blockIdx.z * p.M + m) * p.N + n] = acc[i][j];
+      if (mode == 1) {
+        p.ws[((size_t)z * p.M + m) * p.N + n] = acc[i][j];
+      } else if (mode == 2) {
+        atomicAdd(p.c + (size_t)m * p.c_rs + n, p.alpha * acc[i][j]);
       } else {
         float v = p.alpha * acc[i][j];
         if (p.bias) v += __ldg(p.bias + n);
@@ -139,6 +138,25 @@ __global__ void __launch_bounds__(256, 2) gemm_kernel(const __grid_constant__ Ge
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(256, 2) gemm_kernel(const __grid_constant__ GemmParams p) {
+  __shared__ __align__(16) float As[G_BK * G_STRIDE];
+  __shared__ __align__(16) float Bs[G_BK * G_STRIDE];
+  const int kbeg = blockIdx.z * p.k_per_split;
+  gemm_tile(p, blockIdx.y * G_BM, blockIdx.x * G_BN, kbeg, min(p.K, kbeg + p.k_per_split), blockIdx.z,
+            p.nsplit > 1 ? 1 : 0, As, Bs);
+}
+
+// Many small products in one launch (cape_gemm_batch): blockIdx.y = item, the blocks of a row walk its 64 x 64 tiles.
+// An item with beta == 1 ACCUMULATES atomically (several items may add into the same C), beta == 0 overwrites.
+__global__ void __launch_bounds__(256, 2) gemm_batch_kernel(const GemmParams* __restrict__ items) {
+  __shared__ __align__(16) float As[G_BK * G_STRIDE];
+  __shared__ __align__(16) float Bs[G_BK * G_STRIDE];
+  const GemmParams p = items[blockIdx.y];
+  const int mt = (p.M + G_BM - 1) / G_BM, nt = (p.N + G_BN - 1) / G_BN;
+  for (int tile = blockIdx.x; tile < mt * nt; tile += gridDim.x)
+    gemm_tile(p, (tile / nt) * G_BM, (tile % nt) * G_BN, 0, p.K, 0, p.beta != 0.f ? 2 : 0, As, Bs);
 }
 
 __global__ void gemm_reduce_kernel(const __grid_constant__ GemmParams p) {
@@ -204,3 +222,36 @@ extern "C" int cape_gemm(cape_topology* t, int M, int N, int K, const float* a, 
   }
   return 0;
 }
+
+extern "C" int cape_gemm_batch(const cape_gemm_item* items_host, int n, void* table_device, int blocks_per_item,
+                               void* stream) {
+  // items_host != NULL: (re)build the device table (synchronous copy, done once per distinct step schedule);
+  // items_host == NULL: launch from the table as it is
+  CAPE_REQUIRE(table_device && n > 0 && n <= 65535, "bad arguments");
+  if (items_host != nullptr) {
+    std::vector<GemmParams> tab((size_t)n);
+    for (int i = 0; i < n; ++i) {
+      const cape_gemm_item& s = items_host[i];
+      CAPE_REQUIRE(s.a && s.b && s.c && s.M > 0 && s.N > 0 && s.K > 0, "bad item");
+      CAPE_REQUIRE((s.a_cs == 1 || s.a_rs == 1) && (s.b_cs == 1 || s.b_rs == 1), "operands need a unit stride");
+      CAPE_REQUIRE(s.beta == 0.f || s.beta == 1.f, "beta must be 0 (overwrite) or 1 (atomic accumulate)");
+      GemmParams& p = tab[i];
+      p = GemmParams{};
+      p.M = s.M; p.N = s.N; p.K = s.K;
+      p.a = s.a; p.a_rs = s.a_rs; p.a_cs = s.a_cs;
+      p.b = s.b; p.b_rs = s.b_rs; p.b_cs = s.b_cs;
+      p.c = s.c; p.c_rs = s.c_rs; p.alpha = s.alpha; p.beta = s.beta;
+      p.nsplit = 1; p.k_per_split = s.K;
+    }
+    CAPE_CHECK_CUDA(cudaMemcpy(table_device, tab.data(), (size_t)n * sizeof(GemmParams), cudaMemcpyHostToDevice));
+    return (int)sizeof(GemmParams);
+  }
+  if (blocks_per_item < 1) blocks_per_item = 4;
+  dim3 grid((unsigned)blocks_per_item, (unsigned)n);
+  gemm_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const GemmParams*>(table_device));
+  CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
+  return 0;
+}
+
+extern "C" int cape_gemm_item_bytes(void) { return (int)sizeof(GemmParams); }

@@ -57,6 +57,7 @@ struct GPlan {
   int gw, nsub, ngroups, ntiles;       // group width (columns), BN-wide sub-tiles per group, groups per row tile, row tiles
   int nchain, corr, nbuf, tmem_cols;   // main accumulators per group, 1 = separate correction accumulator, TMEM buffers
   int sr, sl, sbr, sbl;                // ring depths: A raw (TMA), A lo (converters), B raw (TMA), B lo (converters)
+  int rotate;                          // 1: every row tile starts its reduction at a different chunk (see chunk_of)
 };
 
 __device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {     // K-major SWIZZLE_128B operand tile
@@ -64,7 +65,7 @@ __device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {     // K-m
          (2ull << 61);
 }
 
-template <int BN>
+template <int BN, bool PRECISE>
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_constant__ ConvParams p,
                                                                const __grid_constant__ GMaps maps,
                                                                const __grid_constant__ GPlan g) {
@@ -112,6 +113,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
   const int nwork = g.ntiles * g.ngroups;
   // sub-tiles of work item w's column group (the last group of a layer may be narrower than gw)
   auto nsub_of = [&](int w) { return (min(g.gw, p.ncols - (w % g.ngroups) * g.gw) + BN - 1) / BN; };
+  // The reduction of a work item is a list of 32-deep chunks over all terms.  All CTAs walk the same weight tiles, so
+  // with a common order the whole chip asks the same few L2 lines at the same moment; row tile i therefore starts at
+  // chunk (5 i mod nchunks) and wraps around.  chunk_of maps the j-th chunk of work item w to (term, f0).
+  int nchunks = 0;
+  for (int t = 0; t < p.nterms; ++t) nchunks += (p.terms[t].F + BK - 1) / BK;
+  auto chunk_of = [&](int w, int j, int& t, int& f0) {
+    int c = j + (g.rotate ? ((w / g.ngroups) * 5) % nchunks : 0);
+    if (c >= nchunks) c -= nchunks;
+    for (t = 0;; ++t) {
+      const int nt = (p.terms[t].F + BK - 1) / BK;
+      if (c < nt) break;
+      c -= nt;
+    }
+    f0 = c * BK;
+  };
 
   if (warp < G_CONV_WARPS) {
     // =========================== converters: lo tiles of every A chunk and every weight sub-tile ===========================
@@ -128,8 +144,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
     };
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
       const int nsub = nsub_of(w);
-      for (int t = 0; t < p.nterms; ++t) {
-        for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+      for (int j = 0; j < nchunks; ++j) {
+        {
           mbar_wait(bar_rf + 8 * sr, (phr >> sr) & 1u);
           mbar_wait(bar_le + 8 * sl, ((phl >> sl) & 1u) ^ 1u);
           {
@@ -175,8 +191,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
       uint32_t phr = 0;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
         const int row0 = (w / g.ngroups) * BM;
-        for (int t = 0; t < p.nterms; ++t) {
-          for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+        for (int j = 0; j < nchunks; ++j) {
+          {
+            int t, f0;
+            chunk_of(w, j, t, f0);
             mbar_wait(bar_re + 8 * sr, ((phr >> sr) & 1u) ^ 1u);
             mbar_arrive_expect_tx(bar_rf + 8 * sr, (uint32_t)G_A_TILE);
             tma_load_2d(smem_u32(raw_ring + (size_t)sr * G_A_TILE), &maps.a[t], f0, row0, bar_rf + 8 * sr);
@@ -195,8 +213,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
       for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
         const int col0 = (w % g.ngroups) * g.gw;
         const int nsub = nsub_of(w);
-        for (int t = 0; t < p.nterms; ++t) {
-          for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+        for (int j = 0; j < nchunks; ++j) {
+          {
+            int t, f0;
+            chunk_of(w, j, t, f0);
             for (int s = 0; s < nsub; ++s) {
               mbar_wait(bar_be + 8 * sb, ((phb >> sb) & 1u) ^ 1u);
               mbar_arrive_expect_tx(bar_bf + 8 * sb, (uint32_t)B_TILE);
@@ -222,18 +242,23 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
         mbar_wait(bar_te + 8 * buf, (use & 1u) ^ 1u);            // the epilogue has drained this buffer
         tc_fence_after();
         const uint32_t tb = tmem_base + (uint32_t)(buf * g.gw * nacc);
-        const uint32_t corr_off = (uint32_t)(g.nchain * g.gw);
-        uint32_t init_main = 0, init_corr = 0;                    // bit set: that accumulator holds data already
-        int kstep = 0;
         const int gcols = min(g.gw, p.ncols - (w % g.ngroups) * g.gw);
         const int nsub = (gcols + BN - 1) / BN;
-        for (int t = 0; t < p.nterms; ++t) {
-          for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
+        // PRECISE: the hi*hi products of k-step q go to chain q mod 3, the corrections to the fourth accumulator.  This one
+        // thread feeds the tensor core, so the loop below is kept free of divisions and data-dependent branches: the chain
+        // of a chunk's first k-step is carried along (4 k-steps per chunk: it advances by one), and "first write
+        // overwrites" only concerns chunk 0 (k-steps 0..2 start the three chains, k-step 0 the correction accumulator).
+        uint32_t c0 = 0;
+        for (int j = 0; j < nchunks; ++j) {
+          {
+            const uint32_t later = j > 0 ? 1u : 0u;
             mbar_wait(bar_rf + 8 * sr, (phr >> sr) & 1u);         // TMA bytes of the raw tile
             mbar_wait(bar_lf + 8 * sl, (phl >> sl) & 1u);         // its lo tile
             tc_fence_after();
             const uint64_t a_hi = make_desc_k(smem_u32(raw_ring + (size_t)sr * G_A_TILE));
             const uint64_t a_lo = make_desc_k(smem_u32(lo_ring + (size_t)sl * G_A_TILE));
+            const uint32_t c1 = c0 == 2 ? 0u : c0 + 1, c2 = c1 == 2 ? 0u : c1 + 1;
+            const uint32_t chain_off[4] = {c0 * (uint32_t)g.gw, c1 * (uint32_t)g.gw, c2 * (uint32_t)g.gw, c0 * (uint32_t)g.gw};
             for (int s = 0; s < nsub; ++s) {
               // the last sub-tile of a group may be narrower: N = its real columns (ncols % 16 == 0)
               const uint32_t idesc = idesc0 | ((uint32_t)(min(BN, gcols - s * BN) >> 3) << 17);
@@ -242,18 +267,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
               tc_fence_after();
               const uint64_t b_hi = make_desc_k(smem_u32(braw_ring + (size_t)sbr * B_TILE));
               const uint64_t b_lo = make_desc_k(smem_u32(blo_ring + (size_t)sbl * B_TILE));
+              const uint32_t d0 = tb + (uint32_t)(s * BN);
 #pragma unroll
               for (int ks = 0; ks < BK / 8; ++ks) {
                 const uint64_t adv = (uint64_t)(ks * 2);          // +32 bytes along K inside the swizzle row
-                const int chain = g.corr ? (kstep + ks) % g.nchain : 0;
-                const uint32_t d_main = tb + (uint32_t)(chain * g.gw + s * BN);
-                const uint32_t d_corr = g.corr ? tb + corr_off + (uint32_t)(s * BN) : d_main;
-                const uint32_t mbit = 1u << (chain * g.nsub + s);
-                umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (init_main & mbit) ? 1u : 0u);
-                init_main |= mbit;
-                umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, (!g.corr || (init_corr >> s) & 1u) ? 1u : 0u);
-                init_corr |= 1u << s;
-                umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+                if (PRECISE) {
+                  const uint32_t d_corr = d0 + 3u * (uint32_t)g.gw;
+                  umma_tf32(d0 + chain_off[ks], a_hi + adv, b_hi + adv, idesc, ks < 3 ? later : 1u);
+                  umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, ks == 0 ? later : 1u);
+                  umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+                } else {
+                  umma_tf32(d0, a_hi + adv, b_hi + adv, idesc, ks == 0 ? later : 1u);
+                  umma_tf32(d0, a_lo + adv, b_hi + adv, idesc, 1u);
+                  umma_tf32(d0, a_hi + adv, b_lo + adv, idesc, 1u);
+                }
               }
               umma_commit(bar_be + 8 * sbr);
               umma_commit(bar_ble + 8 * sbl);
@@ -261,7 +288,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
               if (++sbr == g.sbr) sbr = 0;
               if (++sbl == g.sbl) sbl = 0;
             }
-            kstep += BK / 8;
+            c0 = c1;
             umma_commit(bar_re + 8 * sr);
             umma_commit(bar_le + 8 * sl);
             phr ^= 1u << sr; phl ^= 1u << sl;
@@ -280,7 +307,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
     const int row = quad * 32 + lane;
     int total_ksteps = 0;
     for (int t = 0; t < p.nterms; ++t) total_ksteps += (p.terms[t].F + BK - 1) / BK * (BK / 8);
-    const int nused = g.corr ? min(g.nchain, total_ksteps) : 1;   // main chains that received data
+    const int nused = PRECISE ? min(3, total_ksteps) : 1;         // main chains that received data
     int it = 0;
     for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
       const int buf = it % g.nbuf;
@@ -334,7 +361,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
           }
         }
         tmem_ld16(taddr_row + (uint32_t)c0, v0);
-        if (g.corr) {
+        if (PRECISE) {
           // precise mode: the main chains and the correction accumulator are added here, in fp32 with round-to-nearest
           float vc[16];
           for (int ch = 1; ch < nused; ++ch) {
@@ -342,7 +369,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
 #pragma unroll
             for (int j = 0; j < 16; ++j) v0[j] += vc[j];
           }
-          tmem_ld16(taddr_row + (uint32_t)(g.nchain * g.gw + c0), vc);
+          tmem_ld16(taddr_row + (uint32_t)(3 * g.gw + c0), vc);
 #pragma unroll
           for (int j = 0; j < 16; ++j) v0[j] += vc[j];
         }
@@ -414,30 +441,31 @@ bool make_map(CUtensorMap* m, const float* base, unsigned long long inner, unsig
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN>
+template <int BN, bool PRECISE>
 int launch_gemm(const cape_topology* t, const ConvParams& p, const GMaps& maps, GPlan g, cudaStream_t st) {
   constexpr int B_TILE = BN * 128;
   // Ring depths from the shared-memory budget.  An A chunk lives for nsub sub-tiles (>= 768 clocks each), so three raw
   // stages cover the TMA latency; a weight sub-tile lives for one, so the weight rings get what is left (two lo stages
   // each: the converters run one tile ahead of the MMAs).
   const int fixed = 1024 + G_QS_FLOATS * 4 + 1024;
-  g.sl = 2; g.sbl = 2;
-  g.sr = g.nsub >= 2 ? 3 : 4;
-  int left = G_SMEM_LIMIT - fixed - (g.sr + g.sl) * G_A_TILE - g.sbl * B_TILE;
-  g.sbr = left / B_TILE;
-  if (g.sbr > G_MAX_STAGES) g.sbr = G_MAX_STAGES;
-  if (g.sbr < 2) return 0;
-  left -= g.sbr * B_TILE;
+  g.sl = 2; g.sbl = 2; g.sbr = 2;
+  int left = G_SMEM_LIMIT - fixed - g.sl * G_A_TILE - (g.sbl + g.sbr) * B_TILE;
+  g.sr = left / G_A_TILE;
+  const int sr_want = g.nsub >= 2 ? 3 : 4;
+  if (g.sr < 2) return 0;
+  if (g.sr > sr_want) g.sr = sr_want;
+  left -= g.sr * G_A_TILE;
+  while (g.sbr < G_MAX_STAGES && left >= B_TILE) { ++g.sbr; left -= B_TILE; }
   while (g.sr < G_MAX_STAGES && left >= G_A_TILE) { ++g.sr; left -= G_A_TILE; }
   const int smem = fixed + (g.sr + g.sl) * G_A_TILE + (g.sbr + g.sbl) * B_TILE;
   static bool configured = false;
   if (!configured) {
-    CAPE_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_LIMIT));
+    CAPE_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_LIMIT));
     configured = true;
   }
   const int nwork = g.ntiles * g.ngroups;
   const int grid = nwork < t->sm_count ? nwork : t->sm_count;
-  gemm_tc_kernel<BN><<<grid, G_THREADS, smem, st>>>(p, maps, g);
+  gemm_tc_kernel<BN, PRECISE><<<grid, G_THREADS, smem, st>>>(p, maps, g);
   CAPE_CHECK_CUDA(cudaGetLastError());
   count_launches(1);
   return 1;
@@ -478,6 +506,7 @@ int launch_gemm_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaS
     g.ngroups = (ncols_r + g.gw - 1) / g.gw;
   }
   const int nacc = g.nchain + g.corr;
+  g.rotate = g_tuning[9] != 1;          // experiment knob 9 = 1: every row tile walks the reduction in the same order
   g.nbuf = (2 * g.gw * nacc <= 512) ? 2 : 1;
   g.tmem_cols = 32;
   while (g.tmem_cols < g.gw * nacc * g.nbuf) g.tmem_cols *= 2;
@@ -495,10 +524,15 @@ int launch_gemm_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaS
         !make_map(&maps.bh[i], tm.wT, (unsigned long long)tm.F, (unsigned long long)p.ncols, tm.wT_stride, BN))
       return 0;
   }
-  if (BN == 256) return launch_gemm<256>(t, p, maps, g, st);
-  if (BN == 128) return launch_gemm<128>(t, p, maps, g, st);
-  if (BN == 64) return launch_gemm<64>(t, p, maps, g, st);
-  return launch_gemm<32>(t, p, maps, g, st);
+  if (p.precise) {
+    if (BN == 128) return launch_gemm<128, true>(t, p, maps, g, st);
+    if (BN == 64) return launch_gemm<64, true>(t, p, maps, g, st);
+    return launch_gemm<32, true>(t, p, maps, g, st);
+  }
+  if (BN == 256) return launch_gemm<256, false>(t, p, maps, g, st);
+  if (BN == 128) return launch_gemm<128, false>(t, p, maps, g, st);
+  if (BN == 64) return launch_gemm<64, false>(t, p, maps, g, st);
+  return launch_gemm<32, false>(t, p, maps, g, st);
 }
 
 }  // namespace cape

@@ -7,31 +7,36 @@
 
 namespace cape {
 
-constexpr int GN_ROWS = 32;      // rows per CTA in the reduction passes
+constexpr int GN_ROWS = 64;      // rows per CTA in the reduction passes
 constexpr int GN_MAXG = 32;
 
+// Partial sums of one block of rows: thread = (row slot, float4 column); per-thread register sums over its rows, a
+// shared-memory reduction over the row slots, then one fp64 atomic per group and block.
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int rows, int C, int G,
-                                                       double* __restrict__ acc) {
-  __shared__ double gs[GN_MAXG][2];
-  const int n = blockIdx.y;
-  const int r0 = blockIdx.x * GN_ROWS, r1 = min(rows, r0 + GN_ROWS);
-  const int cpg = C / G;
-  if (threadIdx.x < GN_MAXG) { gs[threadIdx.x][0] = 0.0; gs[threadIdx.x][1] = 0.0; }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f, q = 0.f;
-    const float* xp = x + ((size_t)n * rows) * C + c;
-    for (int r = r0; r < r1; ++r) {
-      const float v = __ldg(xp + (size_t)r * C);
-      s += v; q = fmaf(v, v, q);
+                                                       int rows_per_block, double* __restrict__ acc) {
+  __shared__ float red[2][1024];
+  const int n = blockIdx.y, cpr = C >> 2, rslots = min(256 / cpr, 32);
+  const int rs = threadIdx.x / cpr, c4 = threadIdx.x % cpr;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rs < rslots) {
+    const float4* xp = reinterpret_cast<const float4*>(x + (size_t)n * rows * C) + c4;
+    for (int r = r0 + rs; r < r1; r += rslots) {
+      const float4 v = __ldg(xp + (size_t)r * cpr);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
     }
-    atomicAdd(&gs[c / cpg][0], (double)s);
-    atomicAdd(&gs[c / cpg][1], (double)q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[0][rs * C + c4 * 4 + j] = s[j]; red[1][rs * C + c4 * 4 + j] = q[j]; }
   }
   __syncthreads();
   if (threadIdx.x < G) {
-    atomicAdd(acc + ((size_t)n * G + threadIdx.x) * 2 + 0, gs[threadIdx.x][0]);
-    atomicAdd(acc + ((size_t)n * G + threadIdx.x) * 2 + 1, gs[threadIdx.x][1]);
+    const int cpg = C / G;
+    double ds = 0.0, dq = 0.0;
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c)
+      for (int k = 0; k < rslots; ++k) { ds += (double)red[0][k * C + c]; dq += (double)red[1][k * C + c]; }
+    atomicAdd(acc + ((size_t)n * G + threadIdx.x) * 2 + 0, ds);
+    atomicAdd(acc + ((size_t)n * G + threadIdx.x) * 2 + 1, dq);
   }
 }
 
@@ -46,73 +51,116 @@ __global__ void gn_finalize_kernel(const double* __restrict__ acc, int total, do
   stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-__global__ void gn_apply_kernel(const float* __restrict__ x, long long total, int rows, int C, int G,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ stats, float* __restrict__ y) {
-  const int cpg = C / G;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const int n = (int)(i / ((long long)rows * C));
-    const float* st = stats + ((size_t)n * G + c / cpg) * 2;
-    const float v = (x[i] - st[0]) * st[1] * __ldg(gamma + c) + __ldg(beta + c);
-    y[i] = fmaxf(v, 0.f);
+// y = relu(gamma * (x - mean) * rstd + beta): blockIdx.y = sample, float4 per thread, 32-bit index arithmetic
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, int rows, int C, int G,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ stats, float* __restrict__ y) {
+  const int n = blockIdx.y, cpg = C / G, c4n = C >> 2;
+  const unsigned per = (unsigned)rows * (unsigned)c4n;
+  const float4* xp = reinterpret_cast<const float4*>(x + (size_t)n * rows * C);
+  float4* yp = reinterpret_cast<float4*>(y + (size_t)n * rows * C);
+  const float* st = stats + (size_t)n * G * 2;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < per; e += gridDim.x * blockDim.x) {
+    const int c = (int)(e % (unsigned)c4n) * 4;
+    const float4 v = __ldg(xp + e);
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c)), bt = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float in[4] = {v.x, v.y, v.z, v.w}, g4[4] = {gm.x, gm.y, gm.z, gm.w}, b4[4] = {bt.x, bt.y, bt.z, bt.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* sg = st + ((c + j) / cpg) * 2;
+      o[j] = fmaxf((in[j] - sg[0]) * sg[1] * g4[j] + b4[j], 0.f);
+    }
+    yp[e] = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
 // pass 1 of backward: per-channel sums (dgamma, dbeta) and per-(n,g) sums of dxhat and dxhat*xhat
 __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                            const float* __restrict__ dy, int rows, int C, int G,
-                                                           const float* __restrict__ gamma,
+                                                           int rows_per_block, const float* __restrict__ gamma,
                                                            const float* __restrict__ stats, float* __restrict__ dgamma,
                                                            float* __restrict__ dbeta, double* __restrict__ acc) {
-  __shared__ double gs[GN_MAXG][2];
-  const int n = blockIdx.y;
-  const int r0 = blockIdx.x * GN_ROWS, r1 = min(rows, r0 + GN_ROWS);
-  const int cpg = C / G;
-  if (threadIdx.x < GN_MAXG) { gs[threadIdx.x][0] = 0.0; gs[threadIdx.x][1] = 0.0; }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float mean = stats[((size_t)n * G + g) * 2], rstd = stats[((size_t)n * G + g) * 2 + 1];
-    float sb = 0.f, sg = 0.f;
-    const size_t off = ((size_t)n * rows) * C + c;
-    for (int r = r0; r < r1; ++r) {
-      const size_t e = off + (size_t)r * C;
-      const float gy = (y[e] > 0.f) ? dy[e] : 0.f;
-      const float xh = (x[e] - mean) * rstd;
-      sb += gy; sg = fmaf(gy, xh, sg);
+  __shared__ float red[2][1024];
+  const int n = blockIdx.y, cpr = C >> 2, rslots = min(256 / cpr, 32), cpg = C / G;
+  const int rs = threadIdx.x / cpr, c4 = threadIdx.x % cpr;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  if (rs < rslots) {
+    float mean[4], rstd[4], sb[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t g = (size_t)n * G + (c4 * 4 + j) / cpg;
+      mean[j] = stats[g * 2]; rstd[j] = stats[g * 2 + 1];
     }
-    atomicAdd(dbeta + c, sb);
-    atomicAdd(dgamma + c, sg);
+    const size_t base = (size_t)n * rows * C;
+    const float4* xp = reinterpret_cast<const float4*>(x + base) + c4;
+    const float4* yp = reinterpret_cast<const float4*>(y + base) + c4;
+    const float4* dp = reinterpret_cast<const float4*>(dy + base) + c4;
+    for (int r = r0 + rs; r < r1; r += rslots) {
+      const float4 xv = __ldg(xp + (size_t)r * cpr), yv = __ldg(yp + (size_t)r * cpr), dv = __ldg(dp + (size_t)r * cpr);
+      const float xi[4] = {xv.x, xv.y, xv.z, xv.w}, yi[4] = {yv.x, yv.y, yv.z, yv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gy = (yi[j] > 0.f) ? di[j] : 0.f;
+        sb[j] += gy;
+        sg[j] = fmaf(gy, (xi[j] - mean[j]) * rstd[j], sg[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[0][rs * C + c4 * 4 + j] = sb[j]; red[1][rs * C + c4 * 4 + j] = sg[j]; }
+  }
+  __syncthreads();
+  // per-channel totals of the block: dbeta / dgamma, and (kept in red[.][c]) the inputs of the group sums
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float b = 0.f, g = 0.f;
+    for (int k = 0; k < rslots; ++k) { b += red[0][k * C + c]; g += red[1][k * C + c]; }
+    atomicAdd(dbeta + c, b);
+    atomicAdd(dgamma + c, g);
     const float gm = __ldg(gamma + c);
-    atomicAdd(&gs[g][0], (double)(gm * sb));
-    atomicAdd(&gs[g][1], (double)(gm * sg));
+    red[0][c] = gm * b; red[1][c] = gm * g;            // slot k = 0 is only read by this thread above
   }
   __syncthreads();
   if (threadIdx.x < G) {
-    atomicAdd(acc + ((size_t)n * G + threadIdx.x) * 2 + 0, gs[threadIdx.x][0]);
-    atomicAdd(acc + ((size_t)n * G + threadIdx.x) * 2 + 1, gs[threadIdx.x][1]);
+    double d0 = 0.0, d1 = 0.0;
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { d0 += (double)red[0][c]; d1 += (double)red[1][c]; }
+    atomicAdd(acc + ((size_t)n * G + threadIdx.x) * 2 + 0, d0);
+    atomicAdd(acc + ((size_t)n * G + threadIdx.x) * 2 + 1, d1);
   }
 }
 
-__global__ void gn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                                    const float* __restrict__ dy, long long total, int rows, int C, int G,
-                                    const float* __restrict__ gamma, const float* __restrict__ stats,
-                                    const double* __restrict__ acc, double inv_cnt, float* __restrict__ dx,
-                                    int accumulate) {
-  const int cpg = C / G;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const int n = (int)(i / ((long long)rows * C));
-    const size_t sg = (size_t)n * G + c / cpg;
-    const float mean = stats[sg * 2], rstd = stats[sg * 2 + 1];
-    const float m1 = (float)(acc[sg * 2] * inv_cnt), m2 = (float)(acc[sg * 2 + 1] * inv_cnt);
-    const float gy = (y[i] > 0.f) ? dy[i] : 0.f;
-    const float xh = (x[i] - mean) * rstd;
-    const float d = rstd * (__ldg(gamma + c) * gy - m1 - xh * m2);
-    dx[i] = accumulate ? dx[i] + d : d;
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                           const float* __restrict__ dy, int rows, int C, int G,
+                                                           const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                           const double* __restrict__ acc, double inv_cnt,
+                                                           float* __restrict__ dx, int accumulate) {
+  const int n = blockIdx.y, cpg = C / G, c4n = C >> 2;
+  const unsigned per = (unsigned)rows * (unsigned)c4n;
+  const size_t base = (size_t)n * rows * C;
+  const float4* xp = reinterpret_cast<const float4*>(x + base);
+  const float4* yp = reinterpret_cast<const float4*>(y + base);
+  const float4* dyp = reinterpret_cast<const float4*>(dy + base);
+  float4* dxp = reinterpret_cast<float4*>(dx + base);
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < per; e += gridDim.x * blockDim.x) {
+    const int c = (int)(e % (unsigned)c4n) * 4;
+    const float4 xv = __ldg(xp + e), yv = __ldg(yp + e), dv = __ldg(dyp + e);
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float xi[4] = {xv.x, xv.y, xv.z, xv.w}, yi[4] = {yv.x, yv.y, yv.z, yv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w};
+    const float g4[4] = {gm.x, gm.y, gm.z, gm.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t sg = (size_t)n * G + (c + j) / cpg;
+      const float mean = stats[sg * 2], rstd = stats[sg * 2 + 1];
+      const float m1 = (float)(acc[sg * 2] * inv_cnt), m2 = (float)(acc[sg * 2 + 1] * inv_cnt);
+      const float gy = (yi[j] > 0.f) ? di[j] : 0.f;
+      const float xh = (xi[j] - mean) * rstd;
+      o[j] = rstd * (g4[j] * gy - m1 - xh * m2);
+    }
+    if (accumulate) {
+      const float4 p = dxp[e];
+      o[0] += p.x; o[1] += p.y; o[2] += p.z; o[3] += p.w;
+    }
+    dxp[e] = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -123,6 +171,7 @@ using namespace cape;
 static int gn_check(cape_topology* t, int N, int rows, int C, int G) {
   CAPE_REQUIRE(t, "null handle");
   CAPE_REQUIRE(N > 0 && rows > 0 && C > 0 && G > 0 && G <= GN_MAXG && C % G == 0, "bad group-norm shape");
+  CAPE_REQUIRE(C % 4 == 0 && C <= 1024, "group norm needs C % 4 == 0 (float4 rows) and C <= 1024");
   CAPE_REQUIRE((int64_t)N * G * 2 * (int64_t)sizeof(double) <= t->workspace_bytes, "workspace too small for group norm");
   CAPE_REQUIRE(N <= 65535, "batch too large");
   return 0;
@@ -136,17 +185,19 @@ extern "C" int cape_gn_relu_fwd(cape_topology* t, const float* x, int N, int row
   double* acc = (double*)t->workspace;
   CAPE_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)N * G * 2 * sizeof(double), st));
   dim3 grid((rows + GN_ROWS - 1) / GN_ROWS, N);
-  gn_stats_kernel<<<grid, 256, 0, st>>>(x, rows, C, G, acc);
+  gn_stats_kernel<<<grid, 256, 0, st>>>(x, rows, C, G, GN_ROWS, acc);
   CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
   const double inv_cnt = 1.0 / ((double)rows * (C / G));
   gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, st>>>(acc, N * G, inv_cnt, eps, stats);
   CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
-  const long long total = (long long)N * rows * C;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  gn_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, total, rows, C, G, gamma, beta, stats, y);
+  {
+    long long bx = ((long long)rows * (C / 4) + 255) / 256;
+    const long long cap = (148LL * 16 + N - 1) / N;
+    if (bx > cap) bx = cap;
+    gn_apply_kernel<<<dim3((unsigned)bx, (unsigned)N), 256, 0, st>>>(x, rows, C, G, gamma, beta, stats, y);
+  }
   CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
   return 0;
@@ -161,14 +212,17 @@ extern "C" int cape_gn_relu_bwd(cape_topology* t, const float* x, const float* y
   double* acc = (double*)t->workspace;
   CAPE_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)N * G * 2 * sizeof(double), st));
   dim3 grid((rows + GN_ROWS - 1) / GN_ROWS, N);
-  gn_bwd_stats_kernel<<<grid, 256, 0, st>>>(x, y, dy, rows, C, G, gamma, stats, dgamma, dbeta, acc);
+  gn_bwd_stats_kernel<<<grid, 256, 0, st>>>(x, y, dy, rows, C, G, GN_ROWS, gamma, stats, dgamma, dbeta, acc);
   CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
   const double inv_cnt = 1.0 / ((double)rows * (C / G));
-  const long long total = (long long)N * rows * C;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  gn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, dy, total, rows, C, G, gamma, stats, acc, inv_cnt, dx, accumulate_dx);
+  {
+    long long bx = ((long long)rows * (C / 4) + 255) / 256;
+    const long long cap = (148LL * 16 + N - 1) / N;
+    if (bx > cap) bx = cap;
+    gn_bwd_apply_kernel<<<dim3((unsigned)bx, (unsigned)N), 256, 0, st>>>(x, y, dy, rows, C, G, gamma, stats, acc, inv_cnt, dx,
+                                                                         accumulate_dx);
+  }
   CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
   return 0;

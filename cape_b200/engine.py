@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from . import topology as topo
 from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, EPI_AFFINE, EPI_DUALMASK, EPI_LINEAR, EPI_SLOPE, ApplyArgs, ConvArgs,
-                   DwArgs, WPrep, check)
+                   DwArgs, GemmItem, WPrep, check)
 
 LEAKY_ALPHA = 0.2  # tf.nn.leaky_relu default (lib/models.py:109,506,582)
 
@@ -138,19 +138,7 @@ class ConvSite:
 # ---------------------------------------------------------------------------------------------------
 def gemm(tp, A, B, Cout, bias=None, act=ACT_NONE, alpha=1.0, beta=0.0, tag=None):
     """Cout = act(alpha * A @ B + bias) + beta * Cout for 2-D (possibly transposed) views."""
-    M, K = A.shape
-    K2, N = B.shape
-    assert K == K2 and tuple(Cout.shape) == (M, N) and (Cout.stride(1) == 1 or N == 1)
-    a_rs, a_cs = A.stride()
-    b_rs, b_cs = B.stride()
-    if K == 1:          # degenerate dims: strides of size-1 axes are arbitrary in torch
-        a_cs = 1
-        if b_cs != 1:
-            b_rs = 1
-    if M == 1 and a_cs != 1:
-        a_rs = 1
-    if N == 1 and b_rs != 1:
-        b_cs = 1
+    M, N, K, a_rs, a_cs, b_rs, b_cs = _gemm_strides(A, B, Cout)
     with _Prof("gemm", tag):
         check(tp.lib.cape_gemm(tp.h, M, N, K, _ptr(_f32(A)), a_rs, a_cs, _ptr(_f32(B)), b_rs, b_cs, _ptr(_f32(Cout)),
                                Cout.stride(0), _ptr(bias), act, LEAKY_ALPHA, alpha, beta, _stream()))
@@ -250,6 +238,56 @@ class WeightPrep:
             self.table = torch.from_numpy(raw).to(self.tp.device)
             torch.cuda.synchronize()
         check(self.tp.lib.cape_weight_prep(C.c_void_p(self.table.data_ptr()), len(self.items), 16, _stream()))
+
+
+def _gemm_strides(A, B, Cout):
+    M, K = A.shape
+    K2, N = B.shape
+    assert K == K2 and tuple(Cout.shape) == (M, N) and (Cout.stride(1) == 1 or N == 1)
+    a_rs, a_cs = A.stride()
+    b_rs, b_cs = B.stride()
+    if K == 1:          # degenerate dims: strides of size-1 axes are arbitrary in torch
+        a_cs = 1
+        if b_cs != 1:
+            b_rs = 1
+    if M == 1 and a_cs != 1:
+        a_rs = 1
+    if N == 1 and b_rs != 1:
+        b_cs = 1
+    return M, N, K, a_rs, a_cs, b_rs, b_cs
+
+
+class SmallGemmBatch:
+    """The tiny products of a training step (bias gradients, condition-channel gradients: ~80 per step, each a few
+    microseconds of launch overhead) collected and issued as ONE launch (cape_gemm_batch).  `add` defers, `flush`
+    launches; beta = 1 items accumulate atomically, so several may add into the same buffer.  The step's schedule is
+    static: the device table of a schedule is built the first time it is seen (outside CUDA-graph capture)."""
+
+    def __init__(self, tp):
+        self.tp, self.pending, self.tables = tp, [], {}
+        self.item_bytes = int(tp.lib.cape_gemm_item_bytes())
+
+    def add(self, A, B, Cout, alpha=1.0, beta=0.0):
+        M, N, K, a_rs, a_cs, b_rs, b_cs = _gemm_strides(A, B, Cout)
+        self.pending.append((_f32(A).data_ptr(), a_rs, a_cs, _f32(B).data_ptr(), b_rs, b_cs, _f32(Cout).data_ptr(),
+                             Cout.stride(0), M, N, K, float(alpha), float(beta)))
+
+    def flush(self):
+        if not self.pending:
+            return
+        key = tuple(self.pending)
+        n = len(key)
+        tab = self.tables.get(key)
+        if tab is None:
+            arr = (GemmItem * n)()
+            for d, it in zip(arr, key):
+                (d.a, d.a_rs, d.a_cs, d.b, d.b_rs, d.b_cs, d.c, d.c_rs, d.M, d.N, d.K, d.alpha, d.beta) = it
+            tab = torch.empty(n * self.item_bytes, dtype=torch.uint8, device=self.tp.device)
+            torch.cuda.synchronize()
+            check(self.tp.lib.cape_gemm_batch(C.cast(arr, C.c_void_p), n, C.c_void_p(tab.data_ptr()), 0, _stream()))
+            self.tables[key] = tab
+        check(self.tp.lib.cape_gemm_batch(None, n, C.c_void_p(tab.data_ptr()), 4, _stream()))
+        self.pending = []
 
 
 def tensor_cores_enabled(tp):

@@ -342,24 +342,25 @@ class ChebLayer:
             else:
                 for o in range(0, nops, 4):
                     self._colsum_chunk(g, N, cs, o)
+            sg = self.net.small.add                  # tiny products: deferred, one launch per step (SmallGemmBatch)
             if has_bias:
-                gemm(tp, self.net.ones[:, :N], cs[:, 0, :], self.gbias.view(1, Fout))
+                sg(self.net.ones[:, :N], cs[:, 0, :], self.gbias.view(1, Fout))
             if C:
                 for k in range(K):
                     dq = cs[:, self.cs_cond0 + k, :]
                     if want_dw:
-                        gemm(tp, ycat.t(), dq, self.gW3[F:, k, :])
+                        sg(ycat.t(), dq, self.gW3[F:, k, :])
                     if dycat is not None:
-                        gemm(tp, dq, self.W3[F:, k, :].t(), dycat, beta=1.0)
+                        sg(dq, self.W3[F:, k, :].t(), dycat, beta=1.0)
         if self.affine and C:
             csa = self.net.arena.get(self.csa_id)[:N]
             colsum(tp, g_aff, N, s.rows_out, Fout, [s.ops[0]], csa)
             if want_dw:
-                gemm(tp, ycat.t(), csa[:, 0, :], self.gWa2[F:])
+                self.net.small.add(ycat.t(), csa[:, 0, :], self.gWa2[F:])
             if dycat is not None:
-                gemm(tp, csa[:, 0, :], self.Wa2[F:].t(), dycat, beta=1.0)
+                self.net.small.add(csa[:, 0, :], self.Wa2[F:].t(), dycat, beta=1.0)
         if self.bias_per_row and want_dw:
-            gemm(tp, self.net.ones[:, :N], g.view(N, s.rows_out * Fout), self.gbias.view(1, s.rows_out * Fout))
+            self.net.small.add(self.net.ones[:, :N], g.view(N, s.rows_out * Fout), self.gbias.view(1, s.rows_out * Fout))
         if dx is not None:
             assert self.need_dx
             gs = want_dw and mode == "gside"
@@ -571,6 +572,7 @@ class CapeNetwork:
         # Weight gradients on plain tensors (stashes) depend on nothing but their layer's operands, so they run on a
         # second stream next to the data-gradient chain and fill the ramp-up / tail bubbles of its kernels.  They get
         # a handle of their own (no operators, its own split-K workspace).
+        self.dp = None                      # set_data_parallel(): bucketed gradient all-reduce inside the step
         self.async_dw = os.environ.get("CAPE_ASYNC_DW", "1") != "0"
         self.tp_dw = Topology(device) if self.async_dw else tp
         self.dw_stream = torch.cuda.Stream(device=dev) if self.async_dw else None
@@ -590,6 +592,7 @@ class CapeNetwork:
         self.PD.load(vals)
         self.arena = Arena()
         self.wprep = E.WeightPrep(tp)
+        self.small = E.SmallGemmBatch(tp)
         self._scratch_need = 4
         self.ones = torch.ones(1, 2 * N, device=dev)
         w, g = self._w, self._g
@@ -948,6 +951,8 @@ class CapeNetwork:
         gflat = self.g_enc_red.view(N, self.flat)
         self.fc_mean.bwd(flat, self.z_mean, self.g_mean, dx=gflat)
         self.fc_var.bwd(flat, self.z_logvar, self.g_logvar, dx=gflat, dx_beta=1.0)
+        self._fc_reg(("generator/encoder/fc_mean", "generator/encoder/fc_var"))
+        self._reduce_bucket("enc_fc")                       # 28 MB of gradients are final: all-reduce behind the conv backward
         self.enc_1x1.bwd(self.enc_act[-1], None, self.g_enc_red, dx=self.g_enc[-1], dx_epi=EPI_SLOPE,
                          dx_aux=self.enc_act[-1])
         for i in range(len(self.enc) - 1, 0, -1):
@@ -1031,20 +1036,60 @@ class CapeNetwork:
                                          E._ptr(self.z_mean), E._ptr(self.z_logvar), self.nz, E._ptr(self.d_xhat),
                                          E._ptr(L), st()))
         self.decoder_bwd()
+        self._fc_reg(("generator/decoder/fc1",))
+        self.small.flush()            # bias / condition-channel gradients of the decoder and discriminator layers
+        self._reduce_bucket("dec")    # decoder (+ discriminator) gradients are final: all-reduce behind the encoder backward
         self.encoder_bwd()
+        self.small.flush()            # encoder bias gradients; d_ycat is complete after the first flush
         self.cond_bwd()
         self.join_dw()
-        # fc L2 regularisation: regularization * sum(l2_regularizer(regularization)(W)) -> grad reg^2 * W (models.py:378)
-        r2 = float(c["regularization"]) ** 2
-        if r2 > 0:
-            for n in ("generator/encoder/fc_mean", "generator/encoder/fc_var", "generator/decoder/fc1"):
-                axpy(tp, self._g(n + "/dense/kernel"), self._w(n + "/dense/kernel"), r2)
         if self.ref_compat:
             self.PD.grad.copy_(self.PD.flat)          # models.py:466: the D "gradients" are its variables
         if not c["optim_condnet"]:                    # models.py:455-458: condition nets excluded from vars_g
             for n in self.PG.names:
                 if not n.startswith("generator"):
                     self.PG.g(n).zero_()
+        self._reduce_bucket("rest")
+        if self.dp is not None:
+            torch.cuda.current_stream().wait_stream(self.dp["stream"])
+
+    def _fc_reg(self, names):
+        """fc L2 regularisation: regularization * sum(l2_regularizer(regularization)(W)) -> grad reg^2 * W (models.py:378)"""
+        r2 = float(self.cfg["regularization"]) ** 2
+        if r2 > 0:
+            for n in names:
+                axpy(self.tp, self._g(n + "/dense/kernel"), self._w(n + "/dense/kernel"), r2)
+
+    # ---- data parallelism: bucketed gradient all-reduce overlapped with the backward pass -------------------------
+    def set_data_parallel(self, world):
+        """One process per GPU, batch sharded.  The flat generator gradient buffer is all-reduced in three
+        buckets as soon as each is final -- decoder (+ the discriminator's buffer) after the decoder backward, the two
+        28 MB encoder FC kernels right after their weight gradients, the encoder convs / condition nets at the end --
+        on a communication stream that the backward pass does not wait for until its very end; the NCCL calls sit inside
+        the captured forward/backward graph.  world <= 1 switches it off."""
+        if world <= 1:
+            self.dp = None
+            return
+        P = self.PG
+        names = P.names
+        fc0 = P.offsets["generator/encoder/fc_mean/dense/kernel"]
+        dec0 = P.offsets[next(n for n in names if n.startswith("generator/decoder"))]
+        assert fc0 < dec0 and all(P.offsets[n] >= dec0 for n in names if n.startswith("generator/decoder"))
+        self.dp = dict(world=world, stream=torch.cuda.Stream(device=self.device),
+                       buckets={"dec": [P.grad[dec0:]] + ([] if self.ref_compat else [self.PD.grad]),
+                                "enc_fc": [P.grad[fc0:dec0]], "rest": [P.grad[:fc0]]})
+
+    def _reduce_bucket(self, which):
+        if self.dp is None:
+            return
+        import torch.distributed as dist
+        comm = self.dp["stream"]
+        comm.wait_stream(torch.cuda.current_stream())
+        if self._dw_pending:
+            comm.wait_stream(self.dw_stream)          # weight gradients of the bucket still running on the side stream
+        with torch.cuda.stream(comm):
+            for b in self.dp["buckets"][which]:
+                dist.all_reduce(b, op=dist.ReduceOp.AVG)
 
     def enqueue_update(self):
         """clip_by_global_norm(5.0) + MomentumOptimizer for both players (models.py:460-467) + weight re-layouts.
@@ -1095,7 +1140,7 @@ class CapeNetwork:
             self.graph_fb.replay()
         else:
             self.enqueue_fwd_bwd()
-        if allreduce is not None:
+        if allreduce is not None and self.dp is None:
             allreduce(self.PG.grad, self.PD.grad)
         if update:
             if use_graph:

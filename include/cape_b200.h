@@ -209,6 +209,21 @@ int cape_gemm(cape_topology* t, int M, int N, int K,
               float* c, int64_t c_rs,
               const float* bias, int act, float leaky_alpha, float alpha, float beta, void* stream);
 
+/* Many small products in ONE launch: C_i = alpha_i * A_i.B_i (beta_i = 0) or C_i += alpha_i * A_i.B_i (beta_i = 1:
+ * atomic, several items may add into the same C).  The bias / condition-channel gradients of a training step are ~80
+ * products of [64 x 64]-sized operands; the step's schedule is static, so the caller collects them, builds the device
+ * table once (items_host != NULL: synchronous upload into table_device, n * cape_gemm_item_bytes() bytes) and from then
+ * on launches it with items_host == NULL. */
+typedef struct {
+  const float* a; int64_t a_rs, a_cs;
+  const float* b; int64_t b_rs, b_cs;
+  float* c; int64_t c_rs;
+  int M, N, K;
+  float alpha, beta;
+} cape_gemm_item;
+int cape_gemm_batch(const cape_gemm_item* items_host, int n, void* table_device, int blocks_per_item, void* stream);
+int cape_gemm_item_bytes(void);
+
 /* Stand-alone mesh resampling y[n, :, :F] = S x[n, :, :F] (poolwT, lib/models.py:129-152) for an operator registered
  * in the topology (D: row selection, U: 3-tap barycentric; op < 0: identity copy); rows of x / y are x_stride /
  * y_stride floats apart.  If cond != NULL the condition channels of the reference's concat-then-unpool are written

@@ -47,6 +47,7 @@ def test_struct_layout_matches_header():
     assert fields("cape_term") == [f[0] for f in _lib.Term._fields_]
     assert fields("cape_conv_args") == [f[0] for f in _lib.ConvArgs._fields_]
     assert fields("cape_dw_args") == [f[0] for f in _lib.DwArgs._fields_]
+    assert fields("cape_gemm_item") == [f[0] for f in _lib.GemmItem._fields_]
     assert fields("cape_wprep") == [f[0] for f in _lib.WPrep._fields_]
     assert fields("cape_apply_term") == [f[0] for f in _lib.ApplyTerm._fields_]
     assert fields("cape_apply_args") == [f[0] for f in _lib.ApplyArgs._fields_]

@@ -1,0 +1,85 @@
+"""Data parallelism on real GPUs (skipped with fewer than two): the bucketed, overlapped NCCL all-reduce inside the
+step (CapeNetwork.set_data_parallel) gives every rank the gradients of the GLOBAL batch."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, use_graph, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), NCCL_DEBUG="WARN")
+    import parity
+    from cape_b200 import distributed as DP
+    from cape_b200 import topology as T
+    from cape_b200.network import CapeNetwork
+    from cape_b200.params import NZ64_AFFINE, param_specs
+    from cape_b200.synthetic import make_batch
+    DP.init("nccl")
+    L, D, U, p, L_d, D_d, _ = T.load_graph_mtx(load_for_demo=True)
+    cfg = dict(NZ64_AFFINE, decay_steps=10)
+    specs = param_specs(cfg, [l.shape[0] for l in L], [l.shape[0] for l in L_d])
+    params = parity.calibrated_params(specs, 3)
+    N = 2
+    order = ("x_g", "cond_g", "cond2_g", "eps", "x_d", "cond_d", "cond2_d")
+    full = make_batch(N * world, cfg["nz"], seed=77)
+    mine = [torch.from_numpy(full[k][rank * N:(rank + 1) * N]) for k in order]
+    net = CapeNetwork(L, D, U, L_d, D_d, cfg, N, device=rank, params=params)
+    net.set_data_parallel(world)
+    net.set_inputs(*mine)
+    if use_graph:
+        net.train_step(step=100, update=False)
+        torch.cuda.synchronize()
+        net.capture_graphs()
+    net.train_step(step=100, use_graph=use_graph)
+    torch.cuda.synchronize()
+    out = {"gg": net.PG.grad.cpu().numpy(), "gd": net.PD.grad.cpu().numpy(), "pg": net.PG.flat.cpu().numpy()}
+    if rank == 0:
+        # the same global batch on one GPU, no data parallelism
+        ref = CapeNetwork(L, D, U, L_d, D_d, cfg, N * world, device=0, params=params)
+        ref.set_inputs(*[torch.from_numpy(full[k]) for k in order])
+        ref.train_step(step=100)
+        torch.cuda.synchronize()
+        out.update(ref_gg=ref.PG.grad.cpu().numpy(), ref_gd=ref.PD.grad.cpu().numpy(), ref_pg=ref.PG.flat.cpu().numpy())
+    q.put((rank, out))
+    import torch.distributed as dist
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_overlapped_allreduce_equals_global_batch(use_graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, use_graph, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    r0, r1 = res[0], res[1]
+    assert np.array_equal(r0["gg"], r1["gg"]) and np.array_equal(r0["pg"], r1["pg"])     # replicas stay identical
+    assert rel(r0["gg"], r0["ref_gg"]) < 2e-5 and rel(r0["gd"], r0["ref_gd"]) < 2e-5
+    assert rel(r0["pg"], r0["ref_pg"]) < 1e-6
