@@ -360,18 +360,24 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
             for (int j = 0; j < 4; ++j) axn[j] = ldg4(p.aux + orow + c0 + 16 + 4 * j);
           }
         }
-        tmem_ld16(taddr_row + (uint32_t)c0, v0);
         if (PRECISE) {
-          // precise mode: the main chains and the correction accumulator are added here, in fp32 with round-to-nearest
-          float vc[16];
-          for (int ch = 1; ch < nused; ++ch) {
-            tmem_ld16(taddr_row + (uint32_t)(ch * g.gw + c0), vc);
+          // precise mode: the main chains and the correction accumulator are added here, in fp32 with round-to-nearest;
+          // all four TMEM loads are in flight before the one wait
+          uint32_t r0[16], r1[16], r2[16], r3[16];
+          tmem_ld16_async(taddr_row + (uint32_t)c0, r0);
+          if (nused > 1) tmem_ld16_async(taddr_row + (uint32_t)(g.gw + c0), r1);
+          if (nused > 2) tmem_ld16_async(taddr_row + (uint32_t)(2 * g.gw + c0), r2);
+          tmem_ld16_async(taddr_row + (uint32_t)(3 * g.gw + c0), r3);
+          tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v0[j] += vc[j];
+          for (int j = 0; j < 16; ++j) {
+            float v = __uint_as_float(r0[j]);
+            if (nused > 1) v += __uint_as_float(r1[j]);
+            if (nused > 2) v += __uint_as_float(r2[j]);
+            v0[j] = v + __uint_as_float(r3[j]);
           }
-          tmem_ld16(taddr_row + (uint32_t)(3 * g.gw + c0), vc);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v0[j] += vc[j];
+        } else {
+          tmem_ld16(taddr_row + (uint32_t)c0, v0);
         }
         if (!valid) continue;
         for (int slot = 0; slot < p.nslots; ++slot) {

@@ -178,13 +178,20 @@ class ChebLayer:
         split_ok = not thin and not plain and F % 16 == 0 and Fout % 16 == 0 and F >= 32 and Fout >= 32
         self.fwd_mode, self.dx_mode = "fused", "fused"
         if split_ok:
-            if C == 0 and not self.affine and self.dw_mode == "aside":
+            # Defaults from the per-layer measurements at batch 64 (profiles/r02_launch_profile.csv):
+            #  * forward: basis-first where the short-chain accumulation is wanted (it needs plain operands: the
+            #    encoder), contract-first for un-pooling layers (half the rows in the contraction, Fout-wide gathers:
+            #    dec/aff3 420 -> 265 us), fused elsewhere (discriminator: three gathers + a contraction lose to one kernel);
+            #  * data gradient: contract-first when the gradient narrows (Fout > F: the gathers run on the narrow side)
+            #    or the layer pools and is at least 128 wide (the contraction runs on half the rows: disc/conv3
+            #    495 -> 333 us); basis-first (op^T G by cape_apply, then a plain contraction) measured slower than the
+            #    fused kernel on every decoder layer but one, so it is opt-in.
+            if self.precise and C == 0 and not self.affine and self.dw_mode == "aside":
                 self.fwd_mode = "basis"
             elif (C > 0 or self.affine) and site.rows_in < site.rows_out:
                 self.fwd_mode = "contract"
-            if need_dx and self.dw_mode == "gside":
-                self.dx_mode = "basis"
-            elif need_dx and self.dw_mode == "aside":
+            if need_dx and self.dw_mode == "aside" and K * F <= 512 and (
+                    Fout > F or (site.rows_out < site.rows_in and Fout == F and F >= 128)):
                 self.dx_mode = "contract"
         # experiment overrides: CAPE_FWD_MODE / CAPE_DX_MODE for every layer, CAPE_MODES="enc/conv8:fwd=fused,disc/conv3:dx=contract"
         # for single ones (ineligible requests are ignored)
