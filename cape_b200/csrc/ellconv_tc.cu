@@ -30,10 +30,6 @@ constexpr int QS_FLOATS = 4096;
 constexpr int MAX_STAGES = 4;
 using namespace tc;     // mbarriers, fences, UMMA issue, TMEM loads, TMA loads (tc_common.cuh)
 
-__device__ __forceinline__ void split_store_m(int rn, float4 v, char* hi, char* lo, uint32_t off) {
-  if (rn) split_store_rn(v, hi, lo, off); else split_store(v, hi, lo, off);
-}
-
 // K-major, SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor, sm100 "version 1"):
 // start address >> 4 | LBO(ignored for swizzled K-major)=1 | SBO = 1024 B (8 rows x 128 B) | layout_type = 2.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
@@ -201,8 +197,8 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
                   if (rn[i + 1] >= 0) *reinterpret_cast<float4*>(tm.stash + (size_t)(row0 + row_b) * tm.stash_stride + f) = vb;
                 }
               }
-              split_store_m(p.split_rn, va, a_hi, a_lo, (uint32_t)(row_a * 128 + ((l8 ^ (row_a & 7)) << 4)));
-              split_store_m(p.split_rn, vb, a_hi, a_lo, (uint32_t)(row_b * 128 + ((l8 ^ (row_b & 7)) << 4)));
+              split_store(va, a_hi, a_lo, (uint32_t)(row_a * 128 + ((l8 ^ (row_a & 7)) << 4)));
+              split_store(vb, a_hi, a_lo, (uint32_t)(row_b * 128 + ((l8 ^ (row_b & 7)) << 4)));
             }
             fence_proxy_async();             // generic-proxy smem writes -> visible to the tensor-core (async) proxy
             __syncwarp();
@@ -220,9 +216,9 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
             for (int i = 0; i < BN / 32; ++i) {
               const int cl = rs + 32 * i;
               const uint32_t off = (uint32_t)(cl * 128 + ((l8 ^ (cl & 7)) << 4));
-              split_store_m(p.split_rn, bw[i], b_hi, b_lo, off);
+              split_store(bw[i], b_hi, b_lo, off);
               if (DUAL) {
-                if (has2) split_store_m(p.split_rn, bw2[i], b_lo + Cfg::B_TILE_BYTES, b_lo + 2 * Cfg::B_TILE_BYTES, off);
+                if (has2) split_store(bw2[i], b_lo + Cfg::B_TILE_BYTES, b_lo + 2 * Cfg::B_TILE_BYTES, off);
               }
             }
             fence_proxy_async();
@@ -268,7 +264,6 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
                 umma_tf32(d0, a_hi + adv, b_hi + adv, idesc, ks == 0 ? acc0_on : 1u);
                 umma_tf32(d0, a_lo + adv, b_hi + adv, idesc, 1);
                 umma_tf32(d0, a_hi + adv, b_lo + adv, idesc, 1);
-                if (p.split_rn == 2) umma_tf32(d0, a_lo + adv, b_lo + adv, idesc, 1);   // experiment: 4th term
                 if (has2) {
                   umma_tf32(d1, a_hi + adv, b2_hi + adv, idesc, ks == 0 ? acc1_on : 1u);
                   umma_tf32(d1, a_lo + adv, b2_hi + adv, idesc, 1);
@@ -625,8 +620,8 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 2) ellconv_tc2_kernel(const _
                 if (n_b >= 0) *reinterpret_cast<float4*>(tm.stash + (size_t)(row0 + row_b) * tm.stash_stride + f) = vb;
               }
             }
-            split_store_m(p.split_rn, va, a_hi, a_lo, (uint32_t)(row_a * 128 + ((l8 ^ (row_a & 7)) << 4)));
-            split_store_m(p.split_rn, vb, a_hi, a_lo, (uint32_t)(row_b * 128 + ((l8 ^ (row_b & 7)) << 4)));
+            split_store(va, a_hi, a_lo, (uint32_t)(row_a * 128 + ((l8 ^ (row_a & 7)) << 4)));
+            split_store(vb, a_hi, a_lo, (uint32_t)(row_b * 128 + ((l8 ^ (row_b & 7)) << 4)));
           }
           fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
           __syncwarp();
@@ -645,12 +640,12 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 2) ellconv_tc2_kernel(const _
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c < p.ncols && f < tm.F) v = ldg4(tm.wT + (size_t)c * tm.wT_stride + f);
             const uint32_t off = (uint32_t)(cl * 128 + ((l8 ^ (cl & 7)) << 4));
-            split_store_m(p.split_rn, v, b_hi, b_lo, off);
+            split_store(v, b_hi, b_lo, off);
             if (DUAL) {
               if (has2) {
                 float4 v2 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (c < p.ncols && f < tm.F) v2 = ldg4(tm.w2T + (size_t)c * tm.w2T_stride + f);
-                split_store_m(p.split_rn, v2, b_lo + Cfg::B_TILE_BYTES, b_lo + 2 * Cfg::B_TILE_BYTES, off);
+                split_store(v2, b_lo + Cfg::B_TILE_BYTES, b_lo + 2 * Cfg::B_TILE_BYTES, off);
               }
             }
           }
@@ -823,7 +818,6 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 2) ellconv_tc2_kernel(const _
               umma_tf32(d0, a_hi + adv, b_hi + adv, idesc, ks == 0 ? acc0_on : 1u);
               umma_tf32(d0, a_lo + adv, b_hi + adv, idesc, 1);
               umma_tf32(d0, a_hi + adv, b_lo + adv, idesc, 1);
-              if (p.split_rn == 2) umma_tf32(d0, a_lo + adv, b_lo + adv, idesc, 1);     // experiment: 4th term
               if (has2) {
                 umma_tf32(d1, a_hi + adv, b2_hi + adv, idesc, ks == 0 ? acc1_on : 1u);
                 umma_tf32(d1, a_lo + adv, b2_hi + adv, idesc, 1);
