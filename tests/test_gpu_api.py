@@ -295,5 +295,9 @@ def test_prefetched_inputs_equal_direct_inputs(hierarchy):
         return np.stack(out)
 
     a, b = run(False), run(True)
-    assert np.isfinite(a).all() and np.allclose(a, b, rtol=1e-4, atol=1e-6)
+    assert np.isfinite(a).all() and np.isfinite(b).all()
+    # same weights, same batch in the first step: equal up to the order of the atomic accumulations (loss / column-sum /
+    # condition-gradient kernels); the later steps have been through updates that amplify those last bits
+    assert np.allclose(a[0], b[0], rtol=1e-5, atol=1e-7), (a[0], b[0])
+    assert np.allclose(a, b, rtol=2e-3, atol=1e-5), (a, b)
     assert not np.array_equal(a[0], a[1])                     # the two batches differ

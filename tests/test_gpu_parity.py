@@ -156,6 +156,13 @@ def test_train_step_groupnorm_decoder(hierarchy):
     _assert_all(parity.train_step(hierarchy, dict(NZ18_PLAIN, decay_steps=10), N=2))
 
 
+def test_train_step_groupnorm_decoder_many_tiles(hierarchy):
+    """The nz18 / GroupNorm model at batch 24: more 128-row tiles than SMs in every layer (persistent loops and
+    column groups of the plain-operand kernel on the 544 / 288 / 160-wide linear layers), graph-replayed."""
+    from cape_b200.params import NZ18_PLAIN
+    _assert_all(parity.train_step(hierarchy, dict(NZ18_PLAIN, decay_steps=10), N=24, use_graph=True))
+
+
 def test_size_independent_properties(hierarchy, cfg):
     """Full-size (batch 64) checks that need no oracle: linearity of the conv in x and W, batch-permutation
     equivariance of the generator, CUDA-graph replay == eager."""

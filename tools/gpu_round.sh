@@ -1,24 +1,27 @@
 #!/bin/bash
-# One GPU-box visit: parity checks, tests, bench (+ optional ncu).  Everything lands in gpurun_out/.
+# One GPU-box visit for the round's evidence: tests, the three bench configs, ncu launch list and full captures of the
+# top kernels.  Everything lands in gpurun_out/; tools/summarize_profiles.py condenses it into profiles/<tag>_*.
 mkdir -p gpurun_out
 nvidia-smi -L | head -1
-echo "== gpu_check"; timeout 900 python tests/gpu_check.py golden tc cheb step step_n5 step_gn 2>&1 | grep -v "Warn\|warn\|return torch\|out = {" > gpurun_out/gpu_check.log; grep -c FAIL gpurun_out/gpu_check.log; grep -v "param-update\|  grad " gpurun_out/gpu_check.log | tail -60; grep FAIL gpurun_out/gpu_check.log | head -30
-echo "== pytest -m gpu"; timeout 1200 python -m pytest tests -q -m gpu 2>&1 > gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log
-echo "== bench"; timeout 900 python bench.py --steps 10 --warmup 3 2> gpurun_out/bench.err | tee gpurun_out/bench.json | cut -c1-400; tail -3 gpurun_out/bench.err
-if [ -n "$AB_ENV$AB_ARGS" ]; then
-echo "== bench A/B: $AB_ENV $AB_ARGS"; env $AB_ENV timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-profile $AB_ARGS 2> gpurun_out/bench_ab.err | tee gpurun_out/bench_ab.json | cut -c1-400
+if [ "$1" != "nopytest" ]; then
+echo "== pytest -m gpu"; timeout 2400 python -m pytest tests -q -m gpu 2>&1 | tail -8 > gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
 fi
-if [ "$1" == "ncu" ]; then
-echo "== ncu launch list"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 450 -c 900 --csv --log-file gpurun_out/launches.csv \
-   python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline --no-profile > gpurun_out/ncu_bench.log 2>&1
-tail -2 gpurun_out/ncu_bench.log | cut -c1-200; wc -l gpurun_out/launches.csv
-echo "== ncu full (wide conv, narrow conv, dense dW)"
-for spec in "conv_wide:ellconv_tc_kernel:12" "conv_narrow:ellconv_tc2_kernel:20" "dw_dense:dw_dense_kernel:16"; do
-  name="${spec%%:*}"; rest="${spec#*:}"; kern="${rest%%:*}"; skip="${rest#*:}"
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kern -s $skip -c 4 -f -o gpurun_out/prof_$name \
-     python bench.py --steps 1 --warmup 0 --no-graph --no-cpu-baseline --no-profile > gpurun_out/ncu_$name.log 2>&1
-  tail -1 gpurun_out/ncu_$name.log | cut -c1-150
+for c in c3 c2 c5; do
+  echo "== bench $c"; timeout 900 python bench.py --config $c --steps 20 --warmup 5 2> gpurun_out/bench_$c.err > gpurun_out/bench_$c.json; cut -c1-260 gpurun_out/bench_$c.json
 done
-fi
-ls -la gpurun_out | head -30
+cp gpurun_out/bench_c3.json gpurun_out/bench.json; cp gpurun_out/launch_profile_c3.json gpurun_out/launch_profile.json
+echo "== reference arm (16 meshes/step sample for the record; the driver runs the full one)"
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 --batch 16 2>/dev/null | cut -c1-300 | tee gpurun_out/bench_reference_sample.json
+echo "== ncu launch list"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 500 -c 1100 --csv --log-file gpurun_out/launches.csv \
+   python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline --no-profile > gpurun_out/ncu_bench.log 2>&1
+tail -1 gpurun_out/ncu_bench.log | cut -c1-200; wc -l gpurun_out/launches.csv
+echo "== ncu full captures"
+rm -f gpurun_out/*.ncu-rep
+for spec in "gemm_tc:gemm_tc_kernel:6:6" "apply:apply_kernel:4:4" "conv_wide:ellconv_tc_kernel:6:4" "conv_narrow:ellconv_tc2_kernel:10:4" "dw_dense:dw_dense_kernel:16:4"; do
+  IFS=: read name kern skip cnt <<< "$spec"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kern -s $skip -c $cnt -f -o gpurun_out/prof_$name \
+     python bench.py --steps 1 --warmup 0 --no-graph --no-cpu-baseline --no-profile > gpurun_out/ncu_$name.log 2>&1
+  tail -1 gpurun_out/ncu_$name.log | cut -c1-120
+done
+ls -la gpurun_out | head -40

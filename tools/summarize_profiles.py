@@ -21,6 +21,19 @@ if os.path.exists(bj):
     md.append("## bench.py (N=1, CUDA-event timing, not under a profiler)\n")
     md.append("* value %.1f meshes/s (%.2f ms/step, batch %d), e2e %.1f meshes/s, launches %d, clocks %s\n" % (
         b["value"], b["ms_per_step"], b["config"]["meshes_per_gpu"], b["e2e"]["value"], b["gpu_launches"], b.get("clocks")))
+    for c in ("c2", "c5"):
+        fn = os.path.join(G, "bench_%s.json" % c)
+        if os.path.exists(fn):
+            try:
+                bc = json.load(open(fn))
+            except Exception:
+                continue
+            json.dump(bc, open(os.path.join(P, "%s_bench_%s.json" % (tag, c)), "w"), indent=1)
+            rc = bc.get("roofline", {})
+            md.append("* `--config %s` (%s): %.1f meshes/s (%.2f ms/step, batch %d), e2e %.1f; dominant family %.3f of the HBM "
+                      "roofline, whole step %.3f\n" % (c, bc["config"]["workload"][:60], bc["value"], bc["ms_per_step"],
+                                                        bc["config"]["meshes_per_gpu"], bc["e2e"]["value"], rc.get("frac", 0),
+                                                        rc.get("whole_step_frac_of_hbm_roofline", 0)))
     r = b.get("roofline")
     if r:
         md.append("* dominant family `%s`: %.0f GB/s algorithmic = %.3f of %s %.0f GB/s; whole step = %.3f of the HBM roofline\n" % (
