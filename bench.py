@@ -242,7 +242,9 @@ def main():
     batch = [hb[k] for k in order]
     net.set_inputs(*batch)
     allreduce = DP.make_allreduce(world) if train else None   # forward-only replicas have nothing to exchange
-    overlap = train and world > 1 and os.environ.get("CAPE_DP_OVERLAP", "1") != "0"
+    # opt-in (CAPE_DP_OVERLAP=1): the bucketed all-reduce inside the step graph; the default is one all-reduce of the two
+    # flat gradient buffers between the graphs
+    overlap = train and world > 1 and os.environ.get("CAPE_DP_OVERLAP", "0") == "1"
     if overlap:
         net.set_data_parallel(world)                          # bucketed all-reduce inside the step, behind the backward
 

@@ -240,6 +240,7 @@ class Oracle:
                 x = self.res_block_affine(x, i, P, s + "decoder_resblock_affine%d" % (i + 1))
             else:
                 x = self.res_block_decoder(x, i, P, s + "decoder_resblock_cmr%d" % (i + 1))
+            self._keep("dec_act%d" % (i + 1), x)
             x = torch.cat([x, self.fit_cond_dim(x, y), self.fit_cond_dim(x, y2)], -1)  # :606-609
         x = self.chebyshev5(x, self.Lt[0], P[s + "outputs/weights"], self.K[0])   # :612
         return x + P[s + "outputs/bias"]                                          # :615-616

@@ -79,6 +79,10 @@ def main():
             parity.rel(net.dec_fc.cpu().numpy(), a.numpy()),
             parity.rel(net.g_dec_fc_t.cpu().numpy(), (G["dec_fc"] * slope).numpy()),
             parity.rel(net.g_z.cpu().numpy(), G["z_total"][:, :net.nz].numpy())))
+        for i in range(1, 9):
+            a = o.keep["dec_act%d" % i].detach()
+            print("  dec_act%d    fwd %.2e   (max %.3e)" % (i, parity.rel(net.dec_act[i - 1].cpu().numpy(), a.numpy()),
+                                                          float(a.abs().max())))
         for i in range(8, 0, -1):
             a = o.keep["enc_act%d" % i].detach()
             # net.g_enc[i-1] is the gradient w.r.t. the PRE-activation (slope already applied), pooled rows
