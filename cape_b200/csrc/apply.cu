@@ -48,6 +48,7 @@ struct ApParams {
   float* out;
   float* out2;
   int out_stride;
+  long long term_stride;               // > 0: "separate" mode, term t is written on its own to out + t * term_stride
 };
 
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -140,9 +141,20 @@ __global__ void __launch_bounds__(AP_THREADS, 3) apply_kernel(const __grid_const
         f4_axpy(ta, ca, qa);
         f4_axpy(tb, cb, qb);
       }
+      if (p.term_stride > 0) {
+        // separate mode (the K basis tensors of a layer in one launch): no summation, no epilogue
+        float* o = p.out + (size_t)t * p.term_stride;
+        *reinterpret_cast<float4*>(o + (size_t)Ra * p.out_stride + c) =
+            make_float4(tm.scale * ta.x, tm.scale * ta.y, tm.scale * ta.z, tm.scale * ta.w);
+        if (vb)
+          *reinterpret_cast<float4*>(o + (size_t)Rb * p.out_stride + c) =
+              make_float4(tm.scale * tb.x, tm.scale * tb.y, tm.scale * tb.z, tm.scale * tb.w);
+        continue;
+      }
       if (DUAL && tm.acc == 1) { f4_axpy(a1, tm.scale, ta); f4_axpy(b1, tm.scale, tb); }
       else { f4_axpy(a0, tm.scale, ta); f4_axpy(b0, tm.scale, tb); }
     }
+    if (p.term_stride > 0) continue;
     ap_store<DUAL>(p, Ra, ra, c, a0, a1);
     if (vb) ap_store<DUAL>(p, Rb, rb, c, b0, b1);
   }
@@ -196,6 +208,12 @@ extern "C" int cape_apply(cape_topology* t, const cape_apply_args* a, void* stre
   p.epilogue = a->epilogue; p.act = a->act; p.alpha = a->alpha;
   p.bias = a->bias; p.bias_per_row = a->bias_per_row; p.aux = a->aux;
   p.out = a->out; p.out2 = a->out2;
+  p.term_stride = a->term_stride;
+  if (a->term_stride != 0) {
+    CAPE_REQUIRE(a->term_stride > 0 && a->term_stride % 4 == 0 && a->epilogue == CAPE_EPI_LINEAR && !a->bias &&
+                 a->act == CAPE_ACT_NONE && p.nslots == 0 && !dual,
+                 "separate outputs (term_stride) take plain terms: LINEAR epilogue, no bias / activation / condition");
+  }
   if (a->epilogue == CAPE_EPI_SLOPE || a->epilogue == CAPE_EPI_DUALMASK) {
     CAPE_REQUIRE(a->aux && aligned16(a->aux), "epilogue needs a 16-byte aligned aux");
     CAPE_REQUIRE(p.out_stride == a->ncols, "SLOPE / DUALMASK epilogues need out_stride == ncols");

@@ -187,7 +187,8 @@ def cheb_call(tp, N, rows_out, ncols, terms, out, out2=None, cond=None, epilogue
 
 
 def apply_call(tp, N, rows_out, ncols, terms, out, out2=None, out_stride=0, cond=None, epilogue=EPI_LINEAR,
-               act=ACT_NONE, alpha=LEAKY_ALPHA, bias=None, bias_per_row=False, aux=None, tag=None, family="ellconv"):
+               act=ACT_NONE, alpha=LEAKY_ALPHA, bias=None, bias_per_row=False, aux=None, tag=None, family="ellconv",
+               term_stride=0):
     """cape_apply: terms = list of dicts(src, op, src_rows, src_stride, acc=0, scale=1.0, wc=None, wc_stride=0)."""
     a = ApplyArgs()
     a.N, a.rows_out, a.ncols, a.nterms = N, rows_out, ncols, len(terms)
@@ -207,6 +208,7 @@ def apply_call(tp, N, rows_out, ncols, terms, out, out2=None, out_stride=0, cond
     a.aux = aux.data_ptr() if aux is not None else None
     a.out, a.out_stride = out.data_ptr(), out_stride
     a.out2 = out2.data_ptr() if out2 is not None else None
+    a.term_stride = term_stride
     if TRACE:
         print("apply", tag[0] if tag else None, N, rows_out, ncols, [(t["op"], t.get("scale", 1.0)) for t in terms], flush=True)
     with _Prof(family, tag):

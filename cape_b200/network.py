@@ -152,8 +152,12 @@ class ChebLayer:
                                       os.environ.get("CAPE_DW_STASH", "1") != "0")
         self.stash_a, self.stash_g, self.stash_ga = [None] * K, [None] * K, None
         if self.dw_mode == "aside":
-            self.stash_a = [None if site.ops[k] == -1 else torch.empty(maxN, site.rows_out, F, device=dev)
-                            for k in range(K)]
+            # the basis tensors of the non-identity terms, contiguous: cape_apply writes all of them in one launch
+            nz = [k for k in range(K) if site.ops[k] != -1]
+            self.stash_all = torch.empty(max(len(nz), 1), maxN, site.rows_out, F, device=dev)
+            self.stash_a = [None] * K
+            for j, k in enumerate(nz):
+                self.stash_a[k] = self.stash_all[j]
         elif self.dw_mode == "gside":
             self.g_merged = K > 1 and K * Fout <= 512
             if self.g_merged:
@@ -188,8 +192,8 @@ class ChebLayer:
             #    fused kernel on every decoder layer but one, so it is opt-in.
             if self.precise and C == 0 and not self.affine and self.dw_mode == "aside":
                 self.fwd_mode = "basis"
-            elif (C > 0 or self.affine) and site.rows_in < site.rows_out:
-                self.fwd_mode = "contract"
+            elif (C > 0 or self.affine) and (site.rows_in < site.rows_out or self.precise):
+                self.fwd_mode = "contract"           # (a precise decoder block: the projection is the plain-operand kernel)
             if need_dx and self.dw_mode == "aside" and K * F <= 512 and (
                     Fout > F or (site.rows_out < site.rows_in and Fout == F and F >= 128)):
                 self.dx_mode = "contract"
@@ -262,7 +266,7 @@ class ChebLayer:
             cheb_call(self.tp, N, s.rows_in, ncz,
                       [dict(src=x, op=-1, F=F, src_rows=s.rows_in, src_stride=sx, w=None, w_stride=0,
                             wT=self.Wt.view(ncz, F), wT_stride=F, wT_lo=self.Wt_lo.view(ncz, F))],
-                      Z, plain_only=True, tag=sub("project"))
+                      Z, plain_only=True, precise=self.precise, tag=sub("project"))
             terms = [dict(src=Z[:, :, k * Fout:], op=s.ops[k], src_rows=s.rows_in, src_stride=ncz, acc=0,
                           wc=self.W3[F:, k, :] if C else None, wc_stride=K * Fout) for k in range(K)]
             if self.affine:
@@ -273,6 +277,16 @@ class ChebLayer:
                          bias_per_row=self.bias_per_row, tag=tag)
             return
         basis = self.fwd_mode == "basis" and self._split()
+        if basis:
+            # B_k = op_k x for every non-identity term by ONE gather launch, written where the weight gradient reads them
+            nz = [k for k in range(K) if s.ops[k] != -1]
+            if N == self.stash_all.shape[1]:
+                E.apply_call(self.tp, N, s.rows_out, F, [dict(src=x, op=s.ops[k], src_rows=s.rows_in, src_stride=sx) for k in nz],
+                             self.stash_all, term_stride=self.stash_all.stride(0), tag=sub("basis"))
+            else:                                   # a partial batch: the tensors of the terms are not adjacent then
+                for k in nz:
+                    E.apply_call(self.tp, N, s.rows_out, F, [dict(src=x, op=s.ops[k], src_rows=s.rows_in, src_stride=sx)],
+                                 self.stash_a[k][:N], tag=sub("basis%d" % k))
         terms = []
         for k in range(K):
             t = dict(src=x, op=s.ops[k], F=F, src_rows=s.rows_in, src_stride=sx, w=self.W3[:, k, :],
@@ -280,11 +294,7 @@ class ChebLayer:
             if C:
                 t["wc"] = self.W3[F:, k, :]
             if basis and s.ops[k] != -1:
-                # B_k = op_k x by the gather kernel, written where the weight gradient reads it; contracted as a plain tensor
-                B = self.stash_a[k][:N]
-                E.apply_call(self.tp, N, s.rows_out, F, [dict(src=x, op=s.ops[k], src_rows=s.rows_in, src_stride=sx)], B,
-                             tag=sub("basis%d" % k))
-                t.update(src=B, op=-1, src_rows=s.rows_out, src_stride=F)
+                t.update(src=self.stash_a[k][:N], op=-1, src_rows=s.rows_out, src_stride=F)   # contracted as a plain tensor
             elif self.stash_a[k] is not None:
                 t["stash"], t["stash_stride"] = self.stash_a[k][:N], F
             if self.affine and k == 0:
@@ -616,6 +626,9 @@ class CapeNetwork:
         # rounding error is what exp(logvar) amplifies (sigma = exp(logvar / 2) reaches 1e2 with the reference's
         # initialisers); everywhere else the plain 3xTF32 accumulation is well inside the 1e-4 gate.
         precise_enc = os.environ.get("CAPE_PRECISE_ENCODER", "1") != "0"
+        # the first decoder blocks have the longest reductions after the encoder (576 and 320 channels x K): the number
+        # of leading blocks that run contract-first with the short-chain projection (x_hat accuracy, not amplified)
+        precise_dec = int(os.environ.get("CAPE_PRECISE_DECODER", "0"))
         self.enc = []
         fin = c["nn_input_channel"]
         for i in range(nl):
@@ -650,7 +663,8 @@ class CapeNetwork:
                 sc = "generator/decoder/decoder_resblock_affine%d" % (i + 1)
                 self.dec.append(ChebLayer(self, site, fin, Cc, Fo, w(sc + "/graph_conv/weights"),
                                           g(sc + "/graph_conv/weights"), Wa=w(sc + "/affine/weights"),
-                                          gWa=g(sc + "/affine/weights"), maxN=N, name="dec/aff%d" % (i + 1)))
+                                          gWa=g(sc + "/affine/weights"), maxN=N, name="dec/aff%d" % (i + 1),
+                                          precise=i < precise_dec))
             else:
                 Fo = F[-i - 1]
                 self.dec.append(GNBlock(self, i, L[-i - 2], U[-i - 1], fin, Cc, Fo, K[-i - 1],

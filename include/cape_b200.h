@@ -155,6 +155,9 @@ typedef struct {
   float* out;          /* rows out_stride floats apart (0: ncols) -- the result may land inside a wider buffer */
   int out_stride;
   float* out2;         /* same stride, or NULL */
+  /* > 0: "separate" mode -- no summation and no epilogue, term t is written on its own to out + t * term_stride floats
+   * (the K basis tensors B_k = op_k x of a layer in ONE launch; LINEAR epilogue, no bias / activation / condition) */
+  int64_t term_stride;
 } cape_apply_args;
 int cape_apply(cape_topology* t, const cape_apply_args* a, void* stream);
 

@@ -191,6 +191,16 @@ def apply_cases(h):
     t2 = 2 * dense_apply(Lt, dense_apply(Lt, x)) - x + b
     out["apply recurrence T2 (strided, bias, leaky)"] = rel(wide[:, :, F:].cpu().numpy(), np.where(t2 > 0, t2, 0.2 * t2))
     out["apply strided output leaves the rest"] = float(wide[:, :, :F].abs().max())
+    # (4) separate outputs: the three basis tensors of a pooled K=3 layer in one launch
+    site = E.ConvSite(tp, h["L_d"][2], 3, D=h["D_d"][2])
+    N, F = 3, 64
+    x = rng.normal(size=(N, site.rows_in, F)).astype(np.float32)
+    xc = _cuda(x)
+    B = torch.empty(3, N, site.rows_out, F, device="cuda")
+    E.apply_call(tp, N, site.rows_out, F, [dict(src=xc, op=site.ops[k], src_rows=site.rows_in, src_stride=F) for k in range(3)],
+                 B, term_stride=B.stride(0))
+    for k in range(3):
+        out["apply separate outputs term %d" % k] = rel(B[k].cpu().numpy(), dense_apply(site.mats[k], x))
     return out
 
 
