@@ -108,6 +108,49 @@ def choose_dw_mode(F, Fout, K, rows_in, rows_out, need_dx, stash=True):
     return "aside"
 
 
+def choose_forms(F, C, Fout, K, rows_in, rows_out, affine, need_dx, dw_mode, precise, plain, name="", env=None):
+    """(fwd_mode, dx_mode) of a conv layer -- how its forward / data-gradient pass is organised (the math is the same):
+      "fused":    one kernel gathers the basis and contracts it (ellconv_tc.cu; thin layers: thin.cu);
+      "basis":    cape_apply writes B_k = op_k x (forward: the stash the weight gradient reads anyway) or H_k = op_k^T G
+                  (data gradient), then the TMA-fed kernel contracts plain tensors;
+      "contract": the TMA-fed kernel computes Z = x @ [W_0 | W_1 | ..] (or G @ [W_k^T]_k) on the SOURCE rows, then
+                  cape_apply applies the operators to the narrower Z and runs the epilogue.
+    Defaults from the per-layer measurements at batch 64 (profiles/r02_launch_profile.csv):
+      * forward: basis-first where the short-chain accumulation is wanted (it needs plain operands: the encoder),
+        contract-first for un-pooling layers (half the rows in the contraction, Fout-wide gathers: dec/aff3 420 -> 265 us)
+        and for precise decoder blocks, fused elsewhere (discriminator: three gathers + a contraction lose to one kernel);
+      * data gradient: contract-first when the gradient narrows (Fout > F: the gathers run on the narrow side) or the
+        layer pools and is at least 128 wide (the contraction runs on half the rows: disc/conv3 495 -> 333 us);
+        basis-first measured slower than the fused kernel on every decoder layer but one, so it is opt-in.
+    Experiment overrides: CAPE_FWD_MODE / CAPE_DX_MODE for every layer, CAPE_MODES="enc/conv8:fwd=fused,disc/conv3:dx=contract"
+    for single ones (ineligible requests are ignored).  `plain`: every operator of the site is the identity."""
+    env = os.environ if env is None else env
+    thin = F <= 4 or Fout <= 4
+    split_ok = not thin and not plain and F % 16 == 0 and Fout % 16 == 0 and F >= 32 and Fout >= 32
+    fwd_mode, dx_mode = "fused", "fused"
+    basis_ok = C == 0 and not affine and dw_mode == "aside"
+    if split_ok:
+        if precise and basis_ok:
+            fwd_mode = "basis"
+        elif (C > 0 or affine) and (rows_in < rows_out or precise):
+            fwd_mode = "contract"
+        if need_dx and dw_mode == "aside" and K * F <= 512 and (Fout > F or (rows_out < rows_in and Fout == F and F >= 128)):
+            dx_mode = "contract"
+    fm, dm = env.get("CAPE_FWD_MODE", ""), env.get("CAPE_DX_MODE", "")
+    for item in filter(None, env.get("CAPE_MODES", "").split(",")):
+        key, val = item.split("=")
+        if key == name + ":fwd":
+            fm = val
+        elif key == name + ":dx":
+            dm = val
+    if fm and (fm == "fused" or (split_ok and (fm != "basis" or basis_ok))):
+        fwd_mode = fm
+    if dm and need_dx and (dm == "fused" or (split_ok and (dm != "basis" or dw_mode == "gside")
+                                             and (dm != "contract" or dw_mode != "gside"))):
+        dx_mode = dm
+    return fwd_mode, dx_mode
+
+
 class ChebLayer:
     """chebyshev5 (+bias/act, +pool/unpool folded into the site, +condition channels, + optional affine
     branch) with its backward."""
@@ -168,49 +211,8 @@ class ChebLayer:
                                 for k in range(K)]
             if self.affine and site.opsT[0] != -1:
                 self.stash_ga = torch.empty(maxN, site.rows_in, Fout, device=dev)
-        # How the forward / data-gradient passes are organised (the math is the same):
-        #   "fused":    one kernel gathers the basis and contracts it (ellconv_tc.cu; thin layers: thin.cu);
-        #   "basis":    cape_apply writes B_k = op_k x (forward: the stash the weight gradient reads anyway) or
-        #               H_k = op_k^T G (data gradient), then the TMA-fed kernel contracts plain tensors;
-        #   "contract": the TMA-fed kernel computes Z = x @ [W_0 | W_1 | ..] (or G @ [W_k^T]_k) on the SOURCE rows, then
-        #               cape_apply applies the operators to the narrower Z and runs the epilogue.
-        # Gather on the narrower side, contract on the level with fewer rows; layers with condition channels contract
-        # first (the condition term then lives in cape_apply, scaled by the operator's row sums).
-        env = os.environ.get
-        thin = F <= 4 or Fout <= 4
-        plain = all(o == -1 for o in site.ops)
-        split_ok = not thin and not plain and F % 16 == 0 and Fout % 16 == 0 and F >= 32 and Fout >= 32
-        self.fwd_mode, self.dx_mode = "fused", "fused"
-        if split_ok:
-            # Defaults from the per-layer measurements at batch 64 (profiles/r02_launch_profile.csv):
-            #  * forward: basis-first where the short-chain accumulation is wanted (it needs plain operands: the
-            #    encoder), contract-first for un-pooling layers (half the rows in the contraction, Fout-wide gathers:
-            #    dec/aff3 420 -> 265 us), fused elsewhere (discriminator: three gathers + a contraction lose to one kernel);
-            #  * data gradient: contract-first when the gradient narrows (Fout > F: the gathers run on the narrow side)
-            #    or the layer pools and is at least 128 wide (the contraction runs on half the rows: disc/conv3
-            #    495 -> 333 us); basis-first (op^T G by cape_apply, then a plain contraction) measured slower than the
-            #    fused kernel on every decoder layer but one, so it is opt-in.
-            if self.precise and C == 0 and not self.affine and self.dw_mode == "aside":
-                self.fwd_mode = "basis"
-            elif (C > 0 or self.affine) and (site.rows_in < site.rows_out or self.precise):
-                self.fwd_mode = "contract"           # (a precise decoder block: the projection is the plain-operand kernel)
-            if need_dx and self.dw_mode == "aside" and K * F <= 512 and (
-                    Fout > F or (site.rows_out < site.rows_in and Fout == F and F >= 128)):
-                self.dx_mode = "contract"
-        # experiment overrides: CAPE_FWD_MODE / CAPE_DX_MODE for every layer, CAPE_MODES="enc/conv8:fwd=fused,disc/conv3:dx=contract"
-        # for single ones (ineligible requests are ignored)
-        fm, dm = env("CAPE_FWD_MODE", ""), env("CAPE_DX_MODE", "")
-        for item in filter(None, env("CAPE_MODES", "").split(",")):
-            key, val = item.split("=")
-            if key == name + ":fwd":
-                fm = val
-            elif key == name + ":dx":
-                dm = val
-        if fm and (fm == "fused" or (split_ok and (fm != "basis" or (C == 0 and not self.affine and self.dw_mode == "aside")))):
-            self.fwd_mode = fm
-        if dm and need_dx and (dm == "fused" or (split_ok and (dm != "basis" or self.dw_mode == "gside")
-                                                 and (dm != "contract" or self.dw_mode != "gside"))):
-            self.dx_mode = dm
+        self.fwd_mode, self.dx_mode = choose_forms(F, C, Fout, K, site.rows_in, site.rows_out, self.affine, need_dx,
+                                                   self.dw_mode, self.precise, all(o == -1 for o in site.ops), name)
         if self.dx_mode == "contract":
             self.Wk, self.Wk_lo = torch.empty(K, F, Fout, device=dev), torch.empty(K, F, Fout, device=dev)
             net.wprep.add(W, F, K, Fout, wk=self.Wk, wk_lo=self.Wk_lo)

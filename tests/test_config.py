@@ -95,3 +95,30 @@ def test_weight_gradient_operand_choice():
     assert m(64, 64, 3, 3445, 1723, True) == "aside"             # disc conv2
     assert m(128, 128, 2, 862, 862, False) == "aside"            # no data gradient requested -> no G-side stash
     assert m(64, 64, 2, 6890, 3445, True, stash=False) == "gather"
+
+
+def test_layer_forms_of_the_shipped_config():
+    """choose_forms (fused / basis-first / contract-first) on the nz64 layer shapes, and its overrides."""
+    from cape_b200.network import choose_forms as f
+    env = {}
+    # encoder conv2 (pooled 64 -> 64, precise): basis-first forward; the data gradient stays fused (64 wide)
+    assert f(64, 0, 64, 2, 6890, 3445, False, True, "aside", True, False, "enc/conv2", env) == ("basis", "fused")
+    # encoder conv3 (64 -> 128): the gradient narrows -> contract first; conv6 (pooled, 256 wide) too; conv8 (K*F > 512) not
+    assert f(64, 0, 128, 2, 3445, 3445, False, True, "aside", True, False, "enc/conv3", env) == ("basis", "contract")
+    assert f(256, 0, 256, 2, 1723, 862, False, True, "aside", True, False, "enc/conv6", env) == ("basis", "contract")
+    assert f(512, 0, 512, 2, 862, 862, False, True, "aside", True, False, "enc/conv8", env) == ("basis", "fused")
+    # decoder: un-pooling affine blocks contract first, same-level ones stay fused; a precise one contracts first too
+    assert f(256, 64, 128, 2, 862, 1723, True, True, "gside", False, False, "dec/aff3", env) == ("contract", "fused")
+    assert f(512, 64, 256, 2, 862, 862, True, True, "gside", False, False, "dec/aff1", env) == ("fused", "fused")
+    assert f(512, 64, 256, 2, 862, 862, True, True, "gside", True, False, "dec/aff1", env)[0] == "contract"
+    # discriminator (not precise): fused forward, contract-first data gradient where the layer pools and narrows
+    assert f(64, 0, 128, 3, 1723, 862, False, True, "aside", False, False, "disc/conv3", env) == ("fused", "contract")
+    assert f(64, 0, 64, 3, 3445, 1723, False, True, "aside", False, False, "disc/conv2", env) == ("fused", "fused")
+    # thin layers and 1x1 convs (identity operators only) never split
+    assert f(3, 0, 64, 2, 6890, 6890, False, False, "gather", True, False, "enc/conv1", env) == ("fused", "fused")
+    assert f(512, 0, 64, 1, 862, 862, False, True, "gside", True, True, "enc/1x1", env) == ("fused", "fused")
+    # overrides: global and per layer; ineligible requests are ignored
+    assert f(64, 0, 128, 2, 3445, 3445, False, True, "aside", True, False, "enc/conv3", {"CAPE_FWD_MODE": "fused"})[0] == "fused"
+    assert f(512, 0, 512, 2, 862, 862, False, True, "aside", True, False, "enc/conv8",
+             {"CAPE_MODES": "enc/conv8:dx=contract,enc/conv7:fwd=fused"}) == ("basis", "contract")
+    assert f(512, 64, 256, 2, 862, 862, True, True, "gside", False, False, "dec/aff1", {"CAPE_FWD_MODE": "basis"})[0] == "fused"
