@@ -20,7 +20,7 @@ namespace cape {
 namespace {
 
 constexpr int AP_THREADS = 256;
-constexpr int AP_ROWS = 64;            // rows per CTA
+constexpr int AP_ROWS = 64;            // rows per CTA (default; experiment knob 10 overrides)
 constexpr int AP_QS = 3072;            // floats of condition vectors per CTA
 
 struct ApTerm {
@@ -33,6 +33,7 @@ struct ApTerm {
 
 struct ApParams {
   int N, rows_out, ncols, nterms, tpr, rpp;     // threads per row, rows per pass
+  int rows_cta;                                 // rows per CTA
   long long total_rows;
   ApTerm terms[CAPE_MAX_TERMS];
   int nslots;
@@ -97,11 +98,12 @@ __device__ __forceinline__ void ap_store(const ApParams& p, long long R, int r, 
 template <bool DUAL>
 __global__ void __launch_bounds__(AP_THREADS, 3) apply_kernel(const __grid_constant__ ApParams p) {
   __shared__ __align__(16) float qs[AP_QS];
-  const long long R0 = (long long)blockIdx.x * AP_ROWS;
+  const int AP_R = p.rows_cta;
+  const long long R0 = (long long)blockIdx.x * AP_R;
   const int n_first = (int)(R0 / p.rows_out);
   if (p.nslots > 0) {
     // condition vectors of the samples this CTA touches: q[s][slot][c] = cond[n_first + s, :] @ wc_slot[:, c]
-    const long long rlast = min(p.total_rows, R0 + AP_ROWS) - 1;
+    const long long rlast = min(p.total_rows, R0 + AP_R) - 1;
     const int S = (int)(rlast / p.rows_out) - n_first + 1;
     const int total = S * p.nslots * p.ncols;
     for (int o = threadIdx.x; o < total; o += AP_THREADS) {
@@ -116,10 +118,10 @@ __global__ void __launch_bounds__(AP_THREADS, 3) apply_kernel(const __grid_const
   }
   const int lr = threadIdx.x / p.tpr, c = (threadIdx.x % p.tpr) * 4;
   if (lr >= p.rpp) return;
-  for (int base = lr; base < AP_ROWS; base += 2 * p.rpp) {
+  for (int base = lr; base < AP_R; base += 2 * p.rpp) {
     const long long Ra = R0 + base, Rb = Ra + p.rpp;
     if (Ra >= p.total_rows) break;
-    const bool vb = (base + p.rpp < AP_ROWS) && Rb < p.total_rows;
+    const bool vb = (base + p.rpp < AP_R) && Rb < p.total_rows;
     const int na = (int)(Ra / p.rows_out), ra = (int)(Ra % p.rows_out);
     const int nb = vb ? (int)(Rb / p.rows_out) : na, rb = vb ? (int)(Rb % p.rows_out) : ra;
     float4 a0 = f4_zero(), a1 = f4_zero(), b0 = f4_zero(), b1 = f4_zero();
@@ -177,8 +179,9 @@ extern "C" int cape_apply(cape_topology* t, const cape_apply_args* a, void* stre
   p.N = a->N; p.rows_out = a->rows_out; p.ncols = a->ncols; p.nterms = a->nterms;
   p.total_rows = (long long)a->N * a->rows_out;
   p.tpr = a->ncols / 4;
+  p.rows_cta = (g_tuning[10] >= 16 && g_tuning[10] <= 1024) ? g_tuning[10] : AP_ROWS;
   p.rpp = AP_THREADS / p.tpr;
-  if (p.rpp > AP_ROWS / 2) p.rpp = AP_ROWS / 2;
+  if (p.rpp > p.rows_cta / 2) p.rpp = p.rows_cta / 2;
   p.out_stride = a->out_stride > 0 ? a->out_stride : a->ncols;
   CAPE_REQUIRE(p.out_stride >= a->ncols && p.out_stride % 4 == 0 && aligned16(a->out) && (!a->out2 || aligned16(a->out2)),
                "out / out2 must be 16-byte aligned with out_stride % 4 == 0");
@@ -201,7 +204,7 @@ extern "C" int cape_apply(cape_topology* t, const cape_apply_args* a, void* stre
     }
   }
   if (p.nslots > 0) {
-    const long long max_samples = (AP_ROWS - 1) / a->rows_out + 2;
+    const long long max_samples = (p.rows_cta - 1) / a->rows_out + 2;
     CAPE_REQUIRE(max_samples * p.nslots * a->ncols <= AP_QS, "too many condition columns for the staging buffer");
   }
   p.cond = a->cond; p.C = a->C;
@@ -218,7 +221,7 @@ extern "C" int cape_apply(cape_topology* t, const cape_apply_args* a, void* stre
     CAPE_REQUIRE(a->aux && aligned16(a->aux), "epilogue needs a 16-byte aligned aux");
     CAPE_REQUIRE(p.out_stride == a->ncols, "SLOPE / DUALMASK epilogues need out_stride == ncols");
   }
-  const long long blocks = (p.total_rows + AP_ROWS - 1) / AP_ROWS;
+  const long long blocks = (p.total_rows + p.rows_cta - 1) / p.rows_cta;
   CAPE_REQUIRE(blocks < (1LL << 31), "grid too large");
   if (dual) apply_kernel<true><<<(unsigned)blocks, AP_THREADS, 0, (cudaStream_t)stream>>>(p);
   else apply_kernel<false><<<(unsigned)blocks, AP_THREADS, 0, (cudaStream_t)stream>>>(p);

@@ -107,7 +107,7 @@ for rep in sorted(f for f in os.listdir(G) if f.endswith(".ncu-rep")):
         for r in rows[2:]:
             w.writerow([r[i] for i in idx])
             try:      # DRAM bytes per launch of the conv kernels -> bench.py's roofline.traffic
-                if "ellconv_tc" in r[hdr.index("Kernel Name")]:
+                if any(k in r[hdr.index("Kernel Name")] for k in ("ellconv_tc", "gemm_tc", "apply_kernel")):   # the conv family
                     b = 0.0
                     for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                         k = hdr.index(key)
@@ -118,8 +118,10 @@ for rep in sorted(f for f in os.listdir(G) if f.endswith(".ncu-rep")):
             md.append("| " + " | ".join(re.sub(r"\(.*", "", r[i])[-48:] + (" " + units[i] if units[i] else "") for i in idx) + " |\n")
 if traffic:
     json.dump({"ellconv": sum(traffic["ellconv"]) / len(traffic["ellconv"]),
-               "note": "mean dram__bytes_read.sum + dram__bytes_write.sum per launch over the %d fused-conv launches captured "
-                       "with ncu --set full (%s_prof_conv_*.csv); bench.py reports it as roofline.traffic" % (len(traffic["ellconv"]), tag)},
+               "source": "profiles/%s_prof_*.csv" % tag,
+               "note": "mean dram__bytes_read.sum + dram__bytes_write.sum per launch over the %d conv-family launches (fused, "
+                       "plain-operand and apply kernels) captured with ncu --set full; bench.py reports it as roofline.traffic"
+                       % len(traffic["ellconv"])},
               open(os.path.join(P, "roofline_traffic.json"), "w"), indent=1)
 open(os.path.join(P, "%s_summary.md" % tag), "w").write("".join(md))
 print("".join(md)[:3000])
