@@ -206,8 +206,8 @@ dw_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     tc_fence_before();
   } else if (warp == DD_CONV_WARPS) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer (whole warp walks the loops, one elected lane issues) ===========================
+    {
       // D=F32, A=B=TF32, A and B MN-major (bits 15,16), N=BN, M=128
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                  ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -225,33 +225,41 @@ dw_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t ghi = smem_u32(ghi_ring + (size_t)gh * Cfg::G_TILE);
           const uint32_t glo = smem_u32(glo_ring + (size_t)gl * Cfg::G_TILE);
           const uint32_t d = tmem_base + (uint32_t)(cs * BN);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < DD_KCH / 8; ++ks) {
-            const uint64_t a_hi = make_desc_mn(ahi + ks * 1024), a_lo = make_desc_mn(alo + ks * 1024);
-            const uint64_t g_hi = make_desc_mn(ghi + ks * 1024), g_lo = make_desc_mn(glo + ks * 1024);
-            umma_tf32(d, a_hi, g_hi, idesc, ks == 0 ? acc_on : 1u);
-            umma_tf32(d, a_lo, g_hi, idesc, 1);
-            umma_tf32(d, a_hi, g_lo, idesc, 1);
+            for (int ks = 0; ks < DD_KCH / 8; ++ks) {
+              const uint64_t a_hi = make_desc_mn(ahi + ks * 1024), a_lo = make_desc_mn(alo + ks * 1024);
+              const uint64_t g_hi = make_desc_mn(ghi + ks * 1024), g_lo = make_desc_mn(glo + ks * 1024);
+              umma_tf32(d, a_hi, g_hi, idesc, ks == 0 ? acc_on : 1u);
+              umma_tf32(d, a_lo, g_hi, idesc, 1);
+              umma_tf32(d, a_hi, g_lo, idesc, 1);
+            }
+            umma_commit(bar_ghe + 8 * gh);
+            umma_commit(bar_gle + 8 * gl);
+            if (cs == nct - 1) {
+              umma_commit(bar_ahe + 8 * ah);
+              umma_commit(bar_ale + 8 * al);
+            }
           }
-          umma_commit(bar_ghe + 8 * gh);
-          umma_commit(bar_gle + 8 * gl);
+          __syncwarp();
           if (++gh == SGH) { gh = 0; pgh ^= 1; }
           if (++gl == SGL) { gl = 0; pgl ^= 1; }
         }
-        umma_commit(bar_ahe + 8 * ah);
-        umma_commit(bar_ale + 8 * al);
         if (++ah == SAH) { ah = 0; pah ^= 1; }
         if (++al == SAL) { al = 0; pal ^= 1; }
         acc_on = 1;
       }
-      umma_commit(bar_accum);
+      if (elect_one()) umma_commit(bar_accum);          // also flips with no chunks at all (empty row range)
     }
     __syncwarp();
   } else {
-    // =========================== TMA issuer ===========================
-    if (lane == 0) {
-      tma_prefetch_desc(&tmA);
-      tma_prefetch_desc(&tmG);
+    // =========================== TMA issuer (whole warp walks the loops, one elected lane issues) ===========================
+    {
+      if (lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmG);
+      }
+      __syncwarp();
       // The A ring runs ahead of the G ring by whole chunks, so the loop is over G sub-tiles in consumption order and
       // an A tile is issued as soon as its stage is free (never blocking the G stream behind a full A ring).
       int ah = 0, gh = 0;
@@ -266,16 +274,19 @@ dw_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 "mbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
                 "selp.u32 %0, 1, 0, q;\n\t}"
                 : "=r"(ok) : "r"(bar_ahe + 8 * ah), "r"(pah ^ 1) : "memory");
-            if (!ok) return;
+            if (!__all_sync(0xffffffffu, ok)) return;    // one answer for the whole warp
           } else {
             mbar_wait(bar_ahe + 8 * ah, pah ^ 1);
           }
-          mbar_arrive_expect_tx(bar_ahf + 8 * ah, (uint32_t)(a_blocks * 4096));
-          const uint32_t adst = smem_u32(ahi_ring + (size_t)ah * DD_A_TILE);
-          const int row0 = (int)(rbeg + ka * DD_KCH);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_ahf + 8 * ah, (uint32_t)(a_blocks * 4096));
+            const uint32_t adst = smem_u32(ahi_ring + (size_t)ah * DD_A_TILE);
+            const int row0 = (int)(rbeg + ka * DD_KCH);
 #pragma unroll
-          for (int mb = 0; mb < 4; ++mb)
-            if (mb < a_blocks) tma_load_2d(adst + mb * 4096, &tmA, ftile + mb * 32, row0, bar_ahf + 8 * ah);
+            for (int mb = 0; mb < 4; ++mb)
+              if (mb < a_blocks) tma_load_2d(adst + mb * 4096, &tmA, ftile + mb * 32, row0, bar_ahf + 8 * ah);
+          }
+          __syncwarp();
           if (++ah == SAH) { ah = 0; pah ^= 1; }
           ++ka;
           block = false;
@@ -286,11 +297,14 @@ dw_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         issue_a(ka <= kc);                               // the A tile of this chunk must be on its way before its G tiles
         for (int cs = 0; cs < nct; ++cs) {
           mbar_wait(bar_ghe + 8 * gh, pgh ^ 1);
-          mbar_arrive_expect_tx(bar_ghf + 8 * gh, Cfg::G_TILE);
-          const uint32_t gdst = smem_u32(ghi_ring + (size_t)gh * Cfg::G_TILE);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_ghf + 8 * gh, Cfg::G_TILE);
+            const uint32_t gdst = smem_u32(ghi_ring + (size_t)gh * Cfg::G_TILE);
 #pragma unroll
-          for (int mb = 0; mb < BN / 32; ++mb)
-            tma_load_2d(gdst + mb * 4096, &tmG, cs * BN + mb * 32, row0, bar_ghf + 8 * gh);
+            for (int mb = 0; mb < BN / 32; ++mb)
+              tma_load_2d(gdst + mb * 4096, &tmG, cs * BN + mb * 32, row0, bar_ghf + 8 * gh);
+          }
+          __syncwarp();
           if (++gh == SGH) { gh = 0; pgh ^= 1; }
           issue_a(false);
         }

@@ -205,8 +205,8 @@ __global__ void __launch_bounds__(DT_THREADS, OCC) ellconv_dw_tc_kernel(const __
     }
     tc_fence_before();
   } else {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer (whole warp walks the loops, one elected lane issues) ===========================
+    {
       // D=F32, A=B=TF32, A and B MN-major (bits 15,16), N=BN, M=128
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                  ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -220,22 +220,25 @@ __global__ void __launch_bounds__(DT_THREADS, OCC) ellconv_dw_tc_kernel(const __
           tc_fence_after();
           const uint32_t gaddr = smem_u32(g_ring + (size_t)sg * Cfg::G_STAGE);
           const uint32_t d = tmem_base + (uint32_t)(cs * BN);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < DT_KCH / 8; ++ks) {
-            const uint64_t a_hi = make_desc_mn(aaddr + ks * 1024), a_lo = make_desc_mn(aaddr + DT_A_TILE + ks * 1024);
-            const uint64_t g_hi = make_desc_mn(gaddr + ks * 1024), g_lo = make_desc_mn(gaddr + Cfg::G_TILE + ks * 1024);
-            umma_tf32(d, a_hi, g_hi, idesc, ks == 0 ? acc_on : 1u);
-            umma_tf32(d, a_lo, g_hi, idesc, 1);
-            umma_tf32(d, a_hi, g_lo, idesc, 1);
+            for (int ks = 0; ks < DT_KCH / 8; ++ks) {
+              const uint64_t a_hi = make_desc_mn(aaddr + ks * 1024), a_lo = make_desc_mn(aaddr + DT_A_TILE + ks * 1024);
+              const uint64_t g_hi = make_desc_mn(gaddr + ks * 1024), g_lo = make_desc_mn(gaddr + Cfg::G_TILE + ks * 1024);
+              umma_tf32(d, a_hi, g_hi, idesc, ks == 0 ? acc_on : 1u);
+              umma_tf32(d, a_lo, g_hi, idesc, 1);
+              umma_tf32(d, a_hi, g_lo, idesc, 1);
+            }
+            umma_commit(bar_gempty + 8 * sg);
+            if (cs == nct - 1) umma_commit(bar_aempty + 8 * sa);
           }
-          umma_commit(bar_gempty + 8 * sg);
+          __syncwarp();
           if (++sg == SG) { sg = 0; phg ^= 1; }
         }
-        umma_commit(bar_aempty + 8 * sa);
         if (++sa == SA) { sa = 0; pha ^= 1; }
         acc_on = 1;
       }
-      umma_commit(bar_accum);
+      if (elect_one()) umma_commit(bar_accum);
     }
     __syncwarp();
   }

@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
       }
     }
   } else if (warp == TC_PROD_WARPS) {
-    // =========================== MMA issuer (one elected lane) ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer (whole warp walks the loops, one elected lane issues) ===========================
+    {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N=BN, M=128
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int sa = 0, sb = 0, it = 0;
@@ -257,35 +257,39 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
               const uint64_t b_hi = make_desc(baddr), b_lo = make_desc(baddr + Cfg::B_TILE_BYTES);
               const uint64_t b2_hi = make_desc(baddr + 2 * Cfg::B_TILE_BYTES), b2_lo = make_desc(baddr + 3 * Cfg::B_TILE_BYTES);
               const uint32_t d0 = tb + (uint32_t)(cs * BN), d1 = d0 + acc1_col;
+              if (tc::elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < BK / 8; ++ks) {
-                const uint64_t adv = (uint64_t)(ks * 2);  // +32 bytes along K inside the 128-byte swizzle row
-                // the very first MMA into a sub-tile's TMEM columns overwrites (TMEM is not zero-initialised)
-                umma_tf32(d0, a_hi + adv, b_hi + adv, idesc, ks == 0 ? acc0_on : 1u);
-                umma_tf32(d0, a_lo + adv, b_hi + adv, idesc, 1);
-                umma_tf32(d0, a_hi + adv, b_lo + adv, idesc, 1);
-                if (has2) {
-                  umma_tf32(d1, a_hi + adv, b2_hi + adv, idesc, ks == 0 ? acc1_on : 1u);
-                  umma_tf32(d1, a_lo + adv, b2_hi + adv, idesc, 1);
-                  umma_tf32(d1, a_hi + adv, b2_lo + adv, idesc, 1);
+                for (int ks = 0; ks < BK / 8; ++ks) {
+                  const uint64_t adv = (uint64_t)(ks * 2);  // +32 bytes along K inside the 128-byte swizzle row
+                  // the very first MMA into a sub-tile's TMEM columns overwrites (TMEM is not zero-initialised)
+                  umma_tf32(d0, a_hi + adv, b_hi + adv, idesc, ks == 0 ? acc0_on : 1u);
+                  umma_tf32(d0, a_lo + adv, b_hi + adv, idesc, 1);
+                  umma_tf32(d0, a_hi + adv, b_lo + adv, idesc, 1);
+                  if (has2) {
+                    umma_tf32(d1, a_hi + adv, b2_hi + adv, idesc, ks == 0 ? acc1_on : 1u);
+                    umma_tf32(d1, a_lo + adv, b2_hi + adv, idesc, 1);
+                    umma_tf32(d1, a_hi + adv, b2_lo + adv, idesc, 1);
+                  }
                 }
+                umma_commit(bar_bempty + 8 * sb);          // weight stage reusable once these MMAs have read it
+                if (cs == nct - 1) umma_commit(bar_aempty + 8 * sa);   // basis stage reusable
               }
-              umma_commit(bar_bempty + 8 * sb);            // weight stage reusable once these MMAs have read it
+              __syncwarp();
               if (++sb == SB) { sb = 0; phb ^= 1; }
             }
-            umma_commit(bar_aempty + 8 * sa);              // basis stage reusable
             if (++sa == SA) { sa = 0; pha ^= 1; }
             acc0_on = 1;
             if (has2) acc1_on = 1;
           }
         }
-        umma_commit(bar_tfull + 8 * buf);                  // this tile's accumulators are complete
+        if (tc::elect_one()) umma_commit(bar_tfull + 8 * buf);   // this tile's accumulators are complete
+        __syncwarp();
       }
     }
     __syncwarp();
   } else if (warp == TC_TMA_WARP) {
     // =========================== TMA issuer: weight tiles (hi = raw fp32, lo = pre-split copy) ===========================
-    if ((tma_b || tma_a) && lane == 0) {
+    if (tma_b || tma_a) {
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -298,20 +302,26 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
             // ago" from "this use", so this thread must never get more than one use of a stage ahead of the MMAs.
             if (tma_a) mbar_wait(bar_aempty + 8 * sa, pha ^ 1);
             if (a_here) {
-              tc::mbar_arrive_expect_tx(bar_atma + 8 * sa, (uint32_t)A_TILE_BYTES);
-              tc::tma_load_2d(smem_u32(a_ring + (size_t)sa * Cfg::A_STAGE_BYTES), &maps.a[t], f0, row0, bar_atma + 8 * sa);
+              if (tc::elect_one()) {
+                tc::mbar_arrive_expect_tx(bar_atma + 8 * sa, (uint32_t)A_TILE_BYTES);
+                tc::tma_load_2d(smem_u32(a_ring + (size_t)sa * Cfg::A_STAGE_BYTES), &maps.a[t], f0, row0, bar_atma + 8 * sa);
+              }
+              __syncwarp();
             }
             if (++sa == SA) { sa = 0; pha ^= 1; }
             for (int cs = 0; cs < (tma_b ? nct : 0); ++cs) {
               mbar_wait(bar_bempty + 8 * sb, phb ^ 1);
-              tc::mbar_arrive_expect_tx(bar_bfull + 8 * sb, (uint32_t)((has2 ? 4 : 2) * Cfg::B_TILE_BYTES));
-              const uint32_t dst = smem_u32(b_ring + (size_t)sb * Cfg::B_STAGE_BYTES);
-              tc::tma_load_2d(dst, &maps.m[t][0], f0, cs * BN, bar_bfull + 8 * sb);
-              tc::tma_load_2d(dst + Cfg::B_TILE_BYTES, &maps.m[t][1], f0, cs * BN, bar_bfull + 8 * sb);
-              if (has2) {
-                tc::tma_load_2d(dst + 2 * Cfg::B_TILE_BYTES, &maps.m[t][2], f0, cs * BN, bar_bfull + 8 * sb);
-                tc::tma_load_2d(dst + 3 * Cfg::B_TILE_BYTES, &maps.m[t][3], f0, cs * BN, bar_bfull + 8 * sb);
+              if (tc::elect_one()) {
+                tc::mbar_arrive_expect_tx(bar_bfull + 8 * sb, (uint32_t)((has2 ? 4 : 2) * Cfg::B_TILE_BYTES));
+                const uint32_t dst = smem_u32(b_ring + (size_t)sb * Cfg::B_STAGE_BYTES);
+                tc::tma_load_2d(dst, &maps.m[t][0], f0, cs * BN, bar_bfull + 8 * sb);
+                tc::tma_load_2d(dst + Cfg::B_TILE_BYTES, &maps.m[t][1], f0, cs * BN, bar_bfull + 8 * sb);
+                if (has2) {
+                  tc::tma_load_2d(dst + 2 * Cfg::B_TILE_BYTES, &maps.m[t][2], f0, cs * BN, bar_bfull + 8 * sb);
+                  tc::tma_load_2d(dst + 3 * Cfg::B_TILE_BYTES, &maps.m[t][3], f0, cs * BN, bar_bfull + 8 * sb);
+                }
               }
+              __syncwarp();
               if (++sb == SB) { sb = 0; phb ^= 1; }
             }
           }
@@ -769,7 +779,7 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 2) ellconv_tc2_kernel(const _
     tc_fence_before();
   } else if (warp == TC_PROD_WARPS + 1) {
     // =========================== TMA issuer: weight tiles (hi = raw fp32, lo = pre-split copy) ===========================
-    if (tma_b && lane == 0) {
+    if (tma_b) {
       int sb = 0;
       uint32_t phb = 0;
       for (int t = 0; t < p.nterms; ++t) {
@@ -777,14 +787,17 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 2) ellconv_tc2_kernel(const _
         for (int f0 = 0; f0 < p.terms[t].F; f0 += BK) {
           for (int cs = 0; cs < nct; ++cs) {
             mbar_wait(bar_bempty + 8 * sb, phb ^ 1);
-            tc::mbar_arrive_expect_tx(bar_bfull + 8 * sb, (uint32_t)((has2 ? 4 : 2) * Cfg::B_TILE_BYTES));
-            const uint32_t dst = smem_u32(b_ring + (size_t)sb * Cfg::B_STAGE_BYTES);
-            tc::tma_load_2d(dst, &maps.m[t][0], f0, cs * BN, bar_bfull + 8 * sb);
-            tc::tma_load_2d(dst + Cfg::B_TILE_BYTES, &maps.m[t][1], f0, cs * BN, bar_bfull + 8 * sb);
-            if (has2) {
-              tc::tma_load_2d(dst + 2 * Cfg::B_TILE_BYTES, &maps.m[t][2], f0, cs * BN, bar_bfull + 8 * sb);
-              tc::tma_load_2d(dst + 3 * Cfg::B_TILE_BYTES, &maps.m[t][3], f0, cs * BN, bar_bfull + 8 * sb);
+            if (tc::elect_one()) {
+              tc::mbar_arrive_expect_tx(bar_bfull + 8 * sb, (uint32_t)((has2 ? 4 : 2) * Cfg::B_TILE_BYTES));
+              const uint32_t dst = smem_u32(b_ring + (size_t)sb * Cfg::B_STAGE_BYTES);
+              tc::tma_load_2d(dst, &maps.m[t][0], f0, cs * BN, bar_bfull + 8 * sb);
+              tc::tma_load_2d(dst + Cfg::B_TILE_BYTES, &maps.m[t][1], f0, cs * BN, bar_bfull + 8 * sb);
+              if (has2) {
+                tc::tma_load_2d(dst + 2 * Cfg::B_TILE_BYTES, &maps.m[t][2], f0, cs * BN, bar_bfull + 8 * sb);
+                tc::tma_load_2d(dst + 3 * Cfg::B_TILE_BYTES, &maps.m[t][3], f0, cs * BN, bar_bfull + 8 * sb);
+              }
             }
+            __syncwarp();
             if (++sb == SB) { sb = 0; phb ^= 1; }
           }
         }
@@ -792,8 +805,8 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 2) ellconv_tc2_kernel(const _
     }
     __syncwarp();
   } else {
-    // =========================== MMA issuer (one elected lane) ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer (whole warp walks the loops, one elected lane issues) ===========================
+    {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N=BN, M=128
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int sa = 0, sb = 0;
@@ -811,29 +824,32 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 2) ellconv_tc2_kernel(const _
             const uint64_t b_hi = make_desc(baddr), b_lo = make_desc(baddr + Cfg::B_TILE_BYTES);
             const uint64_t b2_hi = make_desc(baddr + 2 * Cfg::B_TILE_BYTES), b2_lo = make_desc(baddr + 3 * Cfg::B_TILE_BYTES);
             const uint32_t d0 = tmem_base + (uint32_t)(cs * BN), d1 = d0 + acc1_col;
+            if (tc::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < BK / 8; ++ks) {
-              const uint64_t adv = (uint64_t)(ks * 2);    // +32 bytes along K inside the 128-byte swizzle row
-              // the very first MMA into a sub-tile's TMEM columns overwrites (TMEM is not zero-initialised)
-              umma_tf32(d0, a_hi + adv, b_hi + adv, idesc, ks == 0 ? acc0_on : 1u);
-              umma_tf32(d0, a_lo + adv, b_hi + adv, idesc, 1);
-              umma_tf32(d0, a_hi + adv, b_lo + adv, idesc, 1);
-              if (has2) {
-                umma_tf32(d1, a_hi + adv, b2_hi + adv, idesc, ks == 0 ? acc1_on : 1u);
-                umma_tf32(d1, a_lo + adv, b2_hi + adv, idesc, 1);
-                umma_tf32(d1, a_hi + adv, b2_lo + adv, idesc, 1);
+              for (int ks = 0; ks < BK / 8; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);  // +32 bytes along K inside the 128-byte swizzle row
+                // the very first MMA into a sub-tile's TMEM columns overwrites (TMEM is not zero-initialised)
+                umma_tf32(d0, a_hi + adv, b_hi + adv, idesc, ks == 0 ? acc0_on : 1u);
+                umma_tf32(d0, a_lo + adv, b_hi + adv, idesc, 1);
+                umma_tf32(d0, a_hi + adv, b_lo + adv, idesc, 1);
+                if (has2) {
+                  umma_tf32(d1, a_hi + adv, b2_hi + adv, idesc, ks == 0 ? acc1_on : 1u);
+                  umma_tf32(d1, a_lo + adv, b2_hi + adv, idesc, 1);
+                  umma_tf32(d1, a_hi + adv, b2_lo + adv, idesc, 1);
+                }
               }
+              umma_commit(bar_bempty + 8 * sb);            // weight stage reusable once these MMAs have read it
+              if (cs == nct - 1) umma_commit(bar_aempty + 8 * sa);     // basis stage reusable
             }
-            umma_commit(bar_bempty + 8 * sb);              // weight stage reusable once these MMAs have read it
+            __syncwarp();
             if (++sb == SB) { sb = 0; phb ^= 1; }
           }
-          umma_commit(bar_aempty + 8 * sa);                // basis stage reusable
           if (++sa == SA) { sa = 0; pha ^= 1; }
           acc0_on = 1;
           if (has2) acc1_on = 1;
         }
       }
-      umma_commit(bar_accum);                              // accumulators complete
+      if (tc::elect_one()) umma_commit(bar_accum);         // accumulators complete
     }
     __syncwarp();
   }

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
     }
   } else if (warp == G_TMA_A_WARP) {
     // =========================== TMA: A tiles ===========================
-    if (lane == 0) {
+    {
       int sr = 0;
       uint32_t phr = 0;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -196,8 +196,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
             int t, f0;
             chunk_of(w, j, t, f0);
             mbar_wait(bar_re + 8 * sr, ((phr >> sr) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(bar_rf + 8 * sr, (uint32_t)G_A_TILE);
-            tma_load_2d(smem_u32(raw_ring + (size_t)sr * G_A_TILE), &maps.a[t], f0, row0, bar_rf + 8 * sr);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(bar_rf + 8 * sr, (uint32_t)G_A_TILE);
+              tma_load_2d(smem_u32(raw_ring + (size_t)sr * G_A_TILE), &maps.a[t], f0, row0, bar_rf + 8 * sr);
+            }
+            __syncwarp();
             phr ^= 1u << sr;
             if (++sr == g.sr) sr = 0;
           }
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
     __syncwarp();
   } else if (warp == G_TMA_B_WARP) {
     // =========================== TMA: raw weight tiles ===========================
-    if (lane == 0) {
+    {
       int sb = 0;
       uint32_t phb = 0;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -219,8 +222,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
             chunk_of(w, j, t, f0);
             for (int s = 0; s < nsub; ++s) {
               mbar_wait(bar_be + 8 * sb, ((phb >> sb) & 1u) ^ 1u);
-              mbar_arrive_expect_tx(bar_bf + 8 * sb, (uint32_t)B_TILE);
-              tma_load_2d(smem_u32(braw_ring + (size_t)sb * B_TILE), &maps.bh[t], f0, col0 + s * BN, bar_bf + 8 * sb);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(bar_bf + 8 * sb, (uint32_t)B_TILE);
+                tma_load_2d(smem_u32(braw_ring + (size_t)sb * B_TILE), &maps.bh[t], f0, col0 + s * BN, bar_bf + 8 * sb);
+              }
+              __syncwarp();
               phb ^= 1u << sb;
               if (++sb == g.sbr) sb = 0;
             }
@@ -230,8 +236,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
     }
     __syncwarp();
   } else if (warp == G_MMA_WARP) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer (whole warp, one elected lane issues) ===========================
+    {
       // instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128; N (a multiple of 16) is set per sub-tile
       constexpr uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BM >> 4) << 24);
       int sr = 0, sl = 0, sbr = 0, sbl = 0, it = 0;
@@ -268,35 +274,40 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
               const uint64_t b_hi = make_desc_k(smem_u32(braw_ring + (size_t)sbr * B_TILE));
               const uint64_t b_lo = make_desc_k(smem_u32(blo_ring + (size_t)sbl * B_TILE));
               const uint32_t d0 = tb + (uint32_t)(s * BN);
+              if (elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < BK / 8; ++ks) {
-                const uint64_t adv = (uint64_t)(ks * 2);          // +32 bytes along K inside the swizzle row
-                if (PRECISE) {
-                  const uint32_t d_corr = d0 + 3u * (uint32_t)g.gw;
-                  umma_tf32(d0 + chain_off[ks], a_hi + adv, b_hi + adv, idesc, ks < 3 ? later : 1u);
-                  umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, ks == 0 ? later : 1u);
-                  umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
-                } else {
-                  umma_tf32(d0, a_hi + adv, b_hi + adv, idesc, ks == 0 ? later : 1u);
-                  umma_tf32(d0, a_lo + adv, b_hi + adv, idesc, 1u);
-                  umma_tf32(d0, a_hi + adv, b_lo + adv, idesc, 1u);
+                for (int ks = 0; ks < BK / 8; ++ks) {
+                  const uint64_t adv = (uint64_t)(ks * 2);        // +32 bytes along K inside the swizzle row
+                  if (PRECISE) {
+                    const uint32_t d_corr = d0 + 3u * (uint32_t)g.gw;
+                    umma_tf32(d0 + chain_off[ks], a_hi + adv, b_hi + adv, idesc, ks < 3 ? later : 1u);
+                    umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, ks == 0 ? later : 1u);
+                    umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+                  } else {
+                    umma_tf32(d0, a_hi + adv, b_hi + adv, idesc, ks == 0 ? later : 1u);
+                    umma_tf32(d0, a_lo + adv, b_hi + adv, idesc, 1u);
+                    umma_tf32(d0, a_hi + adv, b_lo + adv, idesc, 1u);
+                  }
+                }
+                umma_commit(bar_be + 8 * sbr);
+                umma_commit(bar_ble + 8 * sbl);
+                if (s == nsub - 1) {                              // last sub-tile: the A tiles of this chunk are free too
+                  umma_commit(bar_re + 8 * sr);
+                  umma_commit(bar_le + 8 * sl);
+                  if (j == nchunks - 1) umma_commit(bar_tf + 8 * buf);
                 }
               }
-              umma_commit(bar_be + 8 * sbr);
-              umma_commit(bar_ble + 8 * sbl);
+              __syncwarp();
               phb ^= 1u << sbr; phbl ^= 1u << sbl;
               if (++sbr == g.sbr) sbr = 0;
               if (++sbl == g.sbl) sbl = 0;
             }
             c0 = c1;
-            umma_commit(bar_re + 8 * sr);
-            umma_commit(bar_le + 8 * sl);
             phr ^= 1u << sr; phl ^= 1u << sl;
             if (++sr == g.sr) sr = 0;
             if (++sl == g.sl) sl = 0;
           }
         }
-        umma_commit(bar_tf + 8 * buf);
       }
     }
     __syncwarp();
@@ -343,6 +354,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
       const uint32_t taddr_row = tmem_base + (uint32_t)(buf * g.gw * nacc) + ((uint32_t)(quad * 32) << 16);
       const size_t orow = (size_t)R * p.ncols + col0;
       const bool use_aux = valid && (p.epilogue == CAPE_EPI_SLOPE || p.epilogue == CAPE_EPI_DUALMASK);
+      const bool linear = p.epilogue == CAPE_EPI_LINEAR;
+      const int act = p.act;
+      const float alpha = p.alpha;
+      const float* bias_row = (linear && p.bias != nullptr) ? p.bias + (p.bias_per_row ? (size_t)r * p.ncols : 0) + col0 : nullptr;
+      const bool bias_vec = bias_row != nullptr && (reinterpret_cast<uintptr_t>(bias_row) & 15u) == 0;
       float4 axn[4];
       if (use_aux) {
 #pragma unroll
@@ -389,14 +405,27 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
         }
         float o1[16], o2[16];
         bool write2 = false;
-        if (p.epilogue == CAPE_EPI_LINEAR) {
+        if (linear) {
+          // 16 columns of one row: bias as four 16-byte loads, the activation chosen once per tile (not per element)
+          if (bias_vec) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float v = v0[j];
-            if (p.bias != nullptr) v += __ldg(p.bias + (p.bias_per_row ? (size_t)r * p.ncols : 0) + col0 + c0 + j);
-            if (p.act == CAPE_ACT_LEAKY) v = v > 0.f ? v : p.alpha * v;
-            else if (p.act == CAPE_ACT_RELU) v = fmaxf(v, 0.f);
-            o1[j] = v;
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = ldg4(bias_row + c0 + j);
+              v0[j] += b4.x; v0[j + 1] += b4.y; v0[j + 2] += b4.z; v0[j + 3] += b4.w;
+            }
+          } else if (bias_row != nullptr) {              // a bias that is a 4-byte-aligned view into a flat parameter buffer
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v0[j] += __ldg(bias_row + c0 + j);
+          }
+          if (act == CAPE_ACT_LEAKY) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o1[j] = v0[j] > 0.f ? v0[j] : alpha * v0[j];
+          } else if (act == CAPE_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o1[j] = fmaxf(v0[j], 0.f);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o1[j] = v0[j];
           }
         } else {
           float ax[16];
@@ -407,7 +436,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
           }
           if (p.epilogue == CAPE_EPI_SLOPE) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o1[j] = v0[j] * (ax[j] > 0.f ? 1.f : p.alpha);
+            for (int j = 0; j < 16; ++j) o1[j] = v0[j] * (ax[j] > 0.f ? 1.f : alpha);
           } else {
             write2 = p.out2 != nullptr;
 #pragma unroll

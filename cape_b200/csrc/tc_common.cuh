@@ -33,6 +33,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > SPIN_LIMIT) __trap();
   }
 }
+// One leader lane of a fully converged warp.  The tcgen05 / TMA issue loops run on ALL 32 lanes (every value they compute
+// is warp-uniform, so it lives in uniform registers) and only the instruction itself sits under this predicate: issued
+// from an `if (lane == 0)` region instead, every UTCHMMA / UTMALDG is wrapped by the compiler in an ELECT / R2UR.BROADCAST /
+// BRA.U.ANY loop (~10 issue slots per MMA on the one thread the tensor pipe depends on).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
