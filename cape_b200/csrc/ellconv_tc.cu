@@ -362,18 +362,22 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
       }
-      mbar_wait(bar_tfull + 8 * buf, use & 1);
-      tc_fence_after();
-      const uint32_t taddr_row = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quad * 32) << 16);
       const size_t orow = (size_t)R * p.ncols;
-      // backward epilogues read the saved activation (aux): fetch it one column group ahead, the loads are row-strided
-      // (one row per lane) and their latency would otherwise sit in front of every group
+      // backward epilogues read the saved activation (aux), written a whole forward pass ago: while the MMAs of this
+      // tile run, pull this lane's row into L2 and start the first column group's loads; inside the loop the loads are
+      // fetched one column group ahead (they are row-strided, one row per lane)
       const bool use_aux = valid && (p.epilogue == CAPE_EPI_SLOPE || p.epilogue == CAPE_EPI_DUALMASK);
+      const float* bias_row = p.bias != nullptr ? p.bias + (p.bias_per_row ? (size_t)r * p.ncols : 0) : nullptr;
+      const bool bias_vec = (reinterpret_cast<uintptr_t>(bias_row) & 15u) == 0;
       float4 axn[4];
       if (use_aux) {
+        for (int c = 0; c < p.ncols; c += 32) tc::prefetch_l2(p.aux + orow + c);
 #pragma unroll
         for (int j = 0; j < 4; ++j) axn[j] = ldg4(p.aux + orow + 4 * j);
       }
+      mbar_wait(bar_tfull + 8 * buf, use & 1);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
       for (int c0 = 0; c0 < p.ncols; c0 += 16) {
         float v0[16], v1[16];
@@ -404,14 +408,7 @@ __global__ void __launch_bounds__(TC_THREADS3, 1) ellconv_tc_kernel(const __grid
         float o1[16], o2[16];
         bool write2 = false;
         if (p.epilogue == CAPE_EPI_LINEAR) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float v = v0[j];
-            if (p.bias != nullptr) v += __ldg(p.bias + (p.bias_per_row ? (size_t)r * p.ncols : 0) + c0 + j);
-            if (p.act == CAPE_ACT_LEAKY) v = v > 0.f ? v : p.alpha * v;
-            else if (p.act == CAPE_ACT_RELU) v = fmaxf(v, 0.f);
-            o1[j] = v;
-          }
+          tc::bias_act16(v0, o1, bias_row != nullptr ? bias_row + c0 : nullptr, bias_vec, p.act, p.alpha);
         } else if (p.epilogue == CAPE_EPI_AFFINE) {
           write2 = p.out2 != nullptr;
 #pragma unroll
@@ -599,6 +596,15 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 2) ellconv_tc2_kernel(const _
     const int l8 = tid & 7, rs = tid >> 3;       // 8 lanes per 128-byte row, 32 row slots
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
+    if (p.epilogue == CAPE_EPI_SLOPE || p.epilogue == CAPE_EPI_DUALMASK) {
+      // the epilogue (these same warps, after the reduction) reads the saved activation of its row, written a whole
+      // forward pass ago: pull this lane's half row into L2 now
+      const int erow = (warp & 3) * 32 + lane, cpw = p.ncols >> 1;
+      if (s_n[erow] >= 0) {
+        const float* ap = p.aux + (size_t)(row0 + erow) * p.ncols + (warp >> 2) * cpw;
+        for (int c = 0; c < cpw; c += 32) tc::prefetch_l2(ap + c);
+      }
+    }
     for (int t = 0; t < p.nterms; ++t) {
       const TermDev& tm = p.terms[t];
       const bool has2 = DUAL && tm.w2T != nullptr;
@@ -699,6 +705,8 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 2) ellconv_tc2_kernel(const _
     // backward epilogues read the saved activation (aux): first column group before waiting for the MMAs, then one
     // group ahead (row-strided loads, one row per lane: their latency would sit in front of every group)
     const bool use_aux = n >= 0 && (p.epilogue == CAPE_EPI_SLOPE || p.epilogue == CAPE_EPI_DUALMASK);
+    const float* bias_row = p.bias != nullptr ? p.bias + (p.bias_per_row ? (size_t)r * p.ncols : 0) : nullptr;
+    const bool bias_vec = (reinterpret_cast<uintptr_t>(bias_row) & 15u) == 0;
     float4 axn[4];
     if (use_aux) {
 #pragma unroll
@@ -737,14 +745,7 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 2) ellconv_tc2_kernel(const _
       float o1[16], o2[16];
       bool write2 = false;
       if (p.epilogue == CAPE_EPI_LINEAR) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v = v0[j];
-          if (p.bias != nullptr) v += __ldg(p.bias + (p.bias_per_row ? (size_t)r * p.ncols : 0) + c0 + j);
-          if (p.act == CAPE_ACT_LEAKY) v = v > 0.f ? v : p.alpha * v;
-          else if (p.act == CAPE_ACT_RELU) v = fmaxf(v, 0.f);
-          o1[j] = v;
-        }
+        tc::bias_act16(v0, o1, bias_row != nullptr ? bias_row + c0 : nullptr, bias_vec, p.act, p.alpha);
       } else if (p.epilogue == CAPE_EPI_AFFINE) {
         write2 = p.out2 != nullptr;
 #pragma unroll

@@ -51,6 +51,7 @@ constexpr int G_SMEM_LIMIT = 227 * 1024;
 struct GMaps {
   CUtensorMap a[G_TERMS];      // source rows of term t: boxes of 32 f x 128 rows
   CUtensorMap bh[G_TERMS];     // K-major weight copy (raw fp32 = hi operand): boxes of 32 f x BN columns
+  CUtensorMap bl[G_TERMS];     // its tf32 low part (cape_term.wT_lo), when every term has one
 };
 
 struct GPlan {
@@ -58,6 +59,8 @@ struct GPlan {
   int nchain, corr, nbuf, tmem_cols;   // main accumulators per group, 1 = separate correction accumulator, TMEM buffers
   int sr, sl, sbr, sbl;                // ring depths: A raw (TMA), A lo (converters), B raw (TMA), B lo (converters)
   int rotate;                          // 1: every row tile starts its reduction at a different chunk (see chunk_of)
+  int blo_tma;                         // 1: the weight lo tiles come by TMA from the pre-split copy (one B ring pair, depth
+                                       // sbr, one full/empty barrier pair); 0: the converters derive them from the raw tiles
 };
 
 __device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {     // K-major SWIZZLE_128B operand tile
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
           phr ^= 1u << sr; phl ^= 1u << sl;
           if (++sr == g.sr) sr = 0;
           if (++sl == g.sl) sl = 0;
-          for (int s = 0; s < nsub; ++s) {
+          for (int s = 0; s < (g.blo_tma ? 0 : nsub); ++s) {
             mbar_wait(bar_bf + 8 * sbr, (phb >> sbr) & 1u);
             mbar_wait(bar_ble + 8 * sbl, ((phbl >> sbl) & 1u) ^ 1u);
             const char* hi = braw_ring + (size_t)sbr * B_TILE;
@@ -223,8 +226,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
             for (int s = 0; s < nsub; ++s) {
               mbar_wait(bar_be + 8 * sb, ((phb >> sb) & 1u) ^ 1u);
               if (elect_one()) {
-                mbar_arrive_expect_tx(bar_bf + 8 * sb, (uint32_t)B_TILE);
+                mbar_arrive_expect_tx(bar_bf + 8 * sb, (uint32_t)(g.blo_tma ? 2 * B_TILE : B_TILE));
                 tma_load_2d(smem_u32(braw_ring + (size_t)sb * B_TILE), &maps.bh[t], f0, col0 + s * BN, bar_bf + 8 * sb);
+                if (g.blo_tma)
+                  tma_load_2d(smem_u32(blo_ring + (size_t)sb * B_TILE), &maps.bl[t], f0, col0 + s * BN, bar_bf + 8 * sb);
               }
               __syncwarp();
               phb ^= 1u << sb;
@@ -268,11 +273,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
             for (int s = 0; s < nsub; ++s) {
               // the last sub-tile of a group may be narrower: N = its real columns (ncols % 16 == 0)
               const uint32_t idesc = idesc0 | ((uint32_t)(min(BN, gcols - s * BN) >> 3) << 17);
-              mbar_wait(bar_bf + 8 * sbr, (phb >> sbr) & 1u);      // TMA bytes of the raw weight tile
-              mbar_wait(bar_blf + 8 * sbl, (phbl >> sbl) & 1u);    // its lo tile
+              mbar_wait(bar_bf + 8 * sbr, (phb >> sbr) & 1u);      // TMA bytes of the raw weight tile (and of its lo tile)
+              if (!g.blo_tma) mbar_wait(bar_blf + 8 * sbl, (phbl >> sbl) & 1u);    // lo tile from the converters
               tc_fence_after();
               const uint64_t b_hi = make_desc_k(smem_u32(braw_ring + (size_t)sbr * B_TILE));
-              const uint64_t b_lo = make_desc_k(smem_u32(blo_ring + (size_t)sbl * B_TILE));
+              const uint64_t b_lo = make_desc_k(smem_u32(blo_ring + (size_t)(g.blo_tma ? sbr : sbl) * B_TILE));
               const uint32_t d0 = tb + (uint32_t)(s * BN);
               if (elect_one()) {
 #pragma unroll
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
                   }
                 }
                 umma_commit(bar_be + 8 * sbr);
-                umma_commit(bar_ble + 8 * sbl);
+                if (!g.blo_tma) umma_commit(bar_ble + 8 * sbl);
                 if (s == nsub - 1) {                              // last sub-tile: the A tiles of this chunk are free too
                   umma_commit(bar_re + 8 * sr);
                   umma_commit(bar_le + 8 * sl);
@@ -349,8 +354,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
         }
         asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
       }
-      mbar_wait(bar_tf + 8 * buf, use & 1u);
-      tc_fence_after();
       const uint32_t taddr_row = tmem_base + (uint32_t)(buf * g.gw * nacc) + ((uint32_t)(quad * 32) << 16);
       const size_t orow = (size_t)R * p.ncols + col0;
       const bool use_aux = valid && (p.epilogue == CAPE_EPI_SLOPE || p.epilogue == CAPE_EPI_DUALMASK);
@@ -360,10 +363,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
       const float* bias_row = (linear && p.bias != nullptr) ? p.bias + (p.bias_per_row ? (size_t)r * p.ncols : 0) + col0 : nullptr;
       const bool bias_vec = bias_row != nullptr && (reinterpret_cast<uintptr_t>(bias_row) & 15u) == 0;
       float4 axn[4];
-      if (use_aux) {
+      if (use_aux) {           // saved activation of this lane's row: into L2 and the first group on its way while the MMAs run
+        for (int c = 0; c < gcols; c += 32) prefetch_l2(p.aux + orow + c);
 #pragma unroll
         for (int j = 0; j < 4; ++j) axn[j] = ldg4(p.aux + orow + 4 * j);
       }
+      mbar_wait(bar_tf + 8 * buf, use & 1u);
+      tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < gcols; c0 += 16) {
         float v0[16];
@@ -490,8 +496,21 @@ int launch_gemm(const cape_topology* t, const ConvParams& p, const GMaps& maps, 
   if (g.sr < 2) return 0;
   if (g.sr > sr_want) g.sr = sr_want;
   left -= g.sr * G_A_TILE;
-  while (g.sbr < G_MAX_STAGES && left >= B_TILE) { ++g.sbr; left -= B_TILE; }
+  if (g.blo_tma) {                     // raw and lo weight tiles travel together: equal depths
+    while (g.sbr < 4 && left >= 2 * B_TILE) { ++g.sbr; left -= 2 * B_TILE; }
+    g.sbl = g.sbr;
+  } else {
+    while (g.sbr < G_MAX_STAGES && left >= B_TILE) { ++g.sbr; left -= B_TILE; }
+  }
   while (g.sr < G_MAX_STAGES && left >= G_A_TILE) { ++g.sr; left -= G_A_TILE; }
+  if (g_tuning[11] > 0 || g_tuning[12] > 0 || g_tuning[13] > 0 || g_tuning[14] > 0) {    // experiment knobs: ring depths
+    const int sl = g_tuning[11] > 0 ? g_tuning[11] : g.sl, sbl = g_tuning[12] > 0 ? g_tuning[12] : g.sbl;
+    const int sr = g_tuning[13] > 0 ? g_tuning[13] : g.sr, sbr = g_tuning[14] > 0 ? g_tuning[14] : g.sbr;
+    if (!g.blo_tma && sl >= 2 && sbl >= 2 && sr >= 2 && sbr >= 2 && sl <= G_MAX_STAGES && sbl <= G_MAX_STAGES && sr <= G_MAX_STAGES &&
+        sbr <= G_MAX_STAGES && fixed + (sr + sl) * G_A_TILE + (sbr + sbl) * B_TILE <= G_SMEM_LIMIT) {
+      g.sl = sl; g.sbl = sbl; g.sr = sr; g.sbr = sbr;
+    }
+  }
   const int smem = fixed + (g.sr + g.sl) * G_A_TILE + (g.sbr + g.sbl) * B_TILE;
   static bool configured = false;
   if (!configured) {
@@ -553,11 +572,15 @@ int launch_gemm_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaS
       if (p.slot_acc[s] != 0) return 0;
   }
   static GMaps maps;
+  g.blo_tma = g_tuning[15] != 1;        // experiment knob 15 = 1: converters derive the weight lo tiles
   for (int i = 0; i < p.nterms; ++i) {
     const TermDev& tm = p.terms[i];
     if (!make_map(&maps.a[i], tm.src, (unsigned long long)tm.F, (unsigned long long)p.total_rows, tm.src_stride, BM) ||
         !make_map(&maps.bh[i], tm.wT, (unsigned long long)tm.F, (unsigned long long)p.ncols, tm.wT_stride, BN))
       return 0;
+    if (tm.wT_lo == nullptr || !aligned16(tm.wT_lo) ||
+        !make_map(&maps.bl[i], tm.wT_lo, (unsigned long long)tm.F, (unsigned long long)p.ncols, tm.wT_stride, BN))
+      g.blo_tma = 0;
   }
   if (p.precise) {
     if (BN == 128) return launch_gemm<128, true>(t, p, maps, g, st);

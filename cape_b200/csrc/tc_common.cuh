@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <stdint.h>
+#include "../../include/cape_b200.h"
 
 namespace cape {
 namespace tc {
@@ -42,6 +43,7 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -119,6 +121,34 @@ __device__ __forceinline__ void split_store_rn(float4 v, char* hi_tile, char* lo
 // 32-bit operands: 32-element MN blocks of 4096 B (LBO), 4-row K groups of 512 B (SBO), 128-byte rows whose 32-byte
 // chunks are XOR-ed with (row & 3)  [cute Layout_MN_SW128_32B_Atom, Swizzle<2,5,2>].  A TMA box of 32 floats x 32 rows
 // with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes exactly one such MN block.
+// LINEAR epilogue of 16 output columns of one row: bias (four 16-byte loads when the pointer allows it: a bias can be a
+// 4-byte-aligned view into a flat parameter buffer) and the activation, chosen once per call instead of per element.
+__device__ __forceinline__ void bias_act16(float (&v)[16], float (&o)[16], const float* bias, bool bias_vec, int act,
+                                           float alpha) {
+  if (bias != nullptr) {
+    if (bias_vec) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + j));
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + j);
+    }
+  }
+  if (act == CAPE_ACT_LEAKY) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = v[j] > 0.f ? v[j] : alpha * v[j];
+  } else if (act == CAPE_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = fmaxf(v[j], 0.f);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = v[j];
+  }
+}
+
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
          (1ull << 46) | (1ull << 61);

@@ -1,8 +1,14 @@
 #!/bin/bash
-# A/B benches on one box: each argument is "ENV=.. ENV=..|bench args"; prints meshes/s for each
+# A/B runs of bench.py over experiment knobs (cape_set_tuning): usage tools/gpu_ab.sh "<tune1>" "<tune2>" ...  ("-" = defaults)
 mkdir -p gpurun_out
-for spec in "$@"; do
-  envs="${spec%%|*}"; args="${spec#*|}"
-  r=$(env $envs timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-profile $args 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('%.1f meshes/s  %.3f ms' % (d['value'], d['ms_per_step']))" 2>&1 | tail -1)
-  echo "[$envs|$args] $r"
+for t in "$@"; do
+  arg=""; [ "$t" != "-" ] && arg="--tune $t"
+  echo "== tune $t"
+  timeout 300 python bench.py --config ${CFG:-c3} --steps 20 --warmup 5 --no-cpu-baseline --no-profile $arg 2>/dev/null | python -c "
+import sys,json
+for l in sys.stdin:
+    try: b=json.loads(l)
+    except Exception: continue
+    print('   ms_per_step %.3f  value %.1f  loss %s' % (b['ms_per_step'], b['value'], {k: round(v,4) for k,v in b.get('loss',{}).items()}))
+"
 done
