@@ -139,8 +139,12 @@ __global__ void bce_kernel(const float* __restrict__ logits, long long n, float 
   if (threadIdx.x == 0 && loss) atomicAdd(loss, tot);
 }
 
-__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* out) {
+// Deterministic: block partial sums go to a scratch array and the LAST block to finish adds them up in index order, so
+// the global norm (and with it the clip factor of the update) is bit-identical on every data-parallel replica and in
+// every run -- a float atomicAdd per block is not, and replicas that clip would drift apart by an ulp per step.
+__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* out, float* partials, unsigned int* counter) {
   __shared__ float red[8];
+  __shared__ bool last;
   float s = 0.f;
   const long long n4 = n / 4;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -152,7 +156,21 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* ou
        i += (long long)gridDim.x * blockDim.x)
     s += g[i] * g[i];
   const float tot = block_sum(s, red);
-  if (threadIdx.x == 0) atomicAdd(out, tot);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = tot;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.f;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) t += __ldcg(partials + i);
+  const float all = block_sum(t, red);
+  if (threadIdx.x == 0) {
+    *out += all;
+    *counter = 0;
+  }
 }
 
 __global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ mom, long long n,
@@ -341,7 +359,19 @@ extern "C" int cape_bce_logits(const float* logits, int64_t n, float label, floa
 extern "C" int cape_sumsq(const float* g, int64_t n, float* sumsq, void* stream) {
   CAPE_REQUIRE(g && sumsq && n > 0, "bad arguments");
   CAPE_REQUIRE(aligned16(g), "g must be 16-byte aligned");
-  sumsq_kernel<<<blocks_for(n / 4 + 1, 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(g, n, sumsq);
+  // per-device scratch of the deterministic reduction (block partials + a ticket counter), allocated by the first call on
+  // a device: make that call outside stream capture.  Calls on one device must not overlap (same stream, or ordered).
+  constexpr int MAX_BLOCKS = 148 * 4;
+  static float* scratch[64] = {nullptr};
+  int dev = 0;
+  CAPE_CHECK_CUDA(cudaGetDevice(&dev));
+  CAPE_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+  if (scratch[dev] == nullptr) {
+    CAPE_CHECK_CUDA(cudaMalloc(&scratch[dev], (MAX_BLOCKS + 1) * sizeof(float)));
+    CAPE_CHECK_CUDA(cudaMemset(scratch[dev], 0, (MAX_BLOCKS + 1) * sizeof(float)));
+  }
+  sumsq_kernel<<<blocks_for(n / 4 + 1, 256, MAX_BLOCKS), 256, 0, (cudaStream_t)stream>>>(
+      g, n, sumsq, scratch[dev] + 1, reinterpret_cast<unsigned int*>(scratch[dev]));
   CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
   return 0;

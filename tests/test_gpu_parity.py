@@ -197,3 +197,21 @@ def test_size_independent_properties(hierarchy, cfg):
     torch.cuda.synchronize()
     d = float((net.PG.grad - g_eager).abs().max() / g_eager.abs().max())
     assert d < 1e-5, d
+
+
+def test_global_norm_is_deterministic():
+    """cape_sumsq reduces in a fixed order: the clip factor of the update must be bit-identical on every data-parallel
+    replica (and in every run), otherwise replicas that clip drift apart by an ulp per step."""
+    import ctypes as C
+    from cape_b200 import _lib
+    lib = _lib.load()
+    g = torch.randn(16_285_668, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)) * 0.01
+    out = torch.zeros(8, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for i in range(8):
+        _lib.check(lib.cape_sumsq(C.c_void_p(g.data_ptr()), g.numel(), C.c_void_p(out[i:].data_ptr()), st))
+    torch.cuda.synchronize()
+    v = out.cpu().numpy()
+    assert (v == v[0]).all(), v
+    ref = float((g.double() ** 2).sum())
+    assert abs(float(v[0]) - ref) < 1e-5 * ref
