@@ -142,7 +142,13 @@ __global__ void bce_kernel(const float* __restrict__ logits, long long n, float 
 // Deterministic: block partial sums go to a scratch array and the LAST block to finish adds them up in index order, so
 // the global norm (and with it the clip factor of the update) is bit-identical on every data-parallel replica and in
 // every run -- a float atomicAdd per block is not, and replicas that clip would drift apart by an ulp per step.
-__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* out, float* partials, unsigned int* counter) {
+constexpr int SUMSQ_MAX_BLOCKS = 148 * 4;
+__device__ float g_sumsq_partials[SUMSQ_MAX_BLOCKS];
+__device__ unsigned int g_sumsq_counter = 0;
+
+__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* out) {
+  float* partials = g_sumsq_partials;
+  unsigned int* counter = &g_sumsq_counter;
   __shared__ float red[8];
   __shared__ bool last;
   float s = 0.f;
@@ -359,19 +365,9 @@ extern "C" int cape_bce_logits(const float* logits, int64_t n, float label, floa
 extern "C" int cape_sumsq(const float* g, int64_t n, float* sumsq, void* stream) {
   CAPE_REQUIRE(g && sumsq && n > 0, "bad arguments");
   CAPE_REQUIRE(aligned16(g), "g must be 16-byte aligned");
-  // per-device scratch of the deterministic reduction (block partials + a ticket counter), allocated by the first call on
-  // a device: make that call outside stream capture.  Calls on one device must not overlap (same stream, or ordered).
-  constexpr int MAX_BLOCKS = 148 * 4;
-  static float* scratch[64] = {nullptr};
-  int dev = 0;
-  CAPE_CHECK_CUDA(cudaGetDevice(&dev));
-  CAPE_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
-  if (scratch[dev] == nullptr) {
-    CAPE_CHECK_CUDA(cudaMalloc(&scratch[dev], (MAX_BLOCKS + 1) * sizeof(float)));
-    CAPE_CHECK_CUDA(cudaMemset(scratch[dev], 0, (MAX_BLOCKS + 1) * sizeof(float)));
-  }
-  sumsq_kernel<<<blocks_for(n / 4 + 1, 256, MAX_BLOCKS), 256, 0, (cudaStream_t)stream>>>(
-      g, n, sumsq, scratch[dev] + 1, reinterpret_cast<unsigned int*>(scratch[dev]));
+  // scratch of the deterministic reduction: module-scope device variables (one copy per device, nothing to allocate, so the
+  // call is capturable from the start).  Calls on one device must not overlap (same stream, or ordered).
+  sumsq_kernel<<<blocks_for(n / 4 + 1, 256, SUMSQ_MAX_BLOCKS), 256, 0, (cudaStream_t)stream>>>(g, n, sumsq);
   CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
   return 0;

@@ -1085,13 +1085,14 @@ class CapeNetwork:
 
     # ---- data parallelism: bucketed gradient all-reduce overlapped with the backward pass -------------------------
     def set_data_parallel(self, world):
-        """EXPERIMENTAL (opt-in; the default data-parallel step all-reduces the two flat gradient buffers between the two
-        graphs: `train_step(allreduce=...)`): its first two-GPU run failed and the GPU budget of the round did not allow
-        debugging it.  One process per GPU, batch sharded.  The flat generator gradient buffer is all-reduced in three
-        buckets as soon as each is final -- decoder (+ the discriminator's buffer) after the decoder backward, the two
-        28 MB encoder FC kernels right after their weight gradients, the encoder convs / condition nets at the end --
-        on a communication stream that the backward pass does not wait for until its very end; the NCCL calls sit inside
-        the captured forward/backward graph.  world <= 1 switches it off."""
+        """Opt-in (the default data-parallel step all-reduces the two flat gradient buffers between the two graphs:
+        `train_step(allreduce=...)`).  One process per GPU, batch sharded.  The flat generator gradient
+        buffer is all-reduced in three buckets as soon as each is final -- decoder (+ the discriminator's buffer) after
+        the decoder backward, the two 28 MB encoder FC kernels right after their weight gradients, the encoder convs /
+        condition nets at the end -- on a communication stream that the backward pass does not wait for until its very
+        end.  Verified eagerly on two B200s (replicas bit-identical, gradients of the global batch); captured inside the
+        forward/backward graph the step also completes, but destroying the process group afterwards hung in the one
+        run the budget allowed, so `bench.py` and `CAPE.fit` keep the default.  world <= 1 switches it off."""
         if world <= 1:
             self.dp = None
             return

@@ -296,8 +296,7 @@ int cape_bce_logits(const float* logits, int64_t n, float label, float scale, fl
 
 /* ---- optimiser (CAPE.training, lib/models.py:419-474) -----------------------------------------------
  * sumsq[0] += sum(g^2) (zero it first), reduced in a fixed order: bit-identical on every replica and in every run
- * (uses a small per-device scratch allocated by the first call on that device: make one call before capturing a
- * CUDA graph; calls on one device must be ordered);  then
+ * (calls on one device must be ordered: they share a small scratch in device memory);  then
  * coef = clip / max(sqrt(sumsq), clip) (tf.clip_by_global_norm), a = momentum*a + coef*g, w -= lr*a
  * (tf.train.MomentumOptimizer, non-Nesterov).  lr is read from device memory (no host sync). */
 int cape_sumsq(const float* g, int64_t n, float* sumsq, void* stream);

@@ -1,7 +1,8 @@
 """Data parallelism on real GPUs (skipped with fewer than two): every rank ends up with the gradients of the GLOBAL
-batch -- with the default all-reduce between the two step graphs, and (opt-in, CAPE_TEST_DP_OVERLAP=1: the first
-two-GPU run of it failed and there was no GPU budget left to debug it) with the bucketed all-reduce inside the step
-(CapeNetwork.set_data_parallel)."""
+batch and replicas stay bit-identical -- with the default all-reduce between the two step graphs (eager and
+graph-replayed), and with the bucketed all-reduce inside the step (CapeNetwork.set_data_parallel; opt-in:
+CAPE_TEST_DP_OVERLAP=eager runs it eagerly -- verified on two B200s --, =1 also graph-replayed: that step completes
+and returns its results, but tearing the process group down afterwards hangs, so it stays off by default)."""
 import os
 import socket
 import sys
@@ -23,6 +24,15 @@ def _free_port():
 
 
 def _worker(rank, world, port, use_graph, overlap, q):
+    try:
+        _worker_body(rank, world, port, use_graph, overlap, q)
+    except BaseException as e:          # the parent must not wait for a result that will never come
+        import traceback
+        q.put((rank, {"error": "".join(traceback.format_exception(type(e), e, e.__traceback__))[-3000:]}))
+        os._exit(1)                     # a peer may be blocked in a collective: do not wait for NCCL teardown
+
+
+def _worker_body(rank, world, port, use_graph, overlap, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
@@ -83,10 +93,19 @@ def test_data_parallel_step_equals_global_batch(use_graph, overlap):
     procs = [ctx.Process(target=_worker, args=(r, world, port, use_graph, overlap, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=300) for _ in range(world))
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    res = {}
+    try:
+        for _ in range(world):
+            rank, out = q.get(timeout=240)
+            res[rank] = out
+            assert "error" not in out, "rank %d failed:\n%s" % (rank, out["error"])
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:                 # never leave a rank behind (it would hold its GPU until the box is recycled)
+            if p.is_alive():
+                p.kill()
     rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
     r0, r1 = res[0], res[1]
     assert np.array_equal(r0["gg"], r1["gg"]) and np.array_equal(r0["pg"], r1["pg"])     # replicas stay identical
