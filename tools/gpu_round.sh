@@ -6,6 +6,7 @@ nvidia-smi -L | head -1
 if [ "$1" != "nopytest" ]; then
 echo "== pytest -m gpu"; timeout 2400 python -m pytest tests -q -m gpu 2>&1 | tail -8 > gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
 fi
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 for c in c3 c2 c5; do
   echo "== bench $c"; timeout 900 python bench.py --config $c --steps 20 --warmup 5 2> gpurun_out/bench_$c.err > gpurun_out/bench_$c.json; cut -c1-260 gpurun_out/bench_$c.json
 done
