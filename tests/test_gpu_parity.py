@@ -40,6 +40,20 @@ def test_plain_operand_kernel(hierarchy):
     _assert_all(parity.plain_operand_cases(hierarchy))
 
 
+def test_plain_operand_kernel_without_presplit_weights(hierarchy):
+    """Same calls with experiment knob 15: the weight lo tiles derived on chip by the converter warps (the path a caller
+    takes who passes no cape_term.wT_lo) instead of fetched by TMA from the pre-split copy; plus the precise mode."""
+    from cape_b200 import _lib
+    lib = _lib.load()
+    prev = lib.cape_set_tuning(15, 1)
+    try:
+        _assert_all(parity.plain_operand_cases(hierarchy))
+        res = parity.precise_vs_truth(hierarchy)
+        assert res["precise L8 1024->512 (max-rel vs fp64)"] < 4e-6, res
+    finally:
+        lib.cape_set_tuning(15, prev)
+
+
 def test_precise_accumulation(hierarchy):
     """cape_conv_args.precise: split tensor-core accumulation chains -- close to fp32 SIMT accuracy, and at least three
     times closer to the float64 truth than the single-chain default on a 1024-long reduction."""
