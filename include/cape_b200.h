@@ -166,8 +166,8 @@ int cape_apply(cape_topology* t, const cape_apply_args* a, void* stream);
  * 128- instead of 256-wide column sub-tiles in it, [4]=1 conv weight tiles by the producer warps instead of TMA,
  * [5]=1 one narrow-conv CTA per SM, [6]=1 identity-term basis tiles by the producer warps, [7]=1 thin-output layers
  * on the generic kernels, [8]=1 no TMA-fed plain-operand conv kernel, [9]=1 no reduction-order rotation in it,
- * [10]=rows per CTA of cape_apply (16..1024), [11..14]=its ring depths (A lo, weight lo, A raw, weight raw),
- * [15]=1 its weight lo tiles derived on chip instead of fetched from cape_term.wT_lo ([0] and [2] are diagnostics
+ * [10]=rows per CTA of cape_apply (16..1024), [15]=1 the plain-operand kernel derives its weight lo tiles on chip
+ * instead of fetching them from cape_term.wT_lo, [11..14]=its ring depths then (A lo, weight lo, A raw, weight raw) ([0] and [2] are diagnostics
  * of the operand split).  Returns the previous value, <0 for an unknown key. */
 int cape_set_tuning(int key, int value);
 
