@@ -159,19 +159,37 @@ __global__ void __launch_bounds__(256, 2) gemm_batch_kernel(const GemmParams* __
     gemm_tile(p, (tile / nt) * G_BM, (tile % nt) * G_BN, 0, p.K, 0, p.beta != 0.f ? 2 : 0, As, Bs);
 }
 
-__global__ void gemm_reduce_kernel(const __grid_constant__ GemmParams p) {
+// Sum of the split-K partials + epilogue.  The outputs that need a split are few (64 x 64 for the encoder's FC layers)
+// and the partials many (a few hundred), so the parallelism has to come from the split axis: 32 consecutive outputs x
+// 32 split lanes per CTA, every lane adds its partials in index order, the lanes are added in index order through
+// shared memory -- a fixed summation order (deterministic, bit-identical on every replica).
+constexpr int GR_EL = 32, GR_ZL = 32;
+__global__ void __launch_bounds__(GR_EL * GR_ZL) gemm_reduce_kernel(const __grid_constant__ GemmParams p) {
+  __shared__ float red[GR_ZL][GR_EL + 1];
   const long long total = (long long)p.M * p.N;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
+  const int el = threadIdx.x % GR_EL, zl = threadIdx.x / GR_EL;
+  for (long long e0 = (long long)blockIdx.x * GR_EL; e0 < total; e0 += (long long)gridDim.x * GR_EL) {
+    const long long e = e0 + el;
     float s = 0.f;
-    for (int z = 0; z < p.nsplit; ++z) s += p.ws[(size_t)z * total + e];
-    const int m = (int)(e / p.N), n = (int)(e % p.N);
-    float v = p.alpha * s;
-    if (p.bias) v += __ldg(p.bias + n);
-    v = apply_act(v, p.act, p.leaky);
-    float* o = p.c + (size_t)m * p.c_rs + n;
-    if (p.beta != 0.f) v += p.beta * (*o);
-    *o = v;
+    if (e < total) {
+#pragma unroll 4
+      for (int z = zl; z < p.nsplit; z += GR_ZL) s += p.ws[(size_t)z * total + e];
+    }
+    red[zl][el] = s;
+    __syncthreads();
+    if (zl == 0 && e < total) {
+      s = 0.f;
+#pragma unroll
+      for (int k = 0; k < GR_ZL; ++k) s += red[k][el];
+      const int m = (int)(e / p.N), n = (int)(e % p.N);
+      float v = p.alpha * s;
+      if (p.bias) v += __ldg(p.bias + n);
+      v = apply_act(v, p.act, p.leaky);
+      float* o = p.c + (size_t)m * p.c_rs + n;
+      if (p.beta != 0.f) v += p.beta * (*o);
+      *o = v;
+    }
+    __syncthreads();
   }
 }
 
@@ -195,7 +213,8 @@ extern "C" int cape_gemm(cape_topology* t, int M, int N, int K, const float* a, 
   const long long tiles = (long long)mt * nt;
   long long nsplit = 1;
   if (tiles < 2LL * t->sm_count) {
-    nsplit = (4LL * t->sm_count + tiles - 1) / tiles;
+    // one wave of CTAs (two are resident per SM): half the partials of the former two waves to write and re-read
+    nsplit = (2LL * t->sm_count + tiles - 1) / tiles;
     const long long max_by_k = (K + 127) / 128;
     if (nsplit > max_by_k) nsplit = max_by_k;
     const long long per = (long long)M * N * (long long)sizeof(float);
@@ -214,9 +233,9 @@ extern "C" int cape_gemm(cape_topology* t, int M, int N, int K, const float* a, 
   cape::count_launches(1);
   if (nsplit > 1) {
     const long long total = (long long)M * N;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 4 * t->sm_count) blocks = 4 * t->sm_count;
-    gemm_reduce_kernel<<<blocks, 256, 0, st>>>(p);
+    long long blocks = (total + GR_EL - 1) / GR_EL;
+    if (blocks > 8LL * t->sm_count) blocks = 8LL * t->sm_count;
+    gemm_reduce_kernel<<<(unsigned)blocks, GR_EL * GR_ZL, 0, st>>>(p);
     CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
   }

@@ -195,6 +195,27 @@ __global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, f
   }
 }
 
+// tf.train.AdamOptimizer (lib/models.py:449-451): m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g^2;
+// w -= lr_t m / (sqrt(v) + eps) with lr_t = lr sqrt(1 - b2^t) / (1 - b1^t) -- the caller puts lr_t in device memory
+__global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, const float* __restrict__ sumsq, float clip,
+                            const float* __restrict__ lr_dev, float beta1, float beta2, float eps) {
+  float coef = 1.f;
+  if (sumsq) {
+    const float norm = sqrtf(*sumsq);
+    coef = clip / fmaxf(norm, clip);
+  }
+  const float lr = *lr_dev;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = coef * g[i];
+    const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
+    const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    w[i] -= lr * mi / (sqrtf(vi) + eps);
+  }
+}
+
 __global__ void wtrans_kernel(const float* __restrict__ w, int Fin, int K, int Fout, float* __restrict__ wt,
                               float* __restrict__ wt_lo) {
   // tile transpose through shared memory: for each k, [Fin x Fout] -> [Fout x Fin]
@@ -378,6 +399,18 @@ extern "C" int cape_sgd_clip_update(float* w, const float* g, float* mom, int64_
   CAPE_REQUIRE(w && g && mom && lr_dev && n > 0, "bad arguments");
   sgd_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(w, g, mom, n, sumsq, clip_norm, lr_dev,
                                                                              momentum);
+  CAPE_CHECK_CUDA(cudaGetLastError());
+  cape::count_launches(1);
+  return 0;
+}
+
+extern "C" int cape_adam_clip_update(float* w, const float* g, float* m, float* v, int64_t n, const float* sumsq,
+                                     float clip_norm, const float* lr_t_dev, float beta1, float beta2, float eps,
+                                     void* stream) {
+  CAPE_REQUIRE(w && g && m && v && lr_t_dev && n > 0, "bad arguments");
+  CAPE_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps > 0.f, "bad Adam constants");
+  adam_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(w, g, m, v, n, sumsq, clip_norm, lr_t_dev,
+                                                                              beta1, beta2, eps);
   CAPE_CHECK_CUDA(cudaGetLastError());
   cape::count_launches(1);
   return 0;

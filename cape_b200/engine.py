@@ -268,6 +268,7 @@ class SmallGemmBatch:
     def __init__(self, tp):
         self.tp, self.pending, self.tables = tp, [], {}
         self.item_bytes = int(tp.lib.cape_gemm_item_bytes())
+        self.blocks_per_item = int(__import__("os").environ.get("CAPE_SMALL_BLOCKS", "64"))
 
     def add(self, A, B, Cout, alpha=1.0, beta=0.0):
         M, N, K, a_rs, a_cs, b_rs, b_cs = _gemm_strides(A, B, Cout)
@@ -288,7 +289,9 @@ class SmallGemmBatch:
             torch.cuda.synchronize()
             check(self.tp.lib.cape_gemm_batch(C.cast(arr, C.c_void_p), n, C.c_void_p(tab.data_ptr()), 0, _stream()))
             self.tables[key] = tab
-        check(self.tp.lib.cape_gemm_batch(None, n, C.c_void_p(tab.data_ptr()), 4, _stream()))
+        # blocks per item: the one wide product of a step (per-vertex output bias: [1 x N] @ [N x 20670], 323 column
+        # tiles) sets the length of the launch; blocks beyond an item's tile count exit at once
+        check(self.tp.lib.cape_gemm_batch(None, n, C.c_void_p(tab.data_ptr()), self.blocks_per_item, _stream()))
         self.pending = []
 
 

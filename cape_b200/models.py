@@ -103,6 +103,10 @@ class CAPE(object):
         vals = self.net.get_params()
         mom = {"momentum/" + k: v for k, v in {**self.net.PG.export(self.net.PG.mom),
                                                 **self.net.PD.export(self.net.PD.mom)}.items()}
+        if self.net.adam:            # second-moment slots and the application count (TF: beta1_power = 0.9 ** (t + 1))
+            mom.update({"adam_v/" + k: v for k, v in {**self.net.PG.export(self.net.PG.var),
+                                                       **self.net.PD.export(self.net.PD.var)}.items()})
+            mom["adam_t"] = np.int64(self.net.adam_t)
         fn = os.path.join(path, "model-%d.npz" % step)
         np.savez(fn, global_step=np.int64(self.global_step), **vals, **mom)
         return fn
@@ -114,8 +118,17 @@ class CAPE(object):
         from . import tf_checkpoint
         path = self._get_path(self.checkpoint_dir)
         vals = dict(self.net.get_params())
+        slot = "/Adam" if self.net.adam else "/Momentum"     # slot names of tf.train.AdamOptimizer / MomentumOptimizer
         for k, v in {**self.net.PG.export(self.net.PG.mom), **self.net.PD.export(self.net.PD.mom)}.items():
-            vals[k + "/Momentum"] = v
+            vals[k + slot] = v
+        if self.net.adam:
+            from .network import ADAM_BETA1, ADAM_BETA2
+            for k, v in {**self.net.PG.export(self.net.PG.var), **self.net.PD.export(self.net.PD.var)}.items():
+                vals[k + "/Adam_1"] = v
+            t1 = self.net.adam_t + 1
+            for sfx in ("", "_1"):                           # opt_g's and opt_d's non-slot variables
+                vals["beta1_power" + sfx] = np.asarray(ADAM_BETA1 ** t1, np.float32)
+                vals["beta2_power" + sfx] = np.asarray(ADAM_BETA2 ** t1, np.float32)
         vals["global_step"] = np.asarray(self.global_step, np.int64)
         return tf_checkpoint.write_checkpoint(os.path.join(path, "model.ckpt-%d" % step), vals)
 
@@ -134,12 +147,20 @@ class CAPE(object):
                 filename = tf_checkpoint.latest_checkpoint(path) if os.path.isdir(path) else None
             if filename is None:
                 raise FileNotFoundError("no checkpoint under %s" % path)
+        adam = self.net.adam
         if tf_checkpoint.is_checkpoint(filename):
             z = tf_checkpoint.read_checkpoint(filename)
-            files, mom_key = list(z), (lambda n: n + "/Momentum")
+            files, mom_key = list(z), (lambda n: n + ("/Adam" if adam else "/Momentum"))
+            var_key = lambda n: n + "/Adam_1"
+            if adam and "beta1_power" in files:
+                from .network import ADAM_BETA1
+                self.net.adam_t = max(int(round(np.log(float(z["beta1_power"])) / np.log(ADAM_BETA1))) - 1, 0)
         else:
             z = np.load(filename)
             files, mom_key = z.files, (lambda n: "momentum/" + n)
+            var_key = lambda n: "adam_v/" + n
+            if adam and "adam_t" in files:
+                self.net.adam_t = int(z["adam_t"])
         want = set(self.net.PG.names) | set(self.net.PD.names)
         missing = sorted(want - set(files))
         if missing:
@@ -150,6 +171,8 @@ class CAPE(object):
             for n in P.names:
                 if mom_key(n) in files:
                     P._view(P.mom, n).copy_(torch.as_tensor(np.asarray(z[mom_key(n)], np.float32).reshape(-1)))
+                if adam and var_key(n) in files:
+                    P._view(P.var, n).copy_(torch.as_tensor(np.asarray(z[var_key(n)], np.float32).reshape(-1)))
         self.global_step = int(z["global_step"]) if "global_step" in files else 0
         self._weights_source = "checkpoint"
         return filename

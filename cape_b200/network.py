@@ -20,6 +20,9 @@ from .engine import (ACT_LEAKY, ACT_NONE, EPI_AFFINE, EPI_DUALMASK, EPI_LINEAR, 
 from .params import init_params, is_d_param, is_g_param, param_specs
 
 
+ADAM_BETA1, ADAM_BETA2, ADAM_EPS = 0.9, 0.999, 1e-8      # tf.train.AdamOptimizer defaults (TF 1.13), lib/models.py:450-451
+
+
 def _pad4(n):
     return (n + 3) // 4 * 4
 
@@ -40,6 +43,11 @@ class ParamStore:
         self.grad = torch.zeros(self.size, device=device)
         self.mom = torch.zeros(self.size, device=device)
         self.lo = torch.zeros(self.size, device=device)     # flat - tf32_trunc(flat): weight tiles by TMA (3xTF32)
+        self.var = None                                     # Adam's second-moment slot (`mom` is its first): add_adam_slot()
+
+    def add_adam_slot(self):
+        if self.var is None:
+            self.var = torch.zeros(self.size, device=self.flat.device)
 
     def lo_of(self, t):
         """The view of `lo` that corresponds to `t`, a contiguous view of `flat`; None if t is not one."""
@@ -357,7 +365,9 @@ class ChebLayer:
             cs = self.net.arena.get(self.cs_id[cs_slot])[:N]
             nops = len(self.cs_ops)
             if nops <= 4:
-                colsum(tp, g, N, s.rows_out, Fout, self.cs_ops, cs)
+                # the column sums feed nothing but the deferred small products: next to the weight gradients on the side
+                # stream (they read the same gradient tensor), always through the main handle (it owns the row sums)
+                self.net.run_glue(lambda: colsum(tp, g, N, s.rows_out, Fout, self.cs_ops, cs))
             else:
                 for o in range(0, nops, 4):
                     self._colsum_chunk(g, N, cs, o)
@@ -373,7 +383,7 @@ class ChebLayer:
                         sg(dq, self.W3[F:, k, :].t(), dycat, beta=1.0)
         if self.affine and C:
             csa = self.net.arena.get(self.csa_id)[:N]
-            colsum(tp, g_aff, N, s.rows_out, Fout, [s.ops[0]], csa)
+            self.net.run_glue(lambda: colsum(tp, g_aff, N, s.rows_out, Fout, [s.ops[0]], csa))
             if want_dw:
                 self.net.small.add(ycat.t(), csa[:, 0, :], self.gWa2[F:])
             if dycat is not None:
@@ -583,8 +593,11 @@ class CapeNetwork:
         if c["use_res_block"] or not c["use_res_block_dec"] or c["cond_encoder"] or c["reduce_dim"] <= 0:
             raise NotImplementedError("only the shipped-config architecture is built: use_res_block=0, "
                                       "use_res_block_dec=1, cond_encoder=0, reduce_dim>0")
-        if c["optimizer"] != "sgd" or c["loss"] != "l1":
-            raise NotImplementedError("only optimizer='sgd' (momentum) and loss='l1' are implemented")
+        if c["optimizer"] not in ("sgd", "adam") or c["loss"] != "l1":
+            raise NotImplementedError("optimizer must be 'sgd' (momentum) or 'adam' (lib/models.py:449-453); only "
+                                      "loss='l1' is implemented")
+        self.adam = c["optimizer"] == "adam"
+        self.adam_t = 0                     # optimiser applications so far (TF: beta1_power = beta1 ** (adam_t + 1))
         self.tp = tp = Topology(device)
         self.device = dev = tp.device
         torch.cuda.set_device(dev)
@@ -596,6 +609,9 @@ class CapeNetwork:
         self.tp_dw = Topology(device) if self.async_dw else tp
         self.dw_stream = torch.cuda.Stream(device=dev) if self.async_dw else None
         self._dw_pending = False
+        # column sums (bias / condition-channel gradients) off the main stream, their small products in ONE launch at the
+        # end of the backward pass (CAPE_SIDE_GLUE=0: in line, one launch per player -- the round-2a schedule)
+        self.side_glue = self.async_dw and os.environ.get("CAPE_SIDE_GLUE", "1") != "0"
         self.p = [int(l.shape[0]) for l in L]
         self.p_d = [int(l.shape[0]) for l in L_d]
         F, K, Kd = c["F"], c["K"], c["Kd"]
@@ -606,6 +622,9 @@ class CapeNetwork:
         gnames = [n for n in specs if is_g_param(n, True)]          # condition nets live in the G store
         dnames = [n for n in specs if is_d_param(n)]
         self.PG, self.PD = ParamStore(specs, gnames, dev), ParamStore(specs, dnames, dev)
+        if self.adam:
+            self.PG.add_adam_slot()
+            self.PD.add_adam_slot()
         vals = params if params is not None else init_params(specs, c["seed"])
         self.PG.load(vals)
         self.PD.load(vals)
@@ -801,6 +820,14 @@ class CapeNetwork:
         with torch.cuda.stream(self.dw_stream):
             fn(self.tp_dw)
         self._dw_pending = True
+
+    def run_glue(self, fn):
+        """Issue a launch whose result only the deferred small products read (bias / condition column sums): on the side
+        stream behind the layer's weight gradients when `side_glue` is on, else in line on the main stream."""
+        if self.side_glue:
+            self.run_dw(lambda _tp: fn())
+        else:
+            fn()
 
     def join_dw(self):
         if self._dw_pending:
@@ -1060,12 +1087,15 @@ class CapeNetwork:
                                          E._ptr(L), st()))
         self.decoder_bwd()
         self._fc_reg(("generator/decoder/fc1",))
-        self.small.flush()            # bias / condition-channel gradients of the decoder and discriminator layers
+        if not self.side_glue:
+            self.small.flush()        # bias / condition-channel gradients of the decoder and discriminator layers
         self._reduce_bucket("dec")    # decoder (+ discriminator) gradients are final: all-reduce behind the encoder backward
         self.encoder_bwd()
-        self.small.flush()            # encoder bias gradients; d_ycat is complete after the first flush
-        self.cond_bwd()
+        # side_glue: the column sums ran on the side stream, so every small product of the step goes out in one launch
+        # once that stream has joined (d_ycat, which the condition nets' backward reads, is complete after it)
         self.join_dw()
+        self.small.flush()            # (not side_glue: the encoder's bias gradients)
+        self.cond_bwd()
         if self.ref_compat:
             self.PD.grad.copy_(self.PD.flat)          # models.py:466: the D "gradients" are its variables
         if not c["optim_condnet"]:                    # models.py:455-458: condition nets excluded from vars_g
@@ -1096,6 +1126,7 @@ class CapeNetwork:
         if world <= 1:
             self.dp = None
             return
+        self.side_glue = False            # the "dec" bucket needs the decoder's bias / condition gradients at its boundary
         P = self.PG
         names = P.names
         fc0 = P.offsets["generator/encoder/fc_mean/dense/kernel"]
@@ -1124,13 +1155,24 @@ class CapeNetwork:
         self.sumsq.zero_()
         for P, i in ((self.PG, 0), (self.PD, 1)):
             _lib.check(lib.cape_sumsq(E._ptr(P.grad), P.size, E._ptr(self.sumsq[i:]), E._stream()))
-            _lib.check(lib.cape_sgd_clip_update(E._ptr(P.flat), E._ptr(P.grad), E._ptr(P.mom), P.size,
-                                                E._ptr(self.sumsq[i:]), 5.0, E._ptr(self.lr[i:]),
-                                                float(self.cfg["momentum"]), E._stream()))
+            if self.adam:
+                _lib.check(lib.cape_adam_clip_update(E._ptr(P.flat), E._ptr(P.grad), E._ptr(P.mom), E._ptr(P.var), P.size,
+                                                     E._ptr(self.sumsq[i:]), 5.0, E._ptr(self.lr[i:]), ADAM_BETA1,
+                                                     ADAM_BETA2, ADAM_EPS, E._stream()))
+            else:
+                _lib.check(lib.cape_sgd_clip_update(E._ptr(P.flat), E._ptr(P.grad), E._ptr(P.mom), P.size,
+                                                    E._ptr(self.sumsq[i:]), 5.0, E._ptr(self.lr[i:]),
+                                                    float(self.cfg["momentum"]), E._stream()))
         self.prep_weights()
 
     def set_lr(self, step):
         lr_g, lr_d = self.lr_now(step)
+        if self.adam:
+            # AdamOptimizer folds its bias correction into the step size: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t), t counting
+            # the applications of this optimiser (both players are applied once per update, so they share t)
+            t = self.adam_t + 1
+            corr = math.sqrt(1.0 - ADAM_BETA2 ** t) / (1.0 - ADAM_BETA1 ** t)
+            lr_g, lr_d = lr_g * corr, lr_d * corr
         slot = self._lr_host[self._lr_slot]
         self._lr_slot = (self._lr_slot + 1) % self._lr_host.shape[0]
         slot[0], slot[1] = lr_g, lr_d
@@ -1174,6 +1216,7 @@ class CapeNetwork:
             else:
                 self.enqueue_update()
             self.step_count = step + 1
+            self.adam_t += 1
         return self.losses
 
     def loss_dict(self):

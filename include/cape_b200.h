@@ -306,6 +306,14 @@ int cape_sumsq(const float* g, int64_t n, float* sumsq, void* stream);
 int cape_sgd_clip_update(float* w, const float* g, float* mom, int64_t n, const float* sumsq, float clip_norm,
                          const float* lr_dev, float momentum, void* stream);
 
+/* tf.train.AdamOptimizer (the reference's `optimizer: adam` branch, lib/models.py:449-451; TF-1.13 defaults
+ * beta1 = 0.9, beta2 = 0.999, eps = 1e-8) behind the same global-norm clip:
+ *   g' = coef g;  m = beta1 m + (1 - beta1) g';  v = beta2 v + (1 - beta2) g'^2;  w -= lr_t m / (sqrt(v) + eps)
+ * lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t) (t = applications so far + 1) is computed by the caller and read from
+ * device memory, so the launch is CUDA-graph capturable like the momentum update. */
+int cape_adam_clip_update(float* w, const float* g, float* m, float* v, int64_t n, const float* sumsq, float clip_norm,
+                          const float* lr_t_dev, float beta1, float beta2, float eps, void* stream);
+
 /* ---- group norm (CAPE.gn, lib/models.py:681-712) + ReLU, for the non-affine decoder blocks ------------
  * x: [N, rows, C], G groups of C/G contiguous channels; stats over (C/G x rows) per (n, g), biased variance,
  * y = relu(gamma*(x-mean)*rstd + beta).  stats: [N, G, 2] = (mean, rstd), saved for the backward pass.

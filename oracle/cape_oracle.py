@@ -327,6 +327,16 @@ def d_var_names(P):
     return [k for k in P if k.startswith("discriminator")]
 
 
+def adam_apply(p, m, v, g, lr, t, b1=0.9, b2=0.999, eps=1e-8):
+    """One application of tf.train.AdamOptimizer (TF-1.13 defaults; the reference's `optimizer: adam` branch,
+    models.py:450-451) to one variable: returns (p', m', v').  t = 1 for the first application.  TF folds the bias
+    correction into the step size and adds eps to the UNcorrected sqrt(v) ("epsilon hat" in the Adam paper)."""
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+    return p - lr_t * m / (torch.sqrt(v) + eps), m, v
+
+
 def train_update(oracle, P, mom, batch, step, edges, ref_compat=False, clip=5.0):
     """One optimiser application = what a single sess.run(op_train_*) does (models.py:460-472).
 
@@ -353,14 +363,28 @@ def train_update(oracle, P, mom, batch, step, edges, ref_compat=False, clip=5.0)
         grads_d = torch.autograd.grad(L["loss_d"], [Pg[k] for k in dn], allow_unused=True)
         grads_d = [g if g is not None else torch.zeros_like(Pg[k]) for g, k in zip(grads_d, dn)]
     lr_g, lr_d = lr_schedule(cfg, step)
+    adam = cfg.get("optimizer", "sgd") == "adam"
+    if adam:
+        # tf.train.AdamOptimizer (models.py:450-451; TF-1.13 defaults): `mom` carries the first moments under the variable
+        # names, the second moments under "adam_v/<name>" and the number of applications so far under "adam_t"
+        t = int(mom.get("adam_t", torch.zeros(())).item()) + 1
+        mom["adam_t"] = torch.tensor(float(t))
     for names, grads, lr in ((gn, grads_g, lr_g), (dn, grads_d, lr_d)):
         norm = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).item()
         coef = clip / max(norm, clip)
         for k, g in zip(names, grads):
-            mom[k] = cfg["momentum"] * mom[k] + coef * g.detach()
-            P[k] = P[k] - lr * mom[k]
+            if adam:
+                gc = coef * g.detach()
+                v = mom.get("adam_v/" + k)
+                v = torch.zeros_like(gc) if v is None else v
+                P[k], mom[k], mom["adam_v/" + k] = adam_apply(P[k], mom[k], v, gc, lr, t)
+            else:
+                mom[k] = cfg["momentum"] * mom[k] + coef * g.detach()
+                P[k] = P[k] - lr * mom[k]
     out = {k: float(v) for k, v in L.items()}
     out["grads"] = {k: g.detach() for k, g in zip(gn + dn, list(grads_g) + list(grads_d))}
     out["mom"] = {k: mom[k].detach() for k in gn + dn}
+    if adam:
+        out["adam_v"] = {k: mom["adam_v/" + k].detach() for k in gn + dn}
     out["x_hat"] = x_hat.detach()
     return out

@@ -399,8 +399,24 @@ def train_step(h, cfg, N=2, ref_compat=False, step=100, seed=123, dtype=torch.fl
             cur["grad " + k] = rel(got_g[k].reshape(-1), g.numpy().reshape(-1))
         for k, m in res["mom"].items():                  # momentum accumulator (first update: clip coefficient * grad)
             cur["clipped-update " + k] = rel(got_m[k].reshape(-1), m.numpy().reshape(-1))
+        adam = "adam_v" in res
+        if adam:                                         # Adam's second-moment slots
+            got_v = net.PG.export(net.PG.var)
+            got_v.update(net.PD.export(net.PD.var))
+            for k, v in res["adam_v"].items():
+                cur["adam-v " + k] = rel(got_v[k].reshape(-1), v.numpy().reshape(-1))
         for k, v in o_params.items():                    # post-update parameters (fp32 resolution of the weights)
-            cur["param " + k] = rel(got_p[k].reshape(-1), v.reshape(-1))
+            a, b = got_p[k].reshape(-1), v.reshape(-1)
+            if adam:
+                # Adam's step lr_t m / (sqrt(v) + eps) is +-lr for ANY gradient magnitude above eps, so an element whose
+                # gradient lies within the parity tolerance of zero moves by a full step in a direction decided by
+                # rounding: the parameters are compared where the gradient is resolved (|g| > 5 % of the tensor's max)
+                g = np.abs(res["grads"][k].numpy().reshape(-1))
+                keep = g > 0.05 * g.max()
+                if not keep.any():
+                    continue
+                a, b = a[keep], b[keep]
+            cur["param " + k] = rel(a, b)
         for k, v in cur.items():
             out[pre + k] = (v, bound.get(k, 0.0)) if truth else v
     return out
@@ -465,3 +481,41 @@ def generator_forward(h, cfg, N=32, seed=123, fc_scale=1.0):
         x_hat, zm, zl = o.generator(tb["x_g"], y, y2, tb["eps"], P)
     return {"x_hat (vertex-L2)": vertex_l2(got, x_hat.numpy()), "x_hat (max-rel)": rel(got, x_hat.numpy()),
             "z_mean": rel(net.z_mean.cpu().numpy(), zm.numpy()), "z_logvar": rel(net.z_logvar.cpu().numpy(), zl.numpy())}
+
+
+def adam_kernel_case(n=100003, seed=5):
+    """cape_adam_clip_update against the formula of tf.train.AdamOptimizer in float64 (two consecutive applications,
+    with and without an active global-norm clip)."""
+    import ctypes as C
+    from cape_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(seed)
+    out = {}
+    for tag, gscale in (("clip inactive", 1e-3), ("clip active", 1.0)):
+        w = rng.randn(n).astype(np.float32) * 0.1
+        m, v = np.zeros(n, np.float64), np.zeros(n, np.float64)
+        wd, md, vd = _cuda(w), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+        w64 = w.astype(np.float64)
+        b1, b2, eps, lr, clip = 0.9, 0.999, 1e-8, 3e-3, 5.0
+        for t in (1, 2):
+            g = (rng.randn(n) * gscale).astype(np.float32)
+            gd = _cuda(g)
+            ss = torch.zeros(1, device="cuda")
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.cape_sumsq(C.c_void_p(gd.data_ptr()), n, C.c_void_p(ss.data_ptr()), st))
+            lr_t = lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+            lrd = torch.tensor([lr_t], dtype=torch.float32, device="cuda")
+            _lib.check(lib.cape_adam_clip_update(C.c_void_p(wd.data_ptr()), C.c_void_p(gd.data_ptr()),
+                                                 C.c_void_p(md.data_ptr()), C.c_void_p(vd.data_ptr()), n,
+                                                 C.c_void_p(ss.data_ptr()), clip, C.c_void_p(lrd.data_ptr()), b1, b2, eps, st))
+            g64 = g.astype(np.float64)
+            coef = clip / max(np.sqrt((g64 ** 2).sum()), clip)
+            gc = coef * g64
+            m = b1 * m + (1 - b1) * gc
+            v = b2 * v + (1 - b2) * gc * gc
+            w64 = w64 - lr_t * m / (np.sqrt(v) + eps)
+        torch.cuda.synchronize()
+        out["adam %s: m" % tag] = rel(md.cpu().numpy(), m)
+        out["adam %s: v" % tag] = rel(vd.cpu().numpy(), v)
+        out["adam %s: w" % tag] = rel(wd.cpu().numpy(), w64)
+    return out

@@ -133,6 +133,17 @@ def test_train_step_reference_quirks(hierarchy, cfg):
     _assert_all(parity.train_step(hierarchy, cfg, N=2, ref_compat=True))
 
 
+def test_adam_kernel():
+    """cape_adam_clip_update == tf.train.AdamOptimizer's update rule (float64 formula), clip active and inactive."""
+    _assert_all(parity.adam_kernel_case(), tol=1e-5)
+
+
+def test_train_step_adam(hierarchy, cfg):
+    """`optimizer: adam` (lib/models.py:449-451): one update -- gradients, both moment slots and the parameters where
+    the gradient is resolved (see parity.train_step) against the oracle's Adam."""
+    _assert_all(parity.train_step(hierarchy, dict(cfg, optimizer="adam"), N=2))
+
+
 def test_tensor_core_path_matches_simt(hierarchy):
     """The tcgen05 3xTF32 contraction and the fp32 FFMA contraction are two implementations of one entry point."""
     _assert_all(parity.tc_vs_simt(hierarchy), tol=2e-5)

@@ -71,3 +71,24 @@ def test_bce_matches_torch():
     l = torch.randn(50, dtype=torch.float64)
     want = torch.nn.functional.binary_cross_entropy_with_logits(l, torch.full_like(l, 0.9))
     assert abs(float(O.Oracle.bce_logits(l, 0.9) - want)) < 1e-12
+
+
+def test_adam_rule_matches_torch_adam():
+    """The oracle's restatement of tf.train.AdamOptimizer against torch.optim.Adam, which differs from TF only in where
+    eps enters (eps vs eps * sqrt(1 - b2^t)): identical to 1e-6 for gradients far above eps, three applications."""
+    torch.manual_seed(0)
+    p0 = torch.randn(1000, dtype=torch.float64)
+    p = p0.clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    q = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([q], lr=3e-3, betas=(0.9, 0.999), eps=1e-8)
+    for t in (1, 2, 3):
+        g = torch.randn(1000, dtype=torch.float64) + 0.5
+        p, m, v = O.adam_apply(p, m, v, g, 3e-3, t)
+        q.grad = g.clone()
+        opt.step()
+    assert _rel(p.numpy(), q.detach().numpy()) < 1e-6
+    # first application: the step is lr * sign(g) for |g| >> eps
+    g = torch.sign(g) * (0.5 + g.abs())
+    p1, _, _ = O.adam_apply(p0, torch.zeros_like(p0), torch.zeros_like(p0), g, 3e-3, 1)
+    assert _rel((p0 - p1).numpy(), (3e-3 * torch.sign(g)).numpy()) < 1e-6
