@@ -47,9 +47,14 @@ class _ChebFn(torch.autograd.Function):
         terms = [dict(src=x, op=site.ops[k], F=Fin, src_rows=site.rows_in, src_stride=Fin, w=W3[:, k, :],
                       w_stride=K * Fout, wT=Wt[:, k, :], wT_stride=K * Fin, wT_lo=Wt_lo[:, k, :]) for k in range(K)]
         b = bias.contiguous().view(-1) if bias is not None else None
-        E.cheb_call(tp, N, site.rows_out, Fout, terms, out, epilogue=EPI_LINEAR, act=act, bias=b, precise=precise)
+        # one bias per filter ([F] / [1, 1, F]: b1*) or per vertex and filter ([1, M, F]: b2relu, lib/models.py:123-127)
+        per_row = b is not None and b.numel() == site.rows_out * Fout and site.rows_out > 1
+        assert b is None or per_row or b.numel() == Fout, "bias must be [F], [1, 1, F] or [1, M, F]"
+        E.cheb_call(tp, N, site.rows_out, Fout, terms, out, epilogue=EPI_LINEAR, act=act, bias=b, bias_per_row=per_row,
+                    precise=precise)
         ctx.save_for_backward(x, W, out)
-        ctx.site, ctx.tp, ctx.act, ctx.has_bias = site, tp, act, bias is not None
+        ctx.site, ctx.tp, ctx.act, ctx.has_bias, ctx.per_row = site, tp, act, bias is not None, per_row
+        ctx.bias_shape = tuple(bias.shape) if bias is not None else None
         return out
 
     @staticmethod
@@ -69,10 +74,12 @@ class _ChebFn(torch.autograd.Function):
         for k in range(K):
             E.cheb_dw(tp, N, site.rows_out, Fout, x, site.ops[k], Fin, site.rows_in, Fin, g, dW3[:, k, :], K * Fout)
         db = None
-        if ctx.has_bias:
+        if ctx.has_bias and ctx.per_row:
+            db = g.sum(0).view(ctx.bias_shape)
+        elif ctx.has_bias:
             cs = torch.zeros(N, 1, Fout, device=x.device)
             E.colsum(tp, g, N, site.rows_out, Fout, [-1], cs)
-            db = cs.sum(0).view(-1)
+            db = cs.sum(0).view(ctx.bias_shape)
         dx = None
         if ctx.needs_input_grad[0]:
             Wt = torch.empty(Fout, K, Fin, device=x.device)
@@ -91,9 +98,19 @@ class _ChebFn(torch.autograd.Function):
 def chebyshev5(x, L, W, K, bias=None, activation=None, pool=None, unpool=None, precise=False):
     """Chebyshev graph convolution y = sum_k T_k(L~) x W[k::K] (lib/models.py:69-103); W is [Fin*K, Fout] with row
     index fin*K + k.  precise: short tensor-core accumulation chains (cape_conv_args.precise; K = 1 / plain operands).  Optional fusions: `unpool` U applied to x first (models.py:750,782), `bias`+`activation`
-    ('b1leakyrelu' | 'b1relu' | None, models.py:105-121) and `pool` D applied last (models.py:168)."""
+    ('b1leakyrelu' | 'b1relu' | 'b2relu' (bias [1, M, Fout]) | 'b1tanh' | None, models.py:105-127) and `pool` D applied
+    last (models.py:168)."""
     tp = topology_for(x.device)
-    act = {None: ACT_NONE, "b1leakyrelu": ACT_LEAKY, "b1relu": ACT_RELU}[activation]
+    if activation == "b1tanh":
+        # lib/models.py:111-115; unused by every shipped config: the bias rides in the conv's epilogue, the tanh is a
+        # separate elementwise pass (and comes before the pooling, as in the reference)
+        y = torch.tanh(chebyshev5(x, L, W, K, bias=bias, activation=None, unpool=unpool, precise=precise))
+        return poolwT(y, pool) if pool is not None else y
+    act = {None: ACT_NONE, "b1leakyrelu": ACT_LEAKY, "b1relu": ACT_RELU, "b2relu": ACT_RELU}[activation]
+    if pool is not None and bias is not None and bias.numel() > W.shape[1]:
+        # a per-vertex bias (b2relu) lives on the un-pooled vertices: conv + bias + activation first, then the pooling
+        y = _ChebFn.apply(x, W, bias, _site(tp, L, K, unpool, None), tp, act, precise)
+        return poolwT(y, pool)
     if pool is not None and (bias is not None or act != ACT_NONE):
         from . import topology as topo
         if not topo.is_selection(pool):
@@ -138,3 +155,16 @@ def poolwT(x, S):
         m = sp.csr_matrix(S)
         _resamplers[key] = ((tp.add_operator(m), tp.add_operator(sp.csr_matrix(m.T)), m.shape[0], m.shape[1]), S)
     return _ResampleFn.apply(x, _resamplers[key][0], tp)
+
+
+def cnp(x, L, D, W, bias, K, activation="b1leakyrelu"):
+    """Convolution, non-linearity, pooling: `base_model.cnp` (lib/models.py:154-171) as ONE fused launch -- the
+    down-sampling D (a row selection) is folded into the operator tables, bias and activation into the epilogue."""
+    return chebyshev5(x, L, W, K, bias=bias, activation=activation, pool=D)
+
+
+def udn(x, L, U, W, bias, K, activation="b1leakyrelu"):
+    """Unpool, (de)convolution, non-linearity: `base_model.udn` (lib/models.py:173-191) as ONE fused launch -- the
+    up-sampling U is folded into the operator tables (op_k = T_k(L~) U), bias and activation into the epilogue.
+    L is the Laplacian of the FINER level (the reference passes Laplacian[-i-2] with Upsample_mtx[-i-1])."""
+    return chebyshev5(x, L, W, K, bias=bias, activation=activation, unpool=U)

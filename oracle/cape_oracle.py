@@ -140,6 +140,28 @@ class Oracle:
         """models.py:105-109 (tf.nn.leaky_relu default alpha=0.2)."""
         return self._act(x + b.reshape(1, 1, -1), 0.2, site)
 
+    def b1tanh(self, x, b):
+        """models.py:111-115."""
+        return torch.tanh(x + b.reshape(1, 1, -1))
+
+    def b1relu(self, x, b, site=None):
+        """models.py:117-121."""
+        return self._act(x + b.reshape(1, 1, -1), 0.0, site)
+
+    def b2relu(self, x, b, site=None):
+        """models.py:123-127: one bias per vertex and filter, b [1, M, F]."""
+        return self._act(x + b.reshape(1, x.shape[1], x.shape[2]), 0.0, site)
+
+    def cnp(self, x, Lt, Dm, W, b, K, brelu=None):
+        """models.py:154-171: filter -> brelu -> pool."""
+        brelu = brelu or self.b1leakyrelu
+        return self.poolwT(brelu(self.chebyshev5(x, Lt, W, K), b), Dm)
+
+    def udn(self, x, Lt, Um, W, b, K, brelu=None):
+        """models.py:173-191: unpool -> filter (Laplacian of the finer level) -> brelu."""
+        brelu = brelu or self.b1leakyrelu
+        return brelu(self.chebyshev5(self.poolwT(x, Um), Lt, W, K), b)
+
     def poolwT(self, x, S):
         """models.py:129-152."""
         N, M, Fin = x.shape

@@ -52,17 +52,15 @@ def cheb_grads(tag, L, K, Fin, Fout, N, U=None, D=None, act="b1leakyrelu", seed=
     Min = U.shape[1] if U is not None else L.shape[0]
     x = rng.normal(size=(N, Min, Fin)).astype(np.float32)
     W = rng.normal(0, 0.1, size=(Fin * K, Fout)).astype(np.float32)
-    b = rng.normal(0, 0.1, size=(Fout,)).astype(np.float32)
+    b = rng.normal(0, 0.1, size=(1, L.shape[0], Fout) if act == "b2relu" else (Fout,)).astype(np.float32)
     o = O.Oracle([L], [D] if D is not None else [], [U] if U is not None else [], [], [], dict(F=[Fout], K=[K], Kd=3))
     xt, Wt, bt = (torch.from_numpy(a).requires_grad_(True) for a in (x, W, b))
     z = xt
     if U is not None:
         z = o.poolwT(z, o.Um[0])
     z = o.chebyshev5(z, o.Lt[0], Wt, K)
-    if act == "b1leakyrelu":
-        z = o.b1leakyrelu(z, bt)
-    elif act == "b1relu":
-        z = torch.relu(z + bt.reshape(1, 1, -1))      # models.py:117-121
+    if act is not None:
+        z = getattr(o, act)(z, bt)                    # b1leakyrelu | b1relu | b2relu | b1tanh, models.py:105-127
     if D is not None:
         z = o.poolwT(z, o.Dm[0])
     dy = rng.normal(size=tuple(z.shape)).astype(np.float32)
@@ -90,6 +88,10 @@ def cheb_grad_cases(h):
     # wide same-level layer through the plain op API (no pre-split weight copies), more 128-row tiles than SMs:
     # persistent kernel, identity term by TMA, weights by the producer warps
     out.update(cheb_grads("wide L6 K=2 128->256 multi-tile", h["L"][6], 2, 128, 256, 24, act=None))
+    # the rest of base_model's operator seam (unused by the shipped configs): udn = unpool + conv + bias/act in one
+    # launch, per-vertex bias (b2relu), tanh (its gradient is smooth: no imposed decisions needed)
+    out.update(cheb_grads("udn L5 K=2 64->32 +unpool b1tanh", h["L"][5], 2, 64, 32, 2, U=h["U"][5], act="b1tanh"))
+    out.update(cheb_grads("b2relu L8 K=2 32->16 per-vertex bias", h["L"][8], 2, 32, 16, 1, act="b2relu"))
     return out
 
 

@@ -301,3 +301,18 @@ def test_prefetched_inputs_equal_direct_inputs(hierarchy):
     assert np.allclose(a[0], b[0], rtol=1e-5, atol=1e-7), (a[0], b[0])
     assert np.allclose(a, b, rtol=2e-3, atol=1e-5), (a, b)
     assert not np.array_equal(a[0], a[1])                     # the two batches differ
+
+
+def test_train_step_on_a_generated_4_layer_hierarchy(hierarchy):
+    """`--num_conv_layers 4` (main.py:31-32,56-57): the hierarchy is generated from the template mesh by
+    cape_b200.mesh_sampling (the reference needs psbody for it and ships fixtures for 8 layers only), the model built on
+    it takes a full VAE+GAN update, checked against the oracle built on the same generated operators."""
+    from cape_b200 import main as M
+    from cape_b200.params import NZ64_AFFINE
+    L, D, U, p = M.build_hierarchy(num_conv_layers=4, ds_factor=2)
+    assert p == [6890, 6890, 3445, 3445, 3445]
+    h = dict(L=L, D=D, U=U, p=p, L_d=hierarchy["L_d"], D_d=hierarchy["D_d"])
+    cfg = dict(NZ64_AFFINE, F=[64, 128, 128, 64], K=[2] * 4, decay_steps=10)
+    res = parity.train_step(h, cfg, N=2)
+    bad = {k: v for k, v in res.items() if not v < parity.TOL}
+    assert not bad, bad
