@@ -73,6 +73,8 @@ def config_dict(name, batch, world):
     c = CONFIGS[name]
     return {"workload": c["workload"], "id": name, "meshes_per_gpu": batch, "global_batch": batch * world,
             "parallelism": "dp%d" % world,
+            "l2": "no explicit flush between timed steps: one step streams %.1f GB of activations (>> 126 MB L2)"
+                  % (c["alg_mb"] * 1e-3 * batch),
             "update_rule": "real discriminator gradients (ref_compat=False); the lib/models.py:466 quirk is available "
                            "as ref_compat=True" if c["mode"] == "train" else "n/a (forward only)"}
 

@@ -405,8 +405,8 @@ def train_step(h, cfg, N=2, ref_compat=False, step=100, seed=123, dtype=torch.fl
         if adam:                                         # Adam's second-moment slots
             got_v = net.PG.export(net.PG.var)
             got_v.update(net.PD.export(net.PD.var))
-            for k, v in res["adam_v"].items():
-                cur["adam-v " + k] = rel(got_v[k].reshape(-1), v.numpy().reshape(-1))
+            for k, v in res["adam_v"].items():      # v is quadratic in g: half its relative error is the gradient's
+                cur["adam-v " + k] = 0.5 * rel(got_v[k].reshape(-1), v.numpy().reshape(-1))
         for k, v in o_params.items():                    # post-update parameters (fp32 resolution of the weights)
             a, b = got_p[k].reshape(-1), v.reshape(-1)
             if adam:
