@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcape_b200.so")
+# CAPE_B200_LIB: another build of the same library (A/B measurements of compile-time variants)
+LIB_PATH = os.environ.get("CAPE_B200_LIB") or os.path.join(_HERE, "libcape_b200.so")
 
 MAX_TERMS = 8
 EPI_LINEAR, EPI_AFFINE, EPI_SLOPE, EPI_DUALMASK = 0, 1, 2, 3

@@ -484,21 +484,24 @@ __global__ void __launch_bounds__(1024) reduce_splits_kernel(const float* __rest
                                                              float* __restrict__ dw, long long dw_stride,
                                                              int accumulate, int Fper, long long term_stride,
                                                              long long col_stride) {
-  // 64 consecutive elements x 16 split lanes per CTA; fixed summation order (deterministic)
-  __shared__ float red[16][64];
+  // 32 consecutive elements x 32 split lanes per CTA (a 64 x 64 gradient with ~300 partials: 128 CTAs, nine loads per
+  // thread); fixed summation order (deterministic)
+  __shared__ float red[32][33];
   const long long total = (long long)F * ncols;
-  const int el = threadIdx.x & 63, zl = threadIdx.x >> 6;
-  for (long long e0 = (long long)blockIdx.x * 64; e0 < total; e0 += (long long)gridDim.x * 64) {
+  const int el = threadIdx.x & 31, zl = threadIdx.x >> 5;
+  for (long long e0 = (long long)blockIdx.x * 32; e0 < total; e0 += (long long)gridDim.x * 32) {
     const long long e = e0 + el;
     float s = 0.f;
-    if (e < total)
-      for (int z = zl; z < nsplit; z += 16) s += ws[(size_t)z * total + e];
+    if (e < total) {
+#pragma unroll 4
+      for (int z = zl; z < nsplit; z += 32) s += ws[(size_t)z * total + e];
+    }
     red[zl][el] = s;
     __syncthreads();
     if (zl == 0 && e < total) {
       s = 0.f;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) s += red[k][el];
+      for (int k = 0; k < 32; ++k) s += red[k][el];
       const int q = (int)(e / ncols), c = (int)(e % ncols);
       float* o = dw + (size_t)(q % Fper) * dw_stride + (size_t)(q / Fper) * term_stride + (size_t)c * col_stride;
       *o = accumulate ? (*o + s) : s;
@@ -532,7 +535,22 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __grid_constant__ Col
 #pragma unroll
     for (int j = 0; j < CS_MAXOPS; ++j) s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ry < rl) {
-      for (int r = r0 + ry; r < r1; r += rl) {
+      int r = r0 + ry;
+      // four rows per trip: their loads are independent, so they are all in flight before the first FMA needs one
+      for (; r + 3 * rl < r1; r += 4 * rl) {
+        const float* g0 = gp + (size_t)r * p.gs + c4 * 4;
+        const size_t step = (size_t)rl * p.gs;
+        const float4 v0 = ldg4(g0), v1 = ldg4(g0 + step), v2 = ldg4(g0 + 2 * step), v3 = ldg4(g0 + 3 * step);
+#pragma unroll
+        for (int j = 0; j < CS_MAXOPS; ++j)
+          if (j < p.nops) {
+            const float* cf = p.coef[j];
+            const float k0 = cf ? __ldg(cf + r) : 1.f, k1 = cf ? __ldg(cf + r + rl) : 1.f;
+            const float k2 = cf ? __ldg(cf + r + 2 * rl) : 1.f, k3 = cf ? __ldg(cf + r + 3 * rl) : 1.f;
+            fma4(s[j], k0, v0); fma4(s[j], k1, v1); fma4(s[j], k2, v2); fma4(s[j], k3, v3);
+          }
+      }
+      for (; r < r1; r += rl) {
         const float4 gv = ldg4(gp + (size_t)r * p.gs + c4 * 4);
 #pragma unroll
         for (int j = 0; j < CS_MAXOPS; ++j)
@@ -764,7 +782,7 @@ extern "C" int cape_cheb_dw(cape_topology* t, const cape_dw_args* a, void* strea
   if (rc < 0) return rc;
   if (rc == 1) {
     const long long total = (long long)a->nops * a->F * a->ncols;
-    long long blocks = (total + 63) / 64;
+    long long blocks = (total + 31) / 32;
     if (blocks > 8LL * t->sm_count) blocks = 8LL * t->sm_count;
     reduce_splits_kernel<<<(unsigned)blocks, 1024, 0, (cudaStream_t)stream>>>(
         (const float*)t->workspace, ns, a->nops * a->F, a->ncols, a->dw, a->dw_stride, a->accumulate, a->F,
@@ -799,7 +817,7 @@ static int dw_single(cape_topology* t, const cape_dw_args* a, void* stream) {
     if (rc == 1) {
       if (ns > 1 || always_reduce) {
         const long long total = (long long)a->F * a->ncols;
-        long long blocks = (total + 63) / 64;
+        long long blocks = (total + 31) / 32;
         if (blocks > 8LL * t->sm_count) blocks = 8LL * t->sm_count;
         reduce_splits_kernel<<<(unsigned)blocks, 1024, 0, (cudaStream_t)stream>>>((const float*)t->workspace, ns, a->F,
                                                                                  a->ncols, a->dw, a->dw_stride,
@@ -837,7 +855,7 @@ static int dw_single(cape_topology* t, const cape_dw_args* a, void* stream) {
   cape::count_launches(1);
   if (nsplit > 1) {
     const long long total = (long long)a->F * a->ncols;
-    long long blocks = (total + 63) / 64;
+    long long blocks = (total + 31) / 32;
     if (blocks > 8LL * t->sm_count) blocks = 8LL * t->sm_count;
     reduce_splits_kernel<<<(unsigned)blocks, 1024, 0, st>>>((const float*)t->workspace, (int)nsplit, a->F, a->ncols, a->dw,
                                                   a->dw_stride, a->accumulate, a->F, 0, 1);

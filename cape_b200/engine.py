@@ -223,6 +223,7 @@ class WeightPrep:
 
     def __init__(self, tp):
         self.tp, self.items, self.table = tp, [], None
+        self.blocks_per_desc = int(__import__("os").environ.get("CAPE_WPREP_BLOCKS", "128"))
 
     def add(self, w, Fin, K, Fout, wt=None, wt_lo=None, wk=None, wk_lo=None):
         self.items.append((w, Fin, K, Fout, wt, wt_lo, wk, wk_lo))
@@ -239,7 +240,10 @@ class WeightPrep:
             raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
             self.table = torch.from_numpy(raw).to(self.tp.device)
             torch.cuda.synchronize()
-        check(self.tp.lib.cape_weight_prep(C.c_void_p(self.table.data_ptr()), len(self.items), 16, _stream()))
+        # blocks per descriptor: the widest layer (512 x 2 x 512: 512 tiles of 32 x 32) sets the length of the launch,
+        # blocks beyond a descriptor's tile count exit at once
+        check(self.tp.lib.cape_weight_prep(C.c_void_p(self.table.data_ptr()), len(self.items), self.blocks_per_desc,
+                                           _stream()))
 
 
 def _gemm_strides(A, B, Cout):

@@ -20,7 +20,9 @@ from .engine import (ACT_LEAKY, ACT_NONE, EPI_AFFINE, EPI_DUALMASK, EPI_LINEAR, 
 from .params import init_params, is_d_param, is_g_param, param_specs
 
 
-ADAM_BETA1, ADAM_BETA2, ADAM_EPS = 0.9, 0.999, 1e-8      # tf.train.AdamOptimizer defaults (TF 1.13), lib/models.py:450-451
+# tf.train.AdamOptimizer defaults (TF 1.13; lib/models.py:450-451), as the float32 tensors TF turns them into: the
+# update's (1 - beta2) is 1 - fl32(0.999) = 9.9998713e-4, not 1e-3
+ADAM_BETA1, ADAM_BETA2, ADAM_EPS = float(np.float32(0.9)), float(np.float32(0.999)), 1e-8
 
 
 def _pad4(n):
@@ -124,12 +126,12 @@ def choose_forms(F, C, Fout, K, rows_in, rows_out, affine, need_dx, dw_mode, pre
       "contract": the TMA-fed kernel computes Z = x @ [W_0 | W_1 | ..] (or G @ [W_k^T]_k) on the SOURCE rows, then
                   cape_apply applies the operators to the narrower Z and runs the epilogue.
     Defaults from the per-layer measurements at batch 64 (profiles/r02_launch_profile.csv):
-      * forward: basis-first where the short-chain accumulation is wanted (it needs plain operands: the encoder),
-        contract-first for un-pooling layers (half the rows in the contraction, Fout-wide gathers: dec/aff3 420 -> 265 us)
+      * forward: basis-first where the short-chain accumulation is wanted (it needs plain operands: the encoder) and for
+        the pooled K = 3 discriminator layers, contract-first for un-pooling layers (half the rows in the contraction, Fout-wide gathers: dec/aff3 420 -> 265 us)
         and for precise decoder blocks, fused elsewhere (discriminator: three gathers + a contraction lose to one kernel);
       * data gradient: contract-first when the gradient narrows (Fout > F: the gathers run on the narrow side) or the
         layer pools and is at least 128 wide (the contraction runs on half the rows: disc/conv3 495 -> 333 us);
-        basis-first measured slower than the fused kernel on every decoder layer but one, so it is opt-in.
+        basis-first only for the wide un-pooling block (every other decoder layer is faster fused).
     Experiment overrides: CAPE_FWD_MODE / CAPE_DX_MODE for every layer, CAPE_MODES="enc/conv8:fwd=fused,disc/conv3:dx=contract"
     for single ones (ineligible requests are ignored).  `plain`: every operator of the site is the identity."""
     env = os.environ if env is None else env
@@ -140,10 +142,24 @@ def choose_forms(F, C, Fout, K, rows_in, rows_out, affine, need_dx, dw_mode, pre
     if split_ok:
         if precise and basis_ok:
             fwd_mode = "basis"
+        elif basis_ok and K >= 3 and rows_out < rows_in:
+            # pooled K = 3 layers (the discriminator): the composed T_2 operator has ~19 taps, and the stash the fused kernel
+            # writes next to its gather is what the separate gather launch produces anyway (round-2b per-layer profile:
+            # disc/conv4 189 -> 136 us, conv2 273 -> 261, conv3 unchanged)
+            fwd_mode = "basis"
         elif (C > 0 or affine) and (rows_in < rows_out or precise):
             fwd_mode = "contract"
-        if need_dx and dw_mode == "aside" and K * F <= 512 and (Fout > F or (rows_out < rows_in and Fout == F and F >= 128)):
+        # (an affine block has TWO upstream gradients -- d out and d out masked by the ReLU branch -- and the contract-first
+        # data gradient projects only one tensor: fused for those.  No shipped config has an affine block that widens,
+        # a generated 4-layer hierarchy does: tests/test_gpu_api.py::test_train_step_on_a_generated_4_layer_hierarchy)
+        if (need_dx and not affine and dw_mode == "aside" and K * F <= 512
+                and (Fout > F or (rows_out < rows_in and Fout == F and F >= 128))):
             dx_mode = "contract"
+        if need_dx and dw_mode == "gside" and rows_in < rows_out and Fout >= 128:
+            # wide un-pooling block (dec/aff3: 256 -> 128 at 862 -> 1723 rows): H = op^T G by the gather kernel into the
+            # weight gradient's stash, then one plain contraction -- 290 -> 245 us; the narrower un-pooling blocks (aff5,
+            # aff7) lose 15-20 % that way and stay fused
+            dx_mode = "basis"
     fm, dm = env.get("CAPE_FWD_MODE", ""), env.get("CAPE_DX_MODE", "")
     for item in filter(None, env.get("CAPE_MODES", "").split(",")):
         key, val = item.split("=")
@@ -154,7 +170,7 @@ def choose_forms(F, C, Fout, K, rows_in, rows_out, affine, need_dx, dw_mode, pre
     if fm and (fm == "fused" or (split_ok and (fm != "basis" or basis_ok))):
         fwd_mode = fm
     if dm and need_dx and (dm == "fused" or (split_ok and (dm != "basis" or dw_mode == "gside")
-                                             and (dm != "contract" or dw_mode != "gside"))):
+                                             and (dm != "contract" or (dw_mode != "gside" and not affine)))):
         dx_mode = dm
     return fwd_mode, dx_mode
 

@@ -349,10 +349,14 @@ def d_var_names(P):
     return [k for k in P if k.startswith("discriminator")]
 
 
-def adam_apply(p, m, v, g, lr, t, b1=0.9, b2=0.999, eps=1e-8):
+ADAM_B1, ADAM_B2 = float(np.float32(0.9)), float(np.float32(0.999))    # TF casts the hyper-parameters to the variable's dtype
+
+
+def adam_apply(p, m, v, g, lr, t, b1=ADAM_B1, b2=ADAM_B2, eps=1e-8):
     """One application of tf.train.AdamOptimizer (TF-1.13 defaults; the reference's `optimizer: adam` branch,
     models.py:450-451) to one variable: returns (p', m', v').  t = 1 for the first application.  TF folds the bias
-    correction into the step size and adds eps to the UNcorrected sqrt(v) ("epsilon hat" in the Adam paper)."""
+    correction into the step size and adds eps to the UNcorrected sqrt(v) ("epsilon hat" in the Adam paper); beta1 /
+    beta2 enter as float32 tensors, so (1 - beta2) is 1 - fl32(0.999) = 9.9998713e-4."""
     m = b1 * m + (1 - b1) * g
     v = b2 * v + (1 - b2) * g * g
     lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)

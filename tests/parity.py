@@ -498,7 +498,8 @@ def adam_kernel_case(n=100003, seed=5):
         m, v = np.zeros(n, np.float64), np.zeros(n, np.float64)
         wd, md, vd = _cuda(w), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
         w64 = w.astype(np.float64)
-        b1, b2, eps, lr, clip = 0.9, 0.999, 1e-8, 3e-3, 5.0
+        # the hyper-parameters as the float32 values the kernel (and TF) see: 1 - fl32(0.999) differs from 1e-3 by 1.3e-5
+        b1, b2, eps, lr, clip = float(np.float32(0.9)), float(np.float32(0.999)), 1e-8, 3e-3, 5.0
         for t in (1, 2):
             g = (rng.randn(n) * gscale).astype(np.float32)
             gd = _cuda(g)

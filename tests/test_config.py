@@ -108,12 +108,21 @@ def test_layer_forms_of_the_shipped_config():
     assert f(256, 0, 256, 2, 1723, 862, False, True, "aside", True, False, "enc/conv6", env) == ("basis", "contract")
     assert f(512, 0, 512, 2, 862, 862, False, True, "aside", True, False, "enc/conv8", env) == ("basis", "fused")
     # decoder: un-pooling affine blocks contract first, same-level ones stay fused; a precise one contracts first too
-    assert f(256, 64, 128, 2, 862, 1723, True, True, "gside", False, False, "dec/aff3", env) == ("contract", "fused")
+    # (the wide un-pooling block also takes its data gradient basis-first, the narrower ones stay fused)
+    assert f(256, 64, 128, 2, 862, 1723, True, True, "gside", False, False, "dec/aff3", env) == ("contract", "basis")
+    assert f(128, 64, 64, 2, 1723, 3445, True, True, "gside", False, False, "dec/aff5", env) == ("contract", "fused")
     assert f(512, 64, 256, 2, 862, 862, True, True, "gside", False, False, "dec/aff1", env) == ("fused", "fused")
     assert f(512, 64, 256, 2, 862, 862, True, True, "gside", True, False, "dec/aff1", env)[0] == "contract"
-    # discriminator (not precise): fused forward, contract-first data gradient where the layer pools and narrows
-    assert f(64, 0, 128, 3, 1723, 862, False, True, "aside", False, False, "disc/conv3", env) == ("fused", "contract")
-    assert f(64, 0, 64, 3, 3445, 1723, False, True, "aside", False, False, "disc/conv2", env) == ("fused", "fused")
+    # an affine block that WIDENS (32 -> 64: generated 4-layer hierarchies) has two upstream gradients: its data gradient
+    # must not take the single-tensor contract-first form, not even on request
+    assert f(32, 64, 64, 2, 3445, 3445, True, True, "aside", False, False, "dec/aff2", env) == ("fused", "fused")
+    assert f(32, 64, 64, 2, 3445, 3445, True, True, "aside", False, False, "dec/aff2", {"CAPE_DX_MODE": "contract"})[1] == "fused"
+    # discriminator (not precise, K = 3, pooled): basis-first forward (the fused kernel's 19-tap gather loses to gather
+    # launch + plain contraction), contract-first data gradient where the layer pools and narrows; the first layer
+    # carries the condition channels and stays fused
+    assert f(64, 0, 128, 3, 1723, 862, False, True, "aside", False, False, "disc/conv3", env) == ("basis", "contract")
+    assert f(64, 0, 64, 3, 3445, 1723, False, True, "aside", False, False, "disc/conv2", env) == ("basis", "fused")
+    assert f(3, 64, 64, 3, 6890, 3445, False, False, "gather", False, False, "disc/conv1", env) == ("fused", "fused")
     # thin layers and 1x1 convs (identity operators only) never split
     assert f(3, 0, 64, 2, 6890, 6890, False, False, "gather", True, False, "enc/conv1", env) == ("fused", "fused")
     assert f(512, 0, 64, 1, 862, 862, False, True, "gside", True, True, "enc/1x1", env) == ("fused", "fused")

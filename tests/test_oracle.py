@@ -81,7 +81,7 @@ def test_adam_rule_matches_torch_adam():
     p = p0.clone()
     m, v = torch.zeros_like(p), torch.zeros_like(p)
     q = p0.clone().requires_grad_(True)
-    opt = torch.optim.Adam([q], lr=3e-3, betas=(0.9, 0.999), eps=1e-8)
+    opt = torch.optim.Adam([q], lr=3e-3, betas=(O.ADAM_B1, O.ADAM_B2), eps=1e-8)
     for t in (1, 2, 3):
         g = torch.randn(1000, dtype=torch.float64) + 0.5
         p, m, v = O.adam_apply(p, m, v, g, 3e-3, t)
