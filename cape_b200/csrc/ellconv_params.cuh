@@ -73,6 +73,6 @@ int launch_dw_dense_tma(const cape_topology* t, const cape_dw_args* a, const OpV
 // producer warps instead of TMA, [5] = 1: one narrow-kernel CTA per SM (bigger L1), [6] = 1: identity-term basis
 // tiles by the producer warps instead of TMA, [7] = 1: thin-output layers on the generic kernels, [8] = 1: no TMA-fed
 // plain-operand kernel (gemm_tc.cu), [0]: operand-split experiment (ConvParams.split_rn)
-extern int g_tuning[16];
+extern int g_tuning[32];
 
 }  // namespace cape

@@ -888,7 +888,7 @@ int launch_two(const ConvParams& p, cudaStream_t st) {
 }  // namespace
 
 static bool g_tc_enabled = true;
-int g_tuning[16] = {0};   // experiment knobs (cape_set_tuning), see ellconv_params.cuh
+int g_tuning[32] = {0};   // experiment knobs (cape_set_tuning), see ellconv_params.cuh
 bool tensor_cores_enabled() { return g_tc_enabled; }
 
 int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cudaStream_t st) {
@@ -927,7 +927,7 @@ int launch_ellconv_tc(const cape_topology* t, const ConvParams& p, bool dual, cu
 }  // namespace cape
 
 extern "C" int cape_set_tuning(int key, int value) {
-  if (key < 0 || key >= 16) return -1;
+  if (key < 0 || key >= 32) return -1;
   const int prev = cape::g_tuning[key];
   cape::g_tuning[key] = value;
   return prev;

@@ -214,7 +214,10 @@ def gemm_cases():
     out = {}
     for (M, N, K, ta, tb, bias, act) in [(64, 128, 55168, False, False, True, 0), (64, 5000, 128, False, True, False, 0),
                                          (300, 130, 64, True, False, False, 0), (7, 3, 2, False, False, True, 1),
-                                         (1, 20670, 5, False, False, False, 0), (33, 64, 1, True, True, False, 0)]:
+                                         (1, 20670, 5, False, False, False, 0), (33, 64, 1, True, True, False, 0),
+                                         # the four operand layouts of the vectorised kernel (FC forward / dW / dx shapes)
+                                         (5000, 64, 64, True, False, True, 1), (4100, 64, 64, True, True, False, 0),
+                                         (64, 4100, 64, False, True, False, 0), (1, 55168, 64, False, False, False, 0)]:
         A = rng.normal(size=(K, M) if ta else (M, K)).astype(np.float32)
         B = rng.normal(size=(N, K) if tb else (K, N)).astype(np.float32)
         bv = rng.normal(size=(N,)).astype(np.float32) if bias else None
