@@ -434,7 +434,10 @@ int launch_thin_dw(const cape_topology* t, const cape_dw_args* a, const OpView* 
   p.src = a->src; p.g = a->g; p.nops = nops;
   for (int j = 0; j < nops; ++j) p.op[j] = ops[j];
   const int nq = nops * a->F;
-  long long nblk = 4LL * t->sm_count;
+  // one full wave: the register count of thin_dw_kernel<KF> admits 4 / 3 / 2 / 2 CTAs per SM for KF = 4 / 8 / 12 / 16
+  // (with 4 x SMs blocks the KF = 8 kernel ran 1.3 waves of three 256-row chunks: two rounds where 4 chunks in one do)
+  const int resident = nq <= 4 ? 4 : (nq <= 8 ? 3 : 2);
+  long long nblk = (g_tuning[17] == 1 ? 4LL : (long long)resident) * t->sm_count;
   const long long max_by_rows = (p.total_rows + TD_CHUNK - 1) / TD_CHUNK;
   if (nblk > max_by_rows) nblk = max_by_rows;
   const long long per = (long long)nq * a->ncols * (long long)sizeof(float);

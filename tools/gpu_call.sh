@@ -1,20 +1,9 @@
 #!/bin/bash
-# One GPU-box visit under a tight budget: the GPU test suite, the default bench, A/B of the glue schedule, the two other
-# configs, the ncu launch list.  Everything lands in gpurun_out/.
+# One GPU-box visit under a tight budget: the GPU test suite, the three bench configs, the ncu launch list.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi -L | head -1
 echo "== pytest -m gpu"; timeout 1300 python -m pytest tests -q -m gpu --timeout 700 --durations=12 2>&1 | tail -60 > gpurun_out/pytest_gpu.log; tail -6 gpurun_out/pytest_gpu.log
 echo "== bench c3 (default)"; timeout 400 python bench.py --config c3 --steps 20 --warmup 5 2> gpurun_out/bench_c3.err > gpurun_out/bench_c3.json; cut -c1-330 gpurun_out/bench_c3.json
-ab() { echo "== A/B $*"; env "$@" timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-profile 2>/dev/null | python -c "
-import sys,json
-for l in sys.stdin:
-    try: b=json.loads(l)
-    except Exception: continue
-    print('   ms_per_step %.3f  value %.1f  e2e %.1f launches/step %d' % (b['ms_per_step'], b['value'], b['e2e']['value'], b['gpu_launches']/b['steps']))
-"; }
-ab CAPE_SIDE_GLUE=1
-ab CAPE_SIDE_GLUE=0
-ab CAPE_SIDE_GLUE=0 CAPE_SMALL_BLOCKS=4
 for c in c2 c5; do
   echo "== bench $c"; timeout 400 python bench.py --config $c --steps 20 --warmup 5 2> gpurun_out/bench_$c.err > gpurun_out/bench_$c.json; cut -c1-260 gpurun_out/bench_$c.json
 done
