@@ -57,6 +57,11 @@ __device__ __forceinline__ void f4_axpy(float4& a, float s, const float4& x) {
   a.x = fmaf(s, x.x, a.x); a.y = fmaf(s, x.y, a.y); a.z = fmaf(s, x.z, a.z); a.w = fmaf(s, x.w, a.w);
 }
 
+__device__ __forceinline__ void ap_advance(int& r, int& n, int by, int rows) {
+  r += by;
+  while (r >= rows) { r -= rows; ++n; }
+}
+
 template <bool DUAL>
 __device__ __forceinline__ void ap_store(const ApParams& p, long long R, int r, int c, float4 a0, float4 a1) {
   const size_t o = (size_t)R * p.out_stride + c;
@@ -118,12 +123,16 @@ __global__ void __launch_bounds__(AP_THREADS, 3) apply_kernel(const __grid_const
   }
   const int lr = threadIdx.x / p.tpr, c = (threadIdx.x % p.tpr) * 4;
   if (lr >= p.rpp) return;
-  for (int base = lr; base < AP_R; base += 2 * p.rpp) {
+  // (sample, vertex) of the thread's first row by one division, of the following rows by stepping: a 64-bit division
+  // per row was a quarter of the loop's instructions
+  const int step = 2 * p.rpp;
+  int na = (int)((R0 + lr) / p.rows_out), ra = (int)((R0 + lr) - (long long)na * p.rows_out);
+  for (int base = lr; base < AP_R; base += step, ap_advance(ra, na, step, p.rows_out)) {
     const long long Ra = R0 + base, Rb = Ra + p.rpp;
     if (Ra >= p.total_rows) break;
     const bool vb = (base + p.rpp < AP_R) && Rb < p.total_rows;
-    const int na = (int)(Ra / p.rows_out), ra = (int)(Ra % p.rows_out);
-    const int nb = vb ? (int)(Rb / p.rows_out) : na, rb = vb ? (int)(Rb % p.rows_out) : ra;
+    int nb = na, rb = ra;
+    if (vb) ap_advance(rb, nb, p.rpp, p.rows_out);
     float4 a0 = f4_zero(), a1 = f4_zero(), b0 = f4_zero(), b1 = f4_zero();
     for (int t = 0; t < p.nterms; ++t) {
       const ApTerm& tm = p.terms[t];
