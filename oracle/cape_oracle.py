@@ -4,13 +4,15 @@ A torch-CPU (autograd) restatement of the reference's TF-1.13 graph, function by
 /root/reference/lib/models.py.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference leg may import this file; the product path (cape_b200/) never does.
 
-PARITY UNPINNED BY THE REFERENCE: the reference ships no tests or golden vectors and its
-arithmetic lives in tensorflow-gpu==1.13.2 (requirements.txt:11), which cannot be installed here.  The
-oracle is pinned instead by (i) the reference's own importable host code (lib/mesh_sampling.py
-laplacian/rescale_L run in the build container; vectors committed under tests/golden/ by
-tests/golden/make_golden.py), (ii) an independent float64 dense-polynomial formulation of the
-Chebyshev conv (oracle/np_ops.py), (iii) a literal numpy/scipy transcription of the op bodies
-(oracle/np_ops.py) that follows the reference's transposes/reshapes line by line.
+PINNING: the reference ships no tests or golden vectors and its arithmetic lives in
+tensorflow-gpu==1.13.2 (requirements.txt:11), which cannot be installed here -- TensorFlow's kernels themselves are
+therefore unpinned.  The reference's MODEL CODE is pinned: lib/models.py is executed unmodified on a TF-1 API shim
+(oracle/tf1_shim.py, torch-CPU behind the ~70 symbols it calls) and its outputs for one full update of both model
+families, the demo-phase graph and the op bodies are committed as golden vectors (tests/golden/make_ref_golden.py ->
+ref_models_golden.npz); tests/test_reference_golden.py requires this file's functions to reproduce them (forward: bit
+for bit; gradients / updates: 4e-7).  Also pinned: the reference's own importable host code (lib/mesh_sampling.py
+laplacian/rescale_L; tests/golden/make_golden.py), an independent float64 dense-polynomial formulation of the Chebyshev
+conv and a literal numpy/scipy transcription of the op bodies (oracle/np_ops.py).
 
 TF-default semantics encoded here (TF-1.13 docs): tf.nn.leaky_relu alpha=0.2; tf.layers.dense y=xW+b;
 tf.losses.* Reduction.MEAN over all elements; l2_regularizer(s)(w) = s*sum(w^2)/2; MomentumOptimizer

@@ -32,9 +32,11 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
 REF = os.environ.get("CAPE_REFERENCE", "/root/reference")
-for p in (ROOT, os.path.join(ROOT, "tests"), REF):
+for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
+if REF not in sys.path:
+    sys.path.append(REF)            # last: only `lib` (the reference's package) is meant to resolve there
 
 OUT = os.path.join(HERE, "ref_models_golden.npz")
 NSAMPLE = 64
