@@ -41,7 +41,7 @@ _pending = []
 GLOBAL_STEP = None
 
 
-def reset(feeds=None, params=None, global_step=0):
+def reset(feeds=None, params=None, global_step=0, slots=None):
     global GLOBAL_STEP
     FEEDS.clear(); PARAMS.clear(); VARS.clear(); REG_LOSSES.clear(); RECORD.clear()
     del TRAINABLE[:], _scope[:], _pending[:]
@@ -49,7 +49,8 @@ def reset(feeds=None, params=None, global_step=0):
     FEEDS.update(feeds or {})
     PARAMS.update(params or {})
     GLOBAL_STEP = _GlobalStep(int(global_step))
-    RECORD.update(grads={}, lr=[], slots={}, created=[])
+    RECORD.update(grads={}, lr=[], created=[],
+                  slots={k: torch.as_tensor(np.asarray(v, np.float32)).clone() for k, v in (slots or {}).items()})
 
 
 class _Shape(list):

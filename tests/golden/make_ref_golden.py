@@ -58,8 +58,9 @@ def reference_kwargs(cfg, h, batch_size, name="golden"):
                 lambda_edge=cfg["lambda_edge"], lambda_latent=cfg["lambda_latent"], restart=True, name=name)
 
 
-def run_reference(cfg, h, params, batch, step):
-    """One `sess.run([op_train_g, op_train_d])` of the reference on the shim.  Returns a dict of numpy results."""
+def run_reference(cfg, h, params, batch, step, momentum=None):
+    """One `sess.run([op_train_g, op_train_d])` of the reference on the shim.  Returns a dict of numpy results.
+    momentum: {variable name: accumulator} carried over from the previous update (None: zeros, a fresh optimiser)."""
     from oracle import tf1_shim as S
     from cape_b200 import topology as T
     S.install(template_vertices=T.template_mesh()[0])
@@ -68,7 +69,8 @@ def run_reference(cfg, h, params, batch, step):
     N = batch["x_g"].shape[0]
     feeds = dict(data_g=batch["x_g"], data_d=batch["x_d"], condition_g=batch["cond_g"], condition2_g=batch["cond2_g"],
                  condition_d=batch["cond_d"], condition2_d=batch["cond2_d"], gt=batch["gt"], eps=batch["eps"])
-    S.reset(feeds=feeds, params=params, global_step=step)
+    S.reset(feeds=feeds, params=params, global_step=step,
+            slots={k + "/Momentum": v for k, v in (momentum or {}).items()})
     with contextlib.redirect_stdout(io.StringIO()):              # the reference prints its layer table
         from lib import models as RM                             # the reference's own module
         model = RM.CAPE(**reference_kwargs(cfg, h, N))
@@ -185,6 +187,11 @@ def inputs(cfg, h, N, seed=123):
     return parity.calibrated_params(specs, seed, 0.05), make_batch(N, cfg["nz"], seed=seed)
 
 
+def second_batch(cfg, N, seed=123):
+    from cape_b200.synthetic import make_batch
+    return make_batch(N, cfg["nz"], seed=seed + 1000)            # the batch tests/parity.train_step draws for update 2
+
+
 def main():
     from cape_b200 import topology as T
     L, D, U, p, L_d, D_d, _ = T.load_graph_mtx(load_for_demo=True)
@@ -197,6 +204,14 @@ def main():
               % (tag, res["x_hat"].shape, res["recon"], res["edge"], res["latent"], res["gan_g"], res["gan_d"], res["lr"],
                  res["global_step_after"], len(res["created"])))
         pack(tag, res, store)
+        if tag == "nz64":
+            # a SECOND update on top of the first: momentum accumulators, the shared global_step (now 102) and the
+            # updated parameters carried over, a fresh batch -- what two consecutive sess.run calls of fit() do
+            batch2 = second_batch(cfg, N)
+            res2 = run_reference(cfg, h, res["params_after"], batch2, res["global_step_after"], momentum=res["momentum"])
+            print("%s_u2: recon %.6f gan_d %.6f lr %s step -> %d" % (tag, res2["recon"], res2["gan_d"], res2["lr"],
+                                                                    res2["global_step_after"]))
+            pack(tag + "_u2", res2, store)
     tag, cfg, N, step = configs()[0]
     params, batch = inputs(cfg, h, N)
     for k, v in run_reference_demo(cfg, h, params, batch).items():
