@@ -187,6 +187,15 @@ def inputs(cfg, h, N, seed=123):
     return parity.calibrated_params(specs, seed, 0.05), make_batch(N, cfg["nz"], seed=seed)
 
 
+def four_layer_case(h):
+    """(tag, cfg, hierarchy) of the 4-conv-layer variant: F = [nf, 2nf, 2nf, nf], ds_factors [1, 2, 1, 1]."""
+    from cape_b200 import main as M
+    from cape_b200.params import NZ64_AFFINE
+    L, D, U, p = M.build_hierarchy(num_conv_layers=4, ds_factor=2)
+    cfg = dict(NZ64_AFFINE, F=[64, 128, 128, 64], K=[2] * 4, decay_steps=10)
+    return "nz64_l4", cfg, dict(L=L, D=D, U=U, p=p, L_d=h["L_d"], D_d=h["D_d"])
+
+
 def second_batch(cfg, N, seed=123):
     from cape_b200.synthetic import make_batch
     return make_batch(N, cfg["nz"], seed=seed + 1000)            # the batch tests/parity.train_step draws for update 2
@@ -216,6 +225,17 @@ def main():
     params, batch = inputs(cfg, h, N)
     for k, v in run_reference_demo(cfg, h, params, batch).items():
         store["%s/demo/%s" % (tag, k)] = v
+    # --num_conv_layers 4 (main.py:31-32,56-57) on the hierarchy cape_b200.mesh_sampling generates from the template:
+    # variable inventory, forward outputs and losses of the reference on an architecture it ships no fixtures for
+    tag4, cfg4, h4 = four_layer_case(h)
+    params4, batch4 = inputs(cfg4, h4, 1)
+    res4 = run_reference(cfg4, h4, params4, batch4, 100)
+    print("%s: recon %.6f gan_d %.6f (%d variables)" % (tag4, res4["recon"], res4["gan_d"], len(res4["created"])))
+    store[tag4 + "/var_names"] = np.asarray([c[0] for c in res4["created"]])
+    store[tag4 + "/var_shapes"] = np.asarray([",".join(map(str, c[1])) for c in res4["created"]])
+    store[tag4 + "/x_hat"] = res4["x_hat"]
+    for k in ("recon", "edge", "latent", "gan_g", "gan_d"):
+        store["%s/%s" % (tag4, k)] = np.asarray(res4[k], np.float64)
     ops = run_reference_ops(h)
     prev = np.load(os.path.join(HERE, "ops_golden.npz"))
     for k, v in ops.items():
