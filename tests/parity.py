@@ -525,3 +525,38 @@ def adam_kernel_case(n=100003, seed=5):
         out["adam %s: v" % tag] = rel(vd.cpu().numpy(), v)
         out["adam %s: w" % tag] = rel(wd.cpu().numpy(), w64)
     return out
+
+
+def compare_with_reference_golden(tag, x_hat, losses, params_after):
+    """Relative errors of an update's results against tests/golden/ref_models_golden.npz -- the numbers the REFERENCE's
+    own lib/models.py produced on the TF shim (tests/golden/make_ref_golden.py) for the inputs of `reference_golden_inputs`.
+    Pure numpy (tests/test_reference_golden.py runs it on the oracle's results on CPU, the GPU test on the CUDA path's)."""
+    import make_ref_golden as G
+    z = np.load(G.OUT)
+    out = {"x_hat (vertex-L2)": vertex_l2(x_hat, z[tag + "/x_hat"]), "x_hat (max-rel)": rel(x_hat, z[tag + "/x_hat"])}
+    for k in ("recon", "edge", "latent", "gan_g", "gan_d"):
+        want = float(z["%s/%s" % (tag, k)])
+        out["loss " + k] = abs(losses[k] - want) / max(abs(want), 1e-30)
+    for name, v in params_after.items():
+        base = "%s/params_after/%s" % (tag, name)
+        v = np.asarray(v, np.float32).reshape(-1)
+        if base + "#full" in z.files:
+            out["param " + name] = rel(v, z[base + "#full"].reshape(-1))
+        else:
+            out["param " + name] = rel(v[G.sample_index(name, v.size)], z[base + "#sample"])
+    return out
+
+
+def reference_golden_update(h, tag="nz64"):
+    """The update the reference golden file holds (affine nz64 model, batch 2, global_step 100, the reference's own
+    optimiser wiring = ref_compat) on the CUDA path, compared with the reference's numbers directly."""
+    import make_ref_golden as G
+    from cape_b200.network import CapeNetwork
+    cfg, N, step = next((c, n, s) for t, c, n, s in G.configs() if t == tag)
+    params, batch = G.inputs(cfg, h, N)
+    net = CapeNetwork(h["L"], h["D"], h["U"], h["L_d"], h["D_d"], cfg, N, params=params, ref_compat=True)
+    tb = {k: torch.from_numpy(v) for k, v in batch.items()}
+    net.set_inputs(tb["x_g"], tb["cond_g"], tb["cond2_g"], tb["eps"], tb["x_d"], tb["cond_d"], tb["cond2_d"])
+    net.train_step(step=step)
+    torch.cuda.synchronize()
+    return compare_with_reference_golden(tag, net.x_hat.cpu().numpy(), net.loss_dict(), net.get_params())

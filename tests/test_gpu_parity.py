@@ -81,6 +81,13 @@ def test_train_step_matches_oracle(hierarchy, cfg):
     _assert_all(res)
 
 
+def test_train_step_matches_the_reference_golden_file(hierarchy):
+    """The CUDA path against numbers produced by the REFERENCE's own lib/models.py (executed on the TF-API shim,
+    tests/golden/make_ref_golden.py): x_hat, the five loss terms and every post-update parameter of one full update with
+    the reference's optimiser wiring.  No oracle in between."""
+    _assert_all(parity.reference_golden_update(hierarchy))
+
+
 def test_train_step_reference_initialisers_vs_float64_truth(hierarchy, cfg):
     """The reference's own initialisers (no calibration: glorot fc_mean/fc_var on N(0,1) inputs, logvar up to +-10,
     KL term ~1e4).  Truth = the float64 oracle; the CUDA path must be within 1e-4 of it, or at least as close as twice
