@@ -83,8 +83,8 @@ def test_train_step_matches_oracle(hierarchy, cfg):
 
 def test_train_step_matches_the_reference_golden_file(hierarchy):
     """The CUDA path against numbers produced by the REFERENCE's own lib/models.py (executed on the TF-API shim,
-    tests/golden/make_ref_golden.py): x_hat, the five loss terms and every post-update parameter of one full update with
-    the reference's optimiser wiring.  No oracle in between."""
+    tests/golden/make_ref_golden.py): x_hat, the five loss terms and the discriminator's post-update parameters (the
+    lib/models.py:466 update) of one full update.  No oracle in between."""
     _assert_all(parity.reference_golden_update(hierarchy))
 
 
