@@ -328,11 +328,25 @@ tf.losses = types.SimpleNamespace(
         _weighted_mean((predictions - labels) ** 2, weights),
     huber_loss=_huber)
 
-# ---- summaries, sessions: nothing to do --------------------------------------------------------------------------------
+# ---- summaries, sessions ------------------------------------------------------------------------------------------------
+class _Null(object):
+    """Accepts any attribute access / call and does nothing (summary writers, protobuf summaries, savers)."""
+
+    def __getattr__(self, name):
+        return _Null()
+
+    def __call__(self, *a, **k):
+        return _Null()
+
+
+# The graph has already been executed when build_graph returns, so there is nothing for a session to run.  Tests that
+# want the reference's host loops (fit / predict: what they feed, how often they run) set SESSION_FACTORY to a class
+# whose instances record `run(fetches, feed_dict)` calls and answer with stand-in values.
+SESSION_FACTORY = None
 tf.summary = types.SimpleNamespace(scalar=lambda *a, **k: None, histogram=lambda *a, **k: None,
-                                   merge_all=lambda *a, **k: None, FileWriter=lambda *a, **k: None)
-tf.Summary = lambda *a, **k: None
-tf.Session = lambda *a, **k: None
+                                   merge_all=lambda *a, **k: "op_summary", FileWriter=lambda *a, **k: _Null())
+tf.Summary = lambda *a, **k: _Null()
+tf.Session = lambda *a, **k: SESSION_FACTORY(*a, **k) if SESSION_FACTORY is not None else None
 
 
 class _EMA(object):
@@ -422,7 +436,7 @@ def run_pending():
 
 tf.train = types.SimpleNamespace(
     exponential_decay=_exponential_decay, MomentumOptimizer=_Momentum, AdamOptimizer=_Adam,
-    ExponentialMovingAverage=_EMA, Saver=lambda *a, **k: None, latest_checkpoint=lambda *a, **k: None)
+    ExponentialMovingAverage=_EMA, Saver=lambda *a, **k: _Null(), latest_checkpoint=lambda *a, **k: None)
 tf.clip_by_global_norm = _clip_by_global_norm
 
 
