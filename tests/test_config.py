@@ -131,3 +131,44 @@ def test_layer_forms_of_the_shipped_config():
     assert f(512, 0, 512, 2, 862, 862, False, True, "aside", True, False, "enc/conv8",
              {"CAPE_MODES": "enc/conv8:dx=contract,enc/conv7:fwd=fused"}) == ("basis", "contract")
     assert f(512, 64, 256, 2, 862, 862, True, True, "gside", False, False, "dec/aff1", {"CAPE_FWD_MODE": "basis"})[0] == "fused"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG), reason="reference tree not present (GPU box)")
+def test_flag_inventory_is_the_references(monkeypatch):
+    """Every flag the reference's own parse_config declares (config_parser.py:11-63) -- name, type, default, choices --
+    against the table this package parses with.  The reference needs `configargparse` (not installed): a recording
+    stand-in captures its add_argument calls while its unmodified parse_config runs."""
+    import argparse
+    import importlib.util
+    import sys
+    import types
+    from cape_b200 import config_parser as ours
+    recorded = []
+
+    class ArgParser(object):
+        def __init__(self, *a, **k):
+            pass
+
+        def add_argument(self, flag, **kw):
+            recorded.append((flag.lstrip("-"), kw))
+
+        def parse_known_args(self, *a, **k):
+            return argparse.Namespace(**{n: kw.get("default") for n, kw in recorded}), []
+
+    stub = types.ModuleType("configargparse")
+    stub.ArgParser, stub.ArgumentDefaultsHelpFormatter, stub.DefaultConfigFileParser = ArgParser, object, object
+    monkeypatch.setitem(sys.modules, "configargparse", stub)
+    spec = importlib.util.spec_from_file_location("ref_config_parser", os.path.join(os.path.dirname(REF_CFG), "config_parser.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    args, args_dict = mod.parse_config()
+    assert recorded[0][0] == "config" and recorded[0][1]["is_config_file"] and recorded[0][1]["default"] == ours.DEFAULT_CONFIG
+    ref = [(n, kw.get("type", str), kw.get("default"), kw.get("choices")) for n, kw in recorded[1:]]
+    mine = [(n, t, d, ours._CHOICES.get(n)) for n, t, d, _ in ours._SPEC]
+    assert [r[0] for r in ref] == [m[0] for m in mine]                       # same flags, same order
+    for r, m in zip(ref, mine):
+        assert r == m, (r, m)
+    # and the defaults our parser hands out when neither a file nor a flag sets them
+    a, _ = ours.parse_config(["--config", os.devnull])
+    for n, kw in recorded[1:]:
+        assert getattr(a, n) == kw.get("default"), n
